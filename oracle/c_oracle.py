@@ -1,0 +1,257 @@
+"""ctypes wrapper over oracle/libflucoma_oracle.so (the CPU fp64 restatement of the reference path).
+
+TEST INFRASTRUCTURE ONLY: importable from tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs.  The product package (flucoma-core_b200/) must never import this module.
+Function-by-function reference citations live in flucoma_oracle.c.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+_i64 = C.c_int64
+_pd = C.POINTER(C.c_double)
+_pf = C.POINTER(C.c_float)
+_pi64 = C.POINTER(C.c_int64)
+PROGRESS_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int64)
+
+
+def build(force: bool = False, march: str = "x86-64-v3", out: str | None = None) -> str:
+    """Compile the oracle with the system gcc (never $CC: the image exports a wrapper without libgomp)."""
+    out = out or os.path.join(_HERE, "libflucoma_oracle.so")
+    src = os.path.join(_HERE, "flucoma_oracle.c")
+    if not force and os.path.exists(out) and os.path.getmtime(out) >= os.path.getmtime(src):
+        return out
+    base = ["/usr/bin/gcc", "-O3", f"-march={march}", "-fPIC", "-std=c11", "-fvisibility=hidden", "-shared", "-o", out, src, "-lm"]
+    try:
+        subprocess.run(base[:3] + ["-fopenmp"] + base[3:], check=True, capture_output=True)
+    except (subprocess.CalledProcessError, FileNotFoundError):
+        subprocess.run(base[:3] + ["-fopenmp-simd"] + base[3:], check=True, capture_output=True)
+    return out
+
+
+def lib(path: str | None = None):
+    global _LIB
+    if _LIB is not None and path is None:
+        return _LIB
+    p = path or os.path.join(_HERE, "libflucoma_oracle.so")
+    if not os.path.exists(p):
+        build(out=p)
+    L = C.CDLL(p)
+    L.fo_next_pow2.restype = _i64
+    L.fo_next_pow2.argtypes = [_i64]
+    L.fo_stft_num_frames.restype = _i64
+    L.fo_stft_num_frames.argtypes = [_i64, _i64, _i64]
+    L.fo_fft_params.argtypes = [_i64, _i64, _i64, _pi64, _pi64, _pi64, _pi64]
+    L.fo_hann.argtypes = [_i64, _pd]
+    L.fo_rfft.argtypes = [_pd, _i64, _i64, _pd]
+    L.fo_irfft_unnorm.argtypes = [_pd, _i64, _pd]
+    L.fo_stft.argtypes = [_pd, _i64, _i64, _i64, _i64, _pd]
+    L.fo_stft_frame.argtypes = [_pd, _i64, _i64, _pd]
+    L.fo_magnitude.argtypes = [_pd, _i64, _pd]
+    L.fo_istft.argtypes = [_pd, _i64, _i64, _i64, _i64, _pd, _i64]
+    L.fo_random_uniform.argtypes = [_i64, _i64, _pd]
+    L.fo_nmf_random_init.argtypes = [_i64, _i64, _i64, _i64, _pd, _pd]
+    L.fo_nmf_process.restype = C.c_int
+    L.fo_nmf_process.argtypes = [_pd, _i64, _i64, _i64, _i64, C.c_int, C.c_int, _i64, _pd, _pd, _pd, _pd, _pd,
+                                 C.c_int, C.c_void_p, C.c_void_p]
+    L.fo_nmf_process_frame.argtypes = [_pd, _pd, _i64, _i64, _i64, _i64, _pd, _pd]
+    L.fo_nmf_estimate.argtypes = [_pd, _pd, _i64, _i64, _i64, _i64, _pd]
+    L.fo_ratio_mask.argtypes = [_pd, _pd, _pd, _i64, _pd]
+    L.fo_bufnmf_channel.restype = C.c_int
+    L.fo_bufnmf_channel.argtypes = [_pf, _i64, _i64, _i64, _i64, _i64, _i64, _i64, C.c_int, _pf, C.c_int, _pf, _pf,
+                                    _pf, _pf, C.c_int, _pd, _pd, _pd]
+    L.fo_bufnmf_batch.restype = C.c_int
+    L.fo_bufnmf_batch.argtypes = [_pf, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _pi64, _pf, _pf, _pf, C.c_int,
+                                  C.c_int]
+    L.fo_nmfmatch_frames.argtypes = [_pd, _i64, _pd, _i64, _i64, _i64, _i64, _pd, C.c_int]
+    L.fo_stream_frames_mag.argtypes = [_pd, _i64, _i64, _i64, _i64, _i64, _pd, _pd]
+    L.fo_num_threads.restype = C.c_int
+    if path is None:
+        _LIB = L
+    return L
+
+
+def _d(a):
+    return None if a is None else a.ctypes.data_as(_pd)
+
+
+def _f(a):
+    return None if a is None else a.ctypes.data_as(_pf)
+
+
+def _c64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def fft_params(win, hop=-1, fft=-1):
+    o = [C.c_int64() for _ in range(4)]
+    lib().fo_fft_params(win, hop, fft, *[C.byref(x) for x in o])
+    return tuple(int(x.value) for x in o)  # win, hop, fft, bins
+
+
+def num_frames(n, win, hop):
+    return int(lib().fo_stft_num_frames(n, win, hop))
+
+
+def hann(size):
+    w = np.empty(size, np.float64)
+    lib().fo_hann(size, _d(w))
+    return w
+
+
+def rfft(x, fft):
+    x = _c64(x)
+    out = np.empty(2 * (fft // 2 + 1), np.float64)
+    lib().fo_rfft(_d(x), x.size, fft, _d(out))
+    return out.view(np.complex128)
+
+
+def irfft_unnorm(X, fft):
+    X = np.ascontiguousarray(X, dtype=np.complex128)
+    y = np.empty(fft, np.float64)
+    lib().fo_irfft_unnorm(_d(X.view(np.float64)), fft, _d(y))
+    return y
+
+
+def stft(audio, win, fft, hop):
+    a = _c64(audio)
+    F = num_frames(a.size, win, hop)
+    B = fft // 2 + 1
+    out = np.empty((F, B), np.complex128)
+    lib().fo_stft(_d(a), a.size, win, fft, hop, _d(out.view(np.float64)))
+    return out
+
+
+def stft_frame(frame, fft):
+    a = _c64(frame)
+    out = np.empty(fft // 2 + 1, np.complex128)
+    lib().fo_stft_frame(_d(a), a.size, fft, _d(out.view(np.float64)))
+    return out
+
+
+def magnitude(spec):
+    s = np.ascontiguousarray(spec, dtype=np.complex128)
+    m = np.empty(s.shape, np.float64)
+    lib().fo_magnitude(_d(s.view(np.float64)), s.size, _d(m))
+    return m
+
+
+def istft(spec, win, fft, hop, n_out):
+    s = np.ascontiguousarray(spec, dtype=np.complex128)
+    y = np.empty(n_out, np.float64)
+    lib().fo_istft(_d(s.view(np.float64)), s.shape[0], win, fft, hop, _d(y), n_out)
+    return y
+
+
+def random_uniform(seed, count):
+    o = np.empty(count, np.float64)
+    lib().fo_random_uniform(seed, count, _d(o))
+    return o
+
+
+def nmf_random_init(seed, bins, rank, frames):
+    W = np.empty((rank, bins), np.float64)
+    H = np.empty((frames, rank), np.float64)
+    lib().fo_nmf_random_init(seed, bins, rank, frames, _d(W), _d(H))
+    return W, H
+
+
+def nmf_process(X, rank, n_iter, update_w=True, update_h=True, seed=-1, W0=None, H0=None, faithful=False,
+                progress=None):
+    """NMF::process.  X[F][B] -> (W[K][B], H[F][K], V[F][B], cancelled)."""
+    X = _c64(X)
+    F, B = X.shape
+    W0 = None if W0 is None else _c64(W0)
+    H0 = None if H0 is None else _c64(H0)
+    if W0 is not None:
+        assert W0.shape == (rank, B)
+    if H0 is not None:
+        assert H0.shape == (F, rank)
+    W = np.empty((rank, B)); H = np.empty((F, rank)); V = np.empty((F, B))
+    cb = PROGRESS_CB(lambda user, it: int(bool(progress(it)))) if progress else None
+    r = lib().fo_nmf_process(_d(X), F, B, rank, n_iter, int(update_w), int(update_h), seed, _d(W0), _d(H0), _d(W),
+                             _d(H), _d(V), int(faithful), C.cast(cb, C.c_void_p) if cb else None, None)
+    return W, H, V, bool(r)
+
+
+def nmf_process_frame(x, W0, n_iter, seed, want_v=True):
+    """NMF::processFrame.  Returns (h[K], v[B] or None, mutated W[K][B])."""
+    x = _c64(x)
+    W = _c64(W0).copy()
+    K, B = W.shape
+    h = np.empty(K); v = np.empty(B) if want_v else None
+    lib().fo_nmf_process_frame(_d(x), _d(W), B, K, n_iter, seed, _d(h), _d(v))
+    return h, v, W
+
+
+def nmf_estimate(W, H, idx):
+    W = _c64(W); H = _c64(H)
+    K, B = W.shape; F = H.shape[0]
+    E = np.empty((F, B))
+    lib().fo_nmf_estimate(_d(W), _d(H), F, B, K, idx, _d(E))
+    return E
+
+
+def ratio_mask(mixture, target, denominator):
+    m = np.ascontiguousarray(mixture, dtype=np.complex128)
+    t = _c64(target); d = _c64(denominator)
+    out = np.empty(m.shape, np.complex128)
+    lib().fo_ratio_mask(_d(m.view(np.float64)), _d(t), _d(d), m.size, _d(out.view(np.float64)))
+    return out
+
+
+def bufnmf_channel(audio, win, fft, hop, rank, iters, seed, bases_mode=0, bases_in=None, acts_mode=0, acts_in=None,
+                   resynth=False, faithful=False, debug=False):
+    """One BufNMF channel.  Returns dict(bases[K][B] f32, acts[F][K] f32, resynth[K][n] f32|None, W,H,V f64 if debug)."""
+    a = np.ascontiguousarray(audio, dtype=np.float32)
+    n = a.size; B = fft // 2 + 1; F = num_frames(n, win, hop)
+    bi = None if bases_in is None else np.ascontiguousarray(bases_in, dtype=np.float32)
+    ai = None if acts_in is None else np.ascontiguousarray(acts_in, dtype=np.float32)
+    bases = np.zeros((rank, B), np.float32); acts = np.zeros((F, rank), np.float32)
+    rs = np.zeros((rank, n), np.float32) if resynth else None
+    dW = np.empty((rank, B)) if debug else None
+    dH = np.empty((F, rank)) if debug else None
+    dV = np.empty((F, B)) if debug else None
+    lib().fo_bufnmf_channel(_f(a), n, win, fft, hop, rank, iters, seed, bases_mode, _f(bi), acts_mode, _f(ai),
+                            _f(bases), _f(acts), _f(rs), int(faithful), _d(dW), _d(dH), _d(dV))
+    return dict(bases=bases, acts=acts, resynth=rs, W=dW, H=dH, V=dV)
+
+
+def bufnmf_batch(audio, win, fft, hop, rank, iters, seeds, resynth=False, faithful=True, threads=0, lib_path=None):
+    a = np.ascontiguousarray(audio, dtype=np.float32)
+    batch, n = a.shape
+    B = fft // 2 + 1; F = num_frames(n, win, hop)
+    seeds = np.ascontiguousarray(seeds, dtype=np.int64)
+    bases = np.zeros((batch, rank, B), np.float32); acts = np.zeros((batch, F, rank), np.float32)
+    rs = np.zeros((batch, rank, n), np.float32) if resynth else None
+    lib(lib_path).fo_bufnmf_batch(_f(a), batch, n, win, fft, hop, rank, iters, seeds.ctypes.data_as(_pi64), _f(bases),
+                                  _f(acts), _f(rs), int(faithful), threads)
+    return bases, acts, rs
+
+
+def nmfmatch_frames(mags, W, n_iter, seed, threads=0):
+    m = _c64(mags); W = _c64(W)
+    K, B = W.shape
+    acts = np.empty((m.shape[0], K))
+    lib().fo_nmfmatch_frames(_d(m), m.shape[0], _d(W), B, K, n_iter, seed, _d(acts), threads)
+    return acts
+
+
+def stream_frames_mag(audio, win, fft, hop, nframes, want_spec=False):
+    a = _c64(audio)
+    B = fft // 2 + 1
+    mags = np.empty((nframes, B))
+    spec = np.empty((nframes, B), np.complex128) if want_spec else None
+    lib().fo_stream_frames_mag(_d(a), a.size, win, fft, hop, nframes, _d(mags),
+                               _d(spec.view(np.float64)) if want_spec else None)
+    return (mags, spec) if want_spec else mags
+
+
+def num_threads():
+    return int(lib().fo_num_threads())

@@ -1,0 +1,687 @@
+/*
+ * flucoma_oracle.c -- CPU fp64 restatement of flucoma-core's STFT -> |X| -> NMF -> mask -> ISTFT path.
+ *
+ * THIS IS TEST INFRASTRUCTURE, NOT PRODUCT CODE.  Only tests/, __graft_entry__.smoke() and
+ * bench.py's cpu_baseline / --impl reference legs may load it.  The product path
+ * (flucoma-core_b200/csrc + include/flucoma_b200.h) never links, loads or calls anything in oracle/.
+ *
+ * PARITY STATUS: "parity unpinned".  The reference cannot be compiled in this image (its arithmetic lives in
+ * Eigen 3.4.0 and HISSTools_Library@f3292ad, fetched by CMake FetchContent, CMakeLists.txt:54-71; neither is on
+ * disk) and the reference's own tests hold no numerical golden vector for this path -- only seed repeatability
+ * (tests/algorithms/public/TestNMF.cpp:11-73, tests/algorithms/util/TestEigenRandom.cpp:92-114) and the Hann
+ * overlap-add identity (tests/clients/common/TestBufferedProcess.cpp:20-70).  Those properties are replicated in
+ * tests/test_oracle.py; everything numerical is additionally cross-checked against an independent numpy/pocketfft
+ * restatement (oracle/np_oracle.py) and analytic known-answer vectors.
+ *
+ * Every function cites the reference lines it follows (paths relative to /root/reference/include/flucoma).
+ * All arithmetic is IEEE fp64, single-threaded per buffer, like the reference.  Layouts are the reference's
+ * FluidTensor row-major layouts: X[F][B], W[K][B], H[F][K], V[F][B], spectrum [F][B] interleaved (re,im).
+ *
+ * Build: see oracle/Makefile  (gcc -O3 -march=x86-64-v3 -fopenmp -shared -fPIC).
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <float.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define FO_EPS DBL_EPSILON /* algorithms/util/AlgorithmUtils.hpp:19 */
+#define FO_EXPORT __attribute__((visibility("default")))
+
+/* ------------------------------------------------------------------------------------------------
+ * Size rules.  clients/common/ParameterTypes.hpp:295-313 (FFTParams) and clients/nrt/NMFClient.hpp:111-113
+ * ---------------------------------------------------------------------------------------------- */
+FO_EXPORT int64_t fo_next_pow2(int64_t x)
+{ /* ParameterTypes.hpp:323-335, up=true */
+  if (x <= 0) return 0;
+  uint32_t v = (uint32_t) x;
+  --v;
+  v |= v >> 1; v |= v >> 2; v |= v >> 4; v |= v >> 8; v |= v >> 16;
+  return (int64_t) (v + 1);
+}
+
+FO_EXPORT void fo_fft_params(int64_t win, int64_t hop, int64_t fft, int64_t* out_win, int64_t* out_hop,
+                             int64_t* out_fft, int64_t* out_bins)
+{
+  int64_t f = fft < 0 ? fo_next_pow2(win) : fft; /* :295-300 */
+  int64_t h = hop > 0 ? hop : (win >> 1);       /* :306-309 */
+  *out_win = win; *out_hop = h; *out_fft = f; *out_bins = (f >> 1) + 1; /* :312 */
+}
+
+/* nWindows of the BufNMF client, NMFClient.hpp:111-113; equals STFT::process's own count STFT.hpp:94-99 */
+FO_EXPORT int64_t fo_stft_num_frames(int64_t n_samples, int64_t win, int64_t hop)
+{
+  int64_t padded = n_samples + win + hop;
+  return (padded - win) / hop;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Hann window.  algorithms/public/WindowFuncs.hpp:41-45
+ * ---------------------------------------------------------------------------------------------- */
+FO_EXPORT void fo_hann(int64_t size, double* out)
+{
+  const double pi = 3.14159265358979323846;
+  for (int64_t i = 0; i < size; i++) out[i] = 0.5 - 0.5 * cos((pi * 2 * (double) i) / (double) size);
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * FFT conventions.  algorithms/util/FFT.hpp:92-108 (forward: true unnormalised DFT of the zero-padded input,
+ * bins 0..fft/2, Im X[0] = Im X[fft/2] = 0) and :149-163 (inverse: Im of DC/Nyquist discarded, result = fft * x).
+ * HISSTools is absent; this is a plain iterative radix-2 complex FFT with directly evaluated twiddles.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct { int64_t n; double* cs; double* sn; int64_t* rev; } fo_fft_plan;
+
+static fo_fft_plan* fo_fft_plan_new(int64_t n)
+{
+  fo_fft_plan* p = (fo_fft_plan*) malloc(sizeof(fo_fft_plan));
+  p->n = n;
+  p->cs = (double*) malloc(sizeof(double) * (size_t) (n / 2 + 1));
+  p->sn = (double*) malloc(sizeof(double) * (size_t) (n / 2 + 1));
+  p->rev = (int64_t*) malloc(sizeof(int64_t) * (size_t) n);
+  const double pi = 3.14159265358979323846;
+  for (int64_t k = 0; k < n / 2 + 1; k++) {
+    p->cs[k] = cos(2 * pi * (double) k / (double) n);
+    p->sn[k] = sin(2 * pi * (double) k / (double) n);
+  }
+  int bits = 0;
+  while (((int64_t) 1 << bits) < n) bits++;
+  for (int64_t i = 0; i < n; i++) {
+    int64_t r = 0;
+    for (int b = 0; b < bits; b++) if (i & ((int64_t) 1 << b)) r |= (int64_t) 1 << (bits - 1 - b);
+    p->rev[i] = r;
+  }
+  return p;
+}
+
+static void fo_fft_plan_free(fo_fft_plan* p)
+{
+  if (!p) return;
+  free(p->cs); free(p->sn); free(p->rev); free(p);
+}
+
+/* in-place complex FFT, sign = -1 forward, +1 inverse (unnormalised) */
+static void fo_cfft(const fo_fft_plan* p, double* re, double* im, int sign)
+{
+  int64_t n = p->n;
+  for (int64_t i = 0; i < n; i++) {
+    int64_t j = p->rev[i];
+    if (j > i) {
+      double t = re[i]; re[i] = re[j]; re[j] = t;
+      t = im[i]; im[i] = im[j]; im[j] = t;
+    }
+  }
+  for (int64_t len = 2; len <= n; len <<= 1) {
+    int64_t half = len >> 1, step = n / len;
+    for (int64_t s = 0; s < n; s += len) {
+      for (int64_t k = 0; k < half; k++) {
+        double wr = p->cs[k * step], wi = sign * p->sn[k * step];
+        double xr = re[s + k + half], xi = im[s + k + half];
+        double tr = xr * wr - xi * wi, ti = xr * wi + xi * wr;
+        re[s + k + half] = re[s + k] - tr; im[s + k + half] = im[s + k] - ti;
+        re[s + k] += tr; im[s + k] += ti;
+      }
+    }
+  }
+}
+
+/* FFT.hpp:92-108. x has n_in <= fft samples (zero-padded). out = interleaved (re,im) [fft/2+1]. */
+static void fo_rfft_plan(const fo_fft_plan* p, const double* x, int64_t n_in, double* out, double* re, double* im)
+{
+  int64_t n = p->n;
+  for (int64_t i = 0; i < n; i++) { re[i] = i < n_in ? x[i] : 0.0; im[i] = 0.0; }
+  fo_cfft(p, re, im, -1);
+  for (int64_t k = 0; k <= n / 2; k++) { out[2 * k] = re[k]; out[2 * k + 1] = im[k]; }
+  out[1] = 0.0;         /* FFT.hpp:101 */
+  out[2 * (n / 2) + 1] = 0.0; /* FFT.hpp:100 */
+}
+
+/* FFT.hpp:149-163: y[n] = sum over the Hermitian-extended spectrum, = fft * x; Im(DC), Im(Nyquist) ignored */
+static void fo_irfft_plan(const fo_fft_plan* p, const double* in, double* y, double* re, double* im)
+{
+  int64_t n = p->n;
+  re[0] = in[0]; im[0] = 0.0;
+  re[n / 2] = in[2 * (n / 2)]; im[n / 2] = 0.0;
+  for (int64_t k = 1; k < n / 2; k++) {
+    re[k] = in[2 * k]; im[k] = in[2 * k + 1];
+    re[n - k] = in[2 * k]; im[n - k] = -in[2 * k + 1];
+  }
+  fo_cfft(p, re, im, +1);
+  for (int64_t i = 0; i < n; i++) y[i] = re[i];
+}
+
+FO_EXPORT void fo_rfft(const double* x, int64_t n_in, int64_t fft, double* out)
+{
+  fo_fft_plan* p = fo_fft_plan_new(fft);
+  double* re = (double*) malloc(sizeof(double) * (size_t) fft * 2);
+  fo_rfft_plan(p, x, n_in, out, re, re + fft);
+  free(re); fo_fft_plan_free(p);
+}
+
+FO_EXPORT void fo_irfft_unnorm(const double* in, int64_t fft, double* y)
+{
+  fo_fft_plan* p = fo_fft_plan_new(fft);
+  double* re = (double*) malloc(sizeof(double) * (size_t) fft * 2);
+  fo_irfft_plan(p, in, y, re, re + fft);
+  free(re); fo_fft_plan_free(p);
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * STFT::process  algorithms/public/STFT.hpp:90-108  (+ ctor :36-47: Hann table of `win`)
+ * spec: interleaved complex [F][B], F = fo_stft_num_frames(n, win, hop), B = fft/2+1
+ * ---------------------------------------------------------------------------------------------- */
+FO_EXPORT void fo_stft(const double* audio, int64_t n, int64_t win, int64_t fft, int64_t hop, double* spec)
+{
+  int64_t half = win / 2;                           /* :92 */
+  int64_t plen = n + win + hop;                     /* :94 */
+  int64_t nframes = (plen - win) / hop;             /* :98-99 */
+  int64_t bins = fft / 2 + 1;
+  double* padded = (double*) calloc((size_t) plen, sizeof(double)); /* :95 */
+  memcpy(padded + half, audio, sizeof(double) * (size_t) n);        /* :96-97 */
+  double* w = (double*) malloc(sizeof(double) * (size_t) win);
+  fo_hann(win, w);
+  fo_fft_plan* p = fo_fft_plan_new(fft);
+  double* scratch = (double*) malloc(sizeof(double) * (size_t) (2 * fft + win));
+  double* frame = scratch + 2 * fft;
+  for (int64_t i = 0; i < nframes; i++) {           /* :102-106 */
+    for (int64_t j = 0; j < win; j++) frame[j] = padded[i * hop + j] * w[j];
+    fo_rfft_plan(p, frame, win, spec + 2 * i * bins, scratch, scratch + fft);
+  }
+  free(scratch); fo_fft_plan_free(p); free(w); free(padded);
+}
+
+/* STFT::processFrame STFT.hpp:110-118: one already-cut frame of `win` samples -> B complex bins */
+FO_EXPORT void fo_stft_frame(const double* frame_in, int64_t win, int64_t fft, double* out)
+{
+  double* w = (double*) malloc(sizeof(double) * (size_t) win * 2);
+  fo_hann(win, w);
+  for (int64_t j = 0; j < win; j++) w[win + j] = frame_in[j] * w[j];
+  fo_rfft(w + win, win, fft, out);
+  free(w);
+}
+
+/* STFT::magnitude STFT.hpp:61-73 */
+FO_EXPORT void fo_magnitude(const double* spec, int64_t count, double* mag)
+{
+  for (int64_t i = 0; i < count; i++) mag[i] = hypot(spec[2 * i], spec[2 * i + 1]);
+}
+
+/* ISTFT::process STFT.hpp:178-199 */
+FO_EXPORT void fo_istft(const double* spec, int64_t nframes, int64_t win, int64_t fft, int64_t hop, double* audio,
+                        int64_t n_out)
+{
+  int64_t half = win / 2;                                         /* :181 */
+  int64_t bins = fft / 2 + 1;
+  int64_t osz = win + (nframes - 1) * hop + win + hop;            /* :183-184 */
+  if (osz < half + n_out) osz = half + n_out; /* guard only; the reference would read out of bounds here */
+  double scale = 1.0 / (double) fft;                              /* :157 */
+  double* out = (double*) calloc((size_t) osz, sizeof(double));
+  double* nrm = (double*) calloc((size_t) osz, sizeof(double));
+  double* w = (double*) malloc(sizeof(double) * (size_t) win);
+  fo_hann(win, w);
+  fo_fft_plan* p = fo_fft_plan_new(fft);
+  double* scratch = (double*) malloc(sizeof(double) * (size_t) fft * 3);
+  double* y = scratch + 2 * fft;
+  for (int64_t i = 0; i < nframes; i++) {                         /* :189-195 */
+    fo_irfft_plan(p, spec + 2 * i * bins, y, scratch, scratch + fft);
+    for (int64_t j = 0; j < win; j++) {
+      out[i * hop + j] += y[j] * scale * w[j];
+      nrm[i * hop + j] += w[j] * w[j];
+    }
+  }
+  for (int64_t i = 0; i < n_out; i++) {                           /* :196-198 */
+    double d = nrm[half + i] > FO_EPS ? nrm[half + i] : FO_EPS;
+    audio[i] = out[half + i] / d;
+  }
+  free(scratch); fo_fft_plan_free(p); free(w); free(nrm); free(out);
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * EigenRandom.  algorithms/util/EigenRandom.hpp:73-110 on libstdc++:
+ *   std::mt19937_64 g{seed}; std::uniform_real_distribution<double>{0,1}(g) == generate_canonical<double,53>
+ *   == double(raw u64) / 2^64 (one draw; a result of exactly 1.0 is replaced by nextafter(1,0)).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct { uint64_t mt[312]; int idx; } fo_mt64;
+
+static void fo_mt64_seed(fo_mt64* s, uint64_t seed)
+{
+  s->mt[0] = seed;
+  for (int i = 1; i < 312; i++) s->mt[i] = 6364136223846793005ULL * (s->mt[i - 1] ^ (s->mt[i - 1] >> 62)) + (uint64_t) i;
+  s->idx = 312;
+}
+
+static uint64_t fo_mt64_next(fo_mt64* s)
+{
+  if (s->idx >= 312) {
+    const uint64_t UM = 0xFFFFFFFF80000000ULL, LM = 0x7FFFFFFFULL, MA = 0xB5026F5AA96619E9ULL;
+    for (int i = 0; i < 312; i++) {
+      uint64_t x = (s->mt[i] & UM) | (s->mt[(i + 1) % 312] & LM);
+      s->mt[i] = s->mt[(i + 156) % 312] ^ (x >> 1) ^ ((x & 1ULL) ? MA : 0ULL);
+    }
+    s->idx = 0;
+  }
+  uint64_t x = s->mt[s->idx++];
+  x ^= (x >> 29) & 0x5555555555555555ULL;
+  x ^= (x << 17) & 0x71D67FFFEDA60000ULL;
+  x ^= (x << 37) & 0xFFF7EEE000000000ULL;
+  x ^= (x >> 43);
+  return x;
+}
+
+static double fo_mt64_uniform(fo_mt64* s)
+{
+  double r = (double) fo_mt64_next(s) / 18446744073709551616.0;
+  if (r >= 1.0) r = nextafter(1.0, 0.0);
+  return r;
+}
+
+/* raw stream: out[i] = i-th draw of uniform[0,1) from mt19937_64(seed) */
+FO_EXPORT void fo_random_uniform(int64_t seed, int64_t count, double* out)
+{
+  fo_mt64 g; fo_mt64_seed(&g, (uint64_t) seed);
+  for (int64_t i = 0; i < count; i++) out[i] = fo_mt64_uniform(&g);
+}
+
+/* NMF.hpp:104-105 / :116-117: Eigen NullaryExpr fills a column-major MatrixXd in storage order, and W and H
+ * each restart from state(seed).  Column-major (B x K) W  == our W[K][B] memory; column-major (K x F) H == H[F][K]. */
+FO_EXPORT void fo_nmf_random_init(int64_t seed, int64_t bins, int64_t rank, int64_t frames, double* W, double* H)
+{
+  if (W) fo_random_uniform(seed, bins * rank, W);
+  if (H) fo_random_uniform(seed, rank * frames, H);
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * NMF::multiplicativeUpdates.  algorithms/public/NMF.hpp:144-183
+ * Memory layouts (== Eigen column-major B x K, K x F, B x F):  W[K][B], H[F][K], V[F][B].
+ * faithful != 0 executes the reference's redundant work too (ones-matrix GEMMs :160,:169 and the dead R=WH :173)
+ * so that CPU timings represent what the reference really runs.
+ * progress: optional callback(iteration 1..n) -> nonzero to continue (NMF.hpp:175-176).
+ * returns 1 if cancelled (V is then left untouched == X, because :182 is skipped), else 0.
+ * ---------------------------------------------------------------------------------------------- */
+typedef int (*fo_progress_cb)(void* user, int64_t iter);
+
+static void fo_wh(const double* W, const double* H, int64_t B, int64_t F, int64_t K, double* P, int clamp)
+{ /* P[f][b] = sum_k H[f][k] W[k][b]; k blocked by 4 so the row of P stays in registers/L1 between updates */
+  for (int64_t f = 0; f < F; f++) {
+    double* p = P + f * B;
+    for (int64_t b = 0; b < B; b++) p[b] = 0.0;
+    int64_t k = 0;
+    for (; k + 4 <= K; k += 4) {
+      double h0 = H[f * K + k], h1 = H[f * K + k + 1], h2 = H[f * K + k + 2], h3 = H[f * K + k + 3];
+      const double *w0 = W + k * B, *w1 = w0 + B, *w2 = w1 + B, *w3 = w2 + B;
+#pragma omp simd
+      for (int64_t b = 0; b < B; b++) p[b] += h0 * w0[b] + h1 * w1[b] + h2 * w2[b] + h3 * w3[b];
+    }
+    for (; k < K; k++) {
+      double h = H[f * K + k];
+      const double* w = W + k * B;
+#pragma omp simd
+      for (int64_t b = 0; b < B; b++) p[b] += h * w[b];
+    }
+    if (clamp) {
+#pragma omp simd
+      for (int64_t b = 0; b < B; b++) p[b] = p[b] > FO_EPS ? p[b] : FO_EPS;
+    }
+  }
+}
+
+/* num[k][b] = sum_f R[f][b] * H[f][k]   (R * H^T) */
+static void fo_r_ht(const double* R, const double* H, int64_t B, int64_t F, int64_t K, double* num)
+{
+  memset(num, 0, sizeof(double) * (size_t) (K * B));
+  for (int64_t f = 0; f < F; f++) {
+    const double* r = R + f * B;
+    int64_t k = 0;
+    for (; k + 4 <= K; k += 4) {
+      double h0 = H[f * K + k], h1 = H[f * K + k + 1], h2 = H[f * K + k + 2], h3 = H[f * K + k + 3];
+      double *o0 = num + k * B, *o1 = o0 + B, *o2 = o1 + B, *o3 = o2 + B;
+#pragma omp simd
+      for (int64_t b = 0; b < B; b++) {
+        double rb = r[b];
+        o0[b] += h0 * rb; o1[b] += h1 * rb; o2[b] += h2 * rb; o3[b] += h3 * rb;
+      }
+    }
+    for (; k < K; k++) {
+      double h = H[f * K + k];
+      double* o = num + k * B;
+#pragma omp simd
+      for (int64_t b = 0; b < B; b++) o[b] += h * r[b];
+    }
+  }
+}
+
+/* num[f][k] = sum_b W[k][b] * R[f][b]   (W^T * R) */
+static void fo_wt_r(const double* W, const double* R, int64_t B, int64_t F, int64_t K, double* num)
+{
+  for (int64_t f = 0; f < F; f++) {
+    const double* r = R + f * B;
+    int64_t k = 0;
+    for (; k + 4 <= K; k += 4) {
+      const double *w0 = W + k * B, *w1 = w0 + B, *w2 = w1 + B, *w3 = w2 + B;
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma omp simd reduction(+ : s0, s1, s2, s3)
+      for (int64_t b = 0; b < B; b++) {
+        double rb = r[b];
+        s0 += w0[b] * rb; s1 += w1[b] * rb; s2 += w2[b] * rb; s3 += w3[b] * rb;
+      }
+      num[f * K + k] = s0; num[f * K + k + 1] = s1; num[f * K + k + 2] = s2; num[f * K + k + 3] = s3;
+    }
+    for (; k < K; k++) {
+      const double* w = W + k * B;
+      double s = 0.0;
+#pragma omp simd reduction(+ : s)
+      for (int64_t b = 0; b < B; b++) s += w[b] * r[b];
+      num[f * K + k] = s;
+    }
+  }
+}
+
+static void fo_normalize_w_rows(double* W, int64_t B, int64_t K)
+{ /* W.colwise().normalize() on B x K == each memory row W[k][:] / ||.||2   (NMF.hpp:152,162) */
+  for (int64_t k = 0; k < K; k++) {
+    double s = 0.0;
+    for (int64_t b = 0; b < B; b++) s += W[k * B + b] * W[k * B + b];
+    double nrm = sqrt(s);
+    /* Eigen's normalize() divides only when the squared norm is > 0 */
+    if (s > 0.0) for (int64_t b = 0; b < B; b++) W[k * B + b] /= nrm;
+  }
+}
+
+static int fo_mu(double* V, double* W, double* H, int64_t B, int64_t F, int64_t K, int64_t n_iter, int update_w,
+                 int update_h, int faithful, fo_progress_cb cb, void* user)
+{
+  double* P = (double*) malloc(sizeof(double) * (size_t) (F * B));
+  double* R = (double*) malloc(sizeof(double) * (size_t) (F * B));
+  double* ones = NULL;
+  double* wnum = (double*) malloc(sizeof(double) * (size_t) (K * B));
+  double* wden = (double*) malloc(sizeof(double) * (size_t) (K * B));
+  double* hnum = (double*) malloc(sizeof(double) * (size_t) (F * K));
+  double* hden = (double*) malloc(sizeof(double) * (size_t) (F * K));
+  if (faithful) {
+    ones = (double*) malloc(sizeof(double) * (size_t) (F * B)); /* :149 */
+    for (int64_t i = 0; i < F * B; i++) ones[i] = 1.0;
+  }
+  for (int64_t i = 0; i < F * K; i++) H[i] = H[i] > FO_EPS ? H[i] : FO_EPS; /* :150 */
+  for (int64_t i = 0; i < K * B; i++) W[i] = W[i] > FO_EPS ? W[i] : FO_EPS; /* :151 */
+  fo_normalize_w_rows(W, B, K);                                             /* :152 */
+  for (int64_t k = 0; k < K; k++) { /* :153 H.rowwise().normalize(): row k of (K x F) == column k of H[F][K] */
+    double s = 0.0;
+    for (int64_t f = 0; f < F; f++) s += H[f * K + k] * H[f * K + k];
+    double nrm = sqrt(s);
+    if (s > 0.0) for (int64_t f = 0; f < F; f++) H[f * K + k] /= nrm;
+  }
+  int cancelled = 0;
+  for (int64_t it = 0; it < n_iter; ++it) {
+    if (update_w) {
+      fo_wh(W, H, B, F, K, P, 1);                                           /* :158 */
+      for (int64_t i = 0; i < F * B; i++) R[i] = V[i] / P[i];
+      fo_r_ht(R, H, B, F, K, wnum);                                         /* :159 */
+      if (faithful) {
+        fo_r_ht(ones, H, B, F, K, wden);                                    /* :160 */
+      } else {
+        for (int64_t k = 0; k < K; k++) {
+          double s = 0.0;
+          for (int64_t f = 0; f < F; f++) s += H[f * K + k];
+          for (int64_t b = 0; b < B; b++) wden[k * B + b] = s;
+        }
+      }
+      double wmax = -INFINITY;
+      for (int64_t i = 0; i < K * B; i++) {                                 /* :161 */
+        double d = wden[i] > FO_EPS ? wden[i] : FO_EPS;
+        W[i] = W[i] * wnum[i] / d;
+        if (W[i] > wmax) wmax = W[i];
+      }
+      if (wmax > FO_EPS) fo_normalize_w_rows(W, B, K);                      /* :162 */
+    }
+    fo_wh(W, H, B, F, K, P, 1);                                             /* :165 */
+    if (update_h) {
+      for (int64_t i = 0; i < F * B; i++) R[i] = V[i] / P[i];
+      fo_wt_r(W, R, B, F, K, hnum);                                         /* :168 */
+      if (faithful) {
+        fo_wt_r(W, ones, B, F, K, hden);                                    /* :169 */
+      } else {
+        for (int64_t k = 0; k < K; k++) {
+          double s = 0.0;
+          for (int64_t b = 0; b < B; b++) s += W[k * B + b];
+          for (int64_t f = 0; f < F; f++) hden[f * K + k] = s;
+        }
+      }
+      for (int64_t i = 0; i < F * K; i++) {                                 /* :170 */
+        double d = hden[i] > FO_EPS ? hden[i] : FO_EPS;
+        H[i] = H[i] * hnum[i] / d;
+      }
+    }
+    if (faithful) fo_wh(W, H, B, F, K, P, 1);                               /* :173-174 dead R */
+    if (cb && !cb(user, it + 1)) { cancelled = 1; break; }                  /* :175-176 */
+  }
+  if (!cancelled) fo_wh(W, H, B, F, K, V, 0);                               /* :182 */
+  free(P); free(R); free(ones); free(wnum); free(wden); free(hnum); free(hden);
+  return cancelled;
+}
+
+/* NMF::process  NMF.hpp:91-134.
+ * X[F][B] in; W0[K][B] / H0[F][K] optional seeds (NULL => random from `seed`, each restarting the stream);
+ * outputs W1[K][B], H1[F][K], V1[F][B] (any may be NULL).  Returns 1 when a progress callback cancelled. */
+FO_EXPORT int fo_nmf_process(const double* X, int64_t F, int64_t B, int64_t K, int64_t n_iter, int update_w,
+                             int update_h, int64_t seed, const double* W0, const double* H0, double* W1, double* H1,
+                             double* V1, int faithful, fo_progress_cb cb, void* user)
+{
+  double* V = (double*) malloc(sizeof(double) * (size_t) (F * B));
+  double* W = (double*) malloc(sizeof(double) * (size_t) (K * B));
+  double* H = (double*) malloc(sizeof(double) * (size_t) (F * K));
+  memcpy(V, X, sizeof(double) * (size_t) (F * B));                          /* :125 */
+  if (W0) memcpy(W, W0, sizeof(double) * (size_t) (K * B));                 /* :111 */
+  else fo_nmf_random_init(seed, B, K, F, W, NULL);                          /* :104-105 */
+  if (H0) memcpy(H, H0, sizeof(double) * (size_t) (F * K));                 /* :123 */
+  else fo_nmf_random_init(seed, B, K, F, NULL, H);                          /* :116-117 */
+  int cancelled = fo_mu(V, W, H, B, F, K, n_iter, update_w, update_h, faithful, cb, user); /* :126 */
+  if (V1) memcpy(V1, V, sizeof(double) * (size_t) (F * B));                 /* :131 */
+  if (W1) memcpy(W1, W, sizeof(double) * (size_t) (K * B));                 /* :132 */
+  if (H1) memcpy(H1, H, sizeof(double) * (size_t) (F * K));                 /* :133 */
+  free(V); free(W); free(H);
+  return cancelled;
+}
+
+/* NMF::processFrame  NMF.hpp:45-89.  W0[K][B] IS MUTATED (eps clamp :58, row normalise :63-64), as in the reference.
+ * out[K] and v[B] may be NULL (:85,:88). */
+FO_EXPORT void fo_nmf_process_frame(const double* x, double* W0, int64_t B, int64_t K, int64_t n_iter, int64_t seed,
+                                    double* out, double* v)
+{
+  double* h = (double*) malloc(sizeof(double) * (size_t) (K * 3));
+  double* hnum = h + K; double* hden = h + 2 * K;
+  double* v0 = (double*) malloc(sizeof(double) * (size_t) (B * 3));
+  double* v1 = v0 + B; double* r = v0 + 2 * B;
+  fo_random_uniform(seed, K, h);                                            /* :55 */
+  for (int64_t i = 0; i < K * B; i++) W0[i] = W0[i] > FO_EPS ? W0[i] : FO_EPS; /* :58 */
+  for (int64_t k = 0; k < K; k++) h[k] = h[k] > FO_EPS ? h[k] : FO_EPS;     /* :59 */
+  for (int64_t b = 0; b < B; b++) v0[b] = x[b] > FO_EPS ? x[b] : FO_EPS;    /* :60 */
+  for (int64_t k = 0; k < K; k++) {                                         /* :63-64 */
+    double s = 0.0;
+    for (int64_t b = 0; b < B; b++) s += W0[k * B + b] * W0[k * B + b];
+    double nrm = sqrt(s);
+    for (int64_t b = 0; b < B; b++) W0[k * B + b] /= nrm;
+  }
+  while (n_iter-- > 0) {                                                    /* :72-83 */
+    for (int64_t b = 0; b < B; b++) v1[b] = 0.0;
+    for (int64_t k = 0; k < K; k++)
+      for (int64_t b = 0; b < B; b++) v1[b] += W0[k * B + b] * h[k];         /* :74 */
+    for (int64_t b = 0; b < B; b++) {
+      double p = v1[b] > FO_EPS ? v1[b] : FO_EPS;                           /* :75 */
+      r[b] = v0[b] / p;                                                     /* :76 */
+    }
+    for (int64_t k = 0; k < K; k++) {
+      double sn = 0.0, sd = 0.0;
+      for (int64_t b = 0; b < B; b++) { sn += W0[k * B + b] * r[b]; sd += W0[k * B + b]; } /* :77-78 */
+      hnum[k] = sn; hden[k] = sd;
+    }
+    for (int64_t k = 0; k < K; k++) h[k] = h[k] * hnum[k] / (hden[k] > FO_EPS ? hden[k] : FO_EPS); /* :79 */
+  }
+  if (out) for (int64_t k = 0; k < K; k++) out[k] = h[k];                   /* :85-86 */
+  if (v) {                                                                  /* :88 */
+    for (int64_t b = 0; b < B; b++) v[b] = 0.0;
+    for (int64_t k = 0; k < K; k++)
+      for (int64_t b = 0; b < B; b++) v[b] += W0[k * B + b] * h[k];
+  }
+  free(h); free(v0);
+}
+
+/* NMF::estimate NMF.hpp:33-42:  E[f][b] = H[f][idx] * W[idx][b] */
+FO_EXPORT void fo_nmf_estimate(const double* W, const double* H, int64_t F, int64_t B, int64_t K, int64_t idx, double* E)
+{
+  for (int64_t f = 0; f < F; f++)
+    for (int64_t b = 0; b < B; b++) E[f * B + b] = H[f * K + idx] * W[idx * B + b];
+}
+
+/* RatioMask::init + process, exponent 1.  algorithms/public/RatioMask.hpp:33-57
+ * out = mixture * min(1, target * (1 / max(denominator, eps)))   (complex interleaved) */
+FO_EXPORT void fo_ratio_mask(const double* mixture, const double* target, const double* denominator, int64_t count,
+                             double* out)
+{
+  for (int64_t i = 0; i < count; i++) {
+    double mult = 1.0 / (denominator[i] > FO_EPS ? denominator[i] : FO_EPS); /* :39-40 */
+    double m = target[i] * mult;                                            /* :53-55 (pow 1) */
+    if (m > 1.0) m = 1.0;                                                   /* :56 */
+    out[2 * i] = mixture[2 * i] * m;
+    out[2 * i + 1] = mixture[2 * i + 1] * m;
+  }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * BufNMF per channel.  clients/nrt/NMFClient.hpp:233-335 with float32 host buffers (BufferAdaptor).
+ * audio: float[n] one channel.  bases_out float[K][B], acts_out float[F][K] (scaled by 1/max(H), :289-298),
+ * resynth_out float[K][n] (NULL = no resynthesis).  Optional seeds bases_in[K][B] / acts_in[F][K] (float) with
+ * modes 0 none / 1 seed / 2 fixed (:116-118, :139-141).  When a mode is 2 the corresponding *_out is not written
+ * (:277, :286).  Raw (unscaled) double W/H/V can be captured through dbg_W/dbg_H/dbg_V (NULL ok).
+ * ---------------------------------------------------------------------------------------------- */
+FO_EXPORT int fo_bufnmf_channel(const float* audio, int64_t n, int64_t win, int64_t fft, int64_t hop, int64_t K,
+                                int64_t iters, int64_t seed, int bases_mode, const float* bases_in, int acts_mode,
+                                const float* acts_in, float* bases_out, float* acts_out, float* resynth_out,
+                                int faithful, double* dbg_W, double* dbg_H, double* dbg_V)
+{
+  int64_t B = fft / 2 + 1;
+  int64_t F = fo_stft_num_frames(n, win, hop);
+  int fix_w = bases_mode == 2, fix_h = acts_mode == 2;
+  int needs_analysis = !(fix_w && fix_h);                                   /* :141 */
+  double* tmp = (double*) malloc(sizeof(double) * (size_t) n);
+  for (int64_t i = 0; i < n; i++) tmp[i] = (double) audio[i];               /* :240 */
+  double* spec = (double*) malloc(sizeof(double) * (size_t) (2 * F * B));
+  double* mag = (double*) malloc(sizeof(double) * (size_t) (F * B));
+  fo_stft(tmp, n, win, fft, hop, spec);                                     /* :241 */
+  fo_magnitude(spec, F * B, mag);                                           /* :242 */
+  double* W0 = NULL; double* H0 = NULL;
+  if (bases_mode > 0) {                                                     /* :248-252 */
+    W0 = (double*) malloc(sizeof(double) * (size_t) (K * B));
+    for (int64_t i = 0; i < K * B; i++) W0[i] = (double) bases_in[i];
+  }
+  if (acts_mode > 0) {                                                      /* :253-257 */
+    H0 = (double*) malloc(sizeof(double) * (size_t) (F * K));
+    for (int64_t i = 0; i < F * K; i++) H0[i] = (double) acts_in[i];
+  }
+  double* W = (double*) malloc(sizeof(double) * (size_t) (K * B));
+  double* H = (double*) malloc(sizeof(double) * (size_t) (F * K));
+  double* Vh = (double*) malloc(sizeof(double) * (size_t) (F * B));
+  fo_nmf_process(mag, F, B, K, iters * needs_analysis, !fix_w, !fix_h, seed, W0, H0, W, H, Vh, faithful, NULL,
+                 NULL);                                                     /* :268-271 */
+  if (dbg_W) memcpy(dbg_W, W, sizeof(double) * (size_t) (K * B));
+  if (dbg_H) memcpy(dbg_H, H, sizeof(double) * (size_t) (F * K));
+  if (dbg_V) memcpy(dbg_V, Vh, sizeof(double) * (size_t) (F * B));
+  if (bases_out && !fix_w)                                                  /* :277-283 */
+    for (int64_t i = 0; i < K * B; i++) bases_out[i] = (float) W[i];
+  if (acts_out && !fix_h) {                                                 /* :286-300 */
+    double maxh = H[0];
+    for (int64_t i = 1; i < F * K; i++) if (H[i] > maxh) maxh = H[i];
+    float scale = (float) (1.0 / maxh);
+    for (int64_t i = 0; i < F * K; i++) { float x = (float) H[i]; x *= scale; acts_out[i] = x; }
+  }
+  if (resynth_out) {                                                        /* :302-333 */
+    double* est = (double*) malloc(sizeof(double) * (size_t) (F * B));
+    double* msp = (double*) malloc(sizeof(double) * (size_t) (2 * F * B));
+    double* aud = (double*) malloc(sizeof(double) * (size_t) n);
+    for (int64_t j = 0; j < K; j++) {
+      fo_nmf_estimate(W, H, F, B, K, j, est);                               /* :319 */
+      fo_ratio_mask(spec, est, Vh, F * B, msp);                             /* :306, :324 */
+      fo_istft(msp, F, win, fft, hop, aud, n);                              /* :328 */
+      for (int64_t i = 0; i < n; i++) resynth_out[j * n + i] = (float) aud[i]; /* :329 */
+    }
+    free(est); free(msp); free(aud);
+  }
+  free(tmp); free(spec); free(mag); free(W0); free(H0); free(W); free(H); free(Vh);
+  return 0;
+}
+
+/* Batch driver used only by the CPU baseline: `batch` independent single-channel buffers of equal length, one
+ * OpenMP thread per buffer (models several concurrent BufNMF jobs; the reference itself is single-threaded per job,
+ * clients/common/FluidNRTClientWrapper.hpp:1048).  seeds[b] per buffer. */
+FO_EXPORT int fo_bufnmf_batch(const float* audio, int64_t batch, int64_t n, int64_t win, int64_t fft, int64_t hop,
+                              int64_t K, int64_t iters, const int64_t* seeds, float* bases_out, float* acts_out,
+                              float* resynth_out, int faithful, int threads)
+{
+  int64_t B = fft / 2 + 1;
+  int64_t F = fo_stft_num_frames(n, win, hop);
+#ifdef _OPENMP
+  if (threads > 0) omp_set_num_threads(threads);
+#else
+  (void) threads;
+#endif
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int64_t b = 0; b < batch; b++) {
+    fo_bufnmf_channel(audio + b * n, n, win, fft, hop, K, iters, seeds ? seeds[b] : b, 0, NULL, 0, NULL,
+                      bases_out ? bases_out + b * K * B : NULL, acts_out ? acts_out + b * F * K : NULL,
+                      resynth_out ? resynth_out + b * K * n : NULL, faithful, NULL, NULL, NULL);
+  }
+  return 0;
+}
+
+/* Streaming NMFMatch equivalent: clients/rt/NMFMatchClient.hpp:106-118 applied to `nframes` magnitude frames.
+ * Every frame: W = float bases copied fresh (:106-107), processFrame with n_iter iterations (10 in NMFMatch, :115),
+ * h0 from `seed` (identical for every frame when seed >= 0).  mags[nframes][B] -> acts[nframes][K]. */
+FO_EXPORT void fo_nmfmatch_frames(const double* mags, int64_t nframes, const double* W_in, int64_t B, int64_t K,
+                                  int64_t n_iter, int64_t seed, double* acts, int threads)
+{
+#ifdef _OPENMP
+  if (threads > 0) omp_set_num_threads(threads);
+#else
+  (void) threads;
+#endif
+#pragma omp parallel
+  {
+    double* W = (double*) malloc(sizeof(double) * (size_t) (K * B));
+#pragma omp for schedule(static)
+    for (int64_t f = 0; f < nframes; f++) {
+      memcpy(W, W_in, sizeof(double) * (size_t) (K * B));
+      fo_nmf_process_frame(mags + f * B, W, B, K, n_iter, seed, acts + f * K, NULL);
+    }
+    free(W);
+  }
+}
+
+/* Streaming frame cutter: the frames a BufferedProcess-driven client sees (clients/common/BufferedProcess.hpp:75-93,
+ * FluidSource.hpp:68-89): frame f covers samples [f*hop - win, f*hop) of the stream, zeros before the start. */
+FO_EXPORT void fo_stream_frames_mag(const double* audio, int64_t n, int64_t win, int64_t fft, int64_t hop,
+                                    int64_t nframes, double* mags, double* spec_out)
+{
+  int64_t B = fft / 2 + 1;
+  double* frame = (double*) malloc(sizeof(double) * (size_t) win);
+  double* sp = (double*) malloc(sizeof(double) * (size_t) (2 * B));
+  for (int64_t f = 0; f < nframes; f++) {
+    for (int64_t j = 0; j < win; j++) {
+      int64_t t = f * hop - win + j;
+      frame[j] = (t >= 0 && t < n) ? audio[t] : 0.0;
+    }
+    fo_stft_frame(frame, win, fft, sp);
+    fo_magnitude(sp, B, mags + f * B);
+    if (spec_out) memcpy(spec_out + 2 * f * B, sp, sizeof(double) * (size_t) (2 * B));
+  }
+  free(frame); free(sp);
+}
+
+FO_EXPORT int fo_num_threads(void)
+{
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}

@@ -1,0 +1,205 @@
+"""Independent numpy (pocketfft, OpenBLAS) fp64 restatement of the reference path -- a second opinion on the C oracle.
+
+TEST INFRASTRUCTURE ONLY (see flucoma_oracle.c header).  Written from the reference sources, not from the C oracle,
+with different arithmetic building blocks (numpy.fft, BLAS matmul, numpy's own MT19937-64 is NOT used: the libstdc++
+distribution is restated from its definition), so agreement between the two at ~1e-12 is meaningful.
+
+Reference citations are relative to /root/reference/include/flucoma.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+EPS = np.finfo(np.float64).eps  # algorithms/util/AlgorithmUtils.hpp:19
+
+
+# ---- size rules: clients/common/ParameterTypes.hpp:295-313, clients/nrt/NMFClient.hpp:111-113 -----------------
+def next_pow2(x: int) -> int:
+    return 0 if x <= 0 else 1 << (int(x) - 1).bit_length()
+
+
+def fft_params(win: int, hop: int = -1, fft: int = -1):
+    f = next_pow2(win) if fft < 0 else fft
+    h = hop if hop > 0 else win >> 1
+    return win, h, f, (f >> 1) + 1
+
+
+def num_frames(n: int, win: int, hop: int) -> int:
+    return (n + win + hop - win) // hop
+
+
+# ---- WindowFuncs.hpp:41-45 ---------------------------------------------------------------------------------------
+def hann(size: int) -> np.ndarray:
+    i = np.arange(size, dtype=np.float64)
+    return 0.5 - 0.5 * np.cos((np.pi * 2 * i) / size)
+
+
+# ---- STFT.hpp:90-108 + FFT.hpp:92-108 ----------------------------------------------------------------------------
+def stft(audio: np.ndarray, win: int, fft: int, hop: int) -> np.ndarray:
+    a = np.asarray(audio, dtype=np.float64)
+    half = win // 2
+    padded = np.zeros(a.size + win + hop)
+    padded[half:half + a.size] = a
+    F = (padded.size - win) // hop
+    w = hann(win)
+    idx = np.arange(F)[:, None] * hop + np.arange(win)[None, :]
+    frames = padded[idx] * w
+    S = np.fft.rfft(frames, n=fft, axis=1)  # zero-pads win -> fft, unnormalised forward DFT
+    S[:, 0] = S[:, 0].real
+    S[:, -1] = S[:, -1].real
+    return S
+
+
+def magnitude(S: np.ndarray) -> np.ndarray:  # STFT.hpp:61-66
+    return np.abs(S)
+
+
+# ---- STFT.hpp:178-199 + FFT.hpp:149-163 --------------------------------------------------------------------------
+def istft(S: np.ndarray, win: int, fft: int, hop: int, n_out: int) -> np.ndarray:
+    F = S.shape[0]
+    half = win // 2
+    osz = win + (F - 1) * hop + win + hop
+    out = np.zeros(osz)
+    nrm = np.zeros(osz)
+    w = hann(win)
+    S = np.array(S, dtype=np.complex128)
+    S[:, 0] = S[:, 0].real   # htl::rifft ignores Im(DC)/Im(Nyquist): FFT.hpp:160
+    S[:, -1] = S[:, -1].real
+    y = np.fft.irfft(S, n=fft, axis=1) * fft  # = rifft result (fft * x)
+    for i in range(F):
+        out[i * hop:i * hop + win] += y[i, :win] * (1.0 / fft) * w
+        nrm[i * hop:i * hop + win] += w * w
+    out = out / np.maximum(nrm, EPS)
+    return out[half:half + n_out]
+
+
+# ---- EigenRandom.hpp:73-110 on libstdc++ -------------------------------------------------------------------------
+def _mt19937_64(seed: int, count: int) -> np.ndarray:
+    """Plain-Python MT19937-64 (Matsumoto & Nishimura 2004 reference constants)."""
+    M = (1 << 64) - 1
+    mt = [0] * 312
+    mt[0] = seed & M
+    for i in range(1, 312):
+        mt[i] = (6364136223846793005 * (mt[i - 1] ^ (mt[i - 1] >> 62)) + i) & M
+    out = np.empty(count, dtype=np.uint64)
+    idx = 312
+    for n in range(count):
+        if idx >= 312:
+            for i in range(312):
+                x = (mt[i] & 0xFFFFFFFF80000000) | (mt[(i + 1) % 312] & 0x7FFFFFFF)
+                mt[i] = mt[(i + 156) % 312] ^ (x >> 1) ^ (0xB5026F5AA96619E9 if x & 1 else 0)
+            idx = 0
+        x = mt[idx]
+        idx += 1
+        x ^= (x >> 29) & 0x5555555555555555
+        x ^= (x << 17) & 0x71D67FFFEDA60000
+        x ^= (x << 37) & 0xFFF7EEE000000000
+        x ^= x >> 43
+        out[n] = x & M
+    return out
+
+
+def random_uniform(seed: int, count: int) -> np.ndarray:
+    raw = _mt19937_64(seed, count)
+    r = raw.astype(np.float64) / 18446744073709551616.0  # generate_canonical<double,53> with a 64-bit engine
+    r[r >= 1.0] = np.nextafter(1.0, 0.0)
+    return r
+
+
+def nmf_random_init(seed: int, bins: int, rank: int, frames: int):
+    # column-major fill of (B x K) and (K x F); each restarts the stream: NMF.hpp:104-105, 116-117
+    W = random_uniform(seed, bins * rank).reshape(rank, bins)      # W[k][b] = u[k*B + b]
+    H = random_uniform(seed, rank * frames).reshape(frames, rank)  # H[f][k] = u[f*K + k]
+    return W, H
+
+
+# ---- NMF.hpp:91-134, 144-183 -------------------------------------------------------------------------------------
+def nmf_process(X, rank, n_iter, update_w=True, update_h=True, seed=-1, W0=None, H0=None, progress=None):
+    """X[F][B] -> W1[K][B], H1[F][K], V1[F][B], cancelled.  Written in the reference's own orientation (B x F)."""
+    X = np.asarray(X, dtype=np.float64)
+    F, B = X.shape
+    V = X.T.copy()                                              # :125  (B x F)
+    if W0 is None:
+        W = nmf_random_init(seed, B, rank, F)[0].T.copy()       # B x K
+    else:
+        W = np.asarray(W0, dtype=np.float64).T.copy()           # :111
+    if H0 is None:
+        H = nmf_random_init(seed, B, rank, F)[1].T.copy()       # K x F
+    else:
+        H = np.asarray(H0, dtype=np.float64).T.copy()           # :123
+    ones = np.ones_like(V)
+    H = np.maximum(H, EPS)                                      # :150
+    W = np.maximum(W, EPS)                                      # :151
+    W = W / np.linalg.norm(W, axis=0, keepdims=True)            # :152
+    H = H / np.linalg.norm(H, axis=1, keepdims=True)            # :153
+    cancelled = False
+    for it in range(n_iter):
+        if update_w:
+            V1 = np.maximum(W @ H, EPS)                         # :158
+            wnum = (V / V1) @ H.T                               # :159
+            wden = ones @ H.T                                   # :160
+            W = W * wnum / np.maximum(wden, EPS)                # :161
+            if W.max() > EPS:                                   # :162
+                W = W / np.linalg.norm(W, axis=0, keepdims=True)
+        V2 = np.maximum(W @ H, EPS)                             # :165
+        if update_h:
+            hnum = W.T @ (V / V2)                               # :168
+            hden = W.T @ ones                                   # :169
+            H = H * hnum / np.maximum(hden, EPS)                # :170
+        if progress is not None and not progress(it + 1):       # :175-176
+            cancelled = True
+            break
+    if not cancelled:
+        V = W @ H                                               # :182
+    return W.T.copy(), H.T.copy(), V.T.copy(), cancelled        # :127-133
+
+
+def nmf_process_frame(x, W0, n_iter, seed):
+    """NMF.hpp:45-89.  Returns (h, v, mutated W)."""
+    x = np.asarray(x, dtype=np.float64)
+    W = np.asarray(W0, dtype=np.float64).copy()                 # K x B
+    K = W.shape[0]
+    h = random_uniform(seed, K)                                 # :55
+    v0 = np.maximum(x, EPS)                                     # :60
+    W = np.maximum(W, EPS)                                      # :58
+    h = np.maximum(h, EPS)                                      # :59
+    W = W / np.linalg.norm(W, axis=1, keepdims=True)            # :63-64
+    ones = np.ones_like(x)
+    for _ in range(n_iter):
+        v1 = np.maximum(W.T @ h, EPS)                           # :74-75
+        r = v0 / v1                                             # :76
+        h = h * (W @ r) / np.maximum(W @ ones, EPS)             # :77-79
+    return h, W.T @ h, W
+
+
+def nmf_estimate(W, H, idx):  # NMF.hpp:33-42
+    return np.outer(np.asarray(H)[:, idx], np.asarray(W)[idx, :])
+
+
+def ratio_mask(mixture, target, denominator):  # RatioMask.hpp:33-57, exponent 1
+    mult = 1.0 / np.maximum(denominator, EPS)
+    return mixture * np.minimum(1.0, target * mult)
+
+
+# ---- NMFClient.hpp:233-335 ---------------------------------------------------------------------------------------
+def bufnmf_channel(audio_f32, win, fft, hop, rank, iters, seed, bases_mode=0, bases_in=None, acts_mode=0, acts_in=None,
+                   resynth=False):
+    a = np.asarray(audio_f32, dtype=np.float32)
+    n = a.size
+    S = stft(a.astype(np.float64), win, fft, hop)
+    M = magnitude(S)
+    fix_w, fix_h = bases_mode == 2, acts_mode == 2
+    needs = not (fix_w and fix_h)
+    W0 = None if bases_mode == 0 else np.asarray(bases_in, dtype=np.float32).astype(np.float64)
+    H0 = None if acts_mode == 0 else np.asarray(acts_in, dtype=np.float32).astype(np.float64)
+    W, H, Vh, _ = nmf_process(M, rank, iters * int(needs), not fix_w, not fix_h, seed, W0, H0)
+    bases = W.astype(np.float32)
+    scale = np.float32(1.0 / H.max())
+    acts = H.astype(np.float32) * scale
+    rs = None
+    if resynth:
+        rs = np.zeros((rank, n), np.float32)
+        for j in range(rank):
+            est = nmf_estimate(W, H, j)
+            rs[j] = istft(ratio_mask(S, est, Vh), win, fft, hop, n).astype(np.float32)
+    return dict(bases=bases, acts=acts, resynth=rs, W=W, H=H, V=Vh)
