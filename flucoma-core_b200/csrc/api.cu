@@ -1,0 +1,660 @@
+// C ABI of libflucoma_b200.so (include/flucoma_b200.h): plan management and the batched pipelines.
+#include "common.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <random>
+
+using namespace fb200;
+
+struct fb200_plan : public fb200::Plan {};
+
+static thread_local std::string g_create_error;
+
+namespace {
+
+int64_t next_pow2_i64(int64_t x)
+{ // clients/common/ParameterTypes.hpp:323-335 (up = true)
+  if (x <= 0) return 0;
+  uint32_t v = (uint32_t) x;
+  --v;
+  v |= v >> 1; v |= v >> 2; v |= v >> 4; v |= v >> 8; v |= v >> 16;
+  return (int64_t) (v + 1);
+}
+
+size_t dsize(int dtype) { return dtype == FB200_F64 ? 8 : 4; }
+
+int32_t get_fft_plan(Plan* p, cufftType type, int64_t batch, cufftHandle* out)
+{
+  auto key = std::make_pair((int) type, batch);
+  auto it = p->fft_plans.find(key);
+  if (it != p->fft_plans.end()) { *out = it->second; return FB200_OK; }
+  if (batch > 0x7fffffffLL) { p->err = "cuFFT batch too large"; return FB200_ERR_INVALID; }
+  cufftHandle h;
+  int n[1] = {p->fft};
+  FB_CUFFT(p, cufftPlanMany(&h, 1, n, nullptr, 1, 0, nullptr, 1, 0, type, (int) batch));
+  FB_CUFFT(p, cufftSetStream(h, p->stream));
+  p->fft_plans[key] = h;
+  *out = h;
+  return FB200_OK;
+}
+
+// buffers per wave so that the cuFFT real-side scratch stays <= ~512 MB
+int64_t wave_size(const Plan* p, int64_t F, int64_t batch, int64_t mult)
+{
+  int64_t per_buf = std::max<int64_t>(1, F * p->fft * mult);
+  int64_t w = std::max<int64_t>(1, ((int64_t) 1 << 27) / per_buf);
+  return std::min(w, batch);
+}
+
+struct StageTimer {
+  Plan* p;
+  explicit StageTimer(Plan* pl) : p(pl)
+  {
+    p->launches = 0; p->launches_nmf = 0;
+    std::memset(&p->stats, 0, sizeof(p->stats));
+  }
+  void mark(int i) { cudaEventRecord(p->ev[i], p->stream); }
+  float ms(int a, int b)
+  {
+    float t = 0.f;
+    cudaEventElapsedTime(&t, p->ev[a], p->ev[b]);
+    return t;
+  }
+};
+
+// STFT of `batch` buffers already on the device (float [batch][n]) -> V (padded magnitudes, may be null) and/or
+// spec_all (float2 [batch][F][B], may be null).  STFT.hpp:90-108 + :61-66.
+int32_t run_stft(Plan* p, const float* d_audio, int64_t batch, int64_t n, int64_t F, float* V, int64_t Fp, int64_t Bp,
+                 float2* spec_all, int half)
+{
+  const int B = p->bins;
+  int64_t wave = wave_size(p, F, batch, 1);
+  FB_CUDA(p, p->frames.ensure(sizeof(float) * (size_t) (wave * F * p->fft)));
+  float2* spec_wave = nullptr;
+  if (!spec_all) {
+    FB_CUDA(p, p->spec.ensure(sizeof(float2) * (size_t) (wave * F * B)));
+    spec_wave = p->spec.as<float2>();
+  }
+  for (int64_t b0 = 0; b0 < batch; b0 += wave) {
+    int64_t nb = std::min(wave, batch - b0);
+    launch_frame_window(p, d_audio + b0 * n, n, nb, F, p->frames.as<float>(), half);
+    cufftHandle h;
+    FB_TRY(get_fft_plan(p, CUFFT_R2C, nb * F, &h));
+    float2* sp = spec_all ? spec_all + b0 * F * B : spec_wave;
+    FB_CUFFT(p, cufftExecR2C(h, p->frames.as<float>(), reinterpret_cast<cufftComplex*>(sp)));
+    p->launches++;
+    launch_magnitude(p, sp, nb, F, V ? V + b0 * Fp * Bp : nullptr, Fp, Bp);
+  }
+  return FB200_OK;
+}
+
+// ISTFT of nsig spectra (float2 [nsig][F][B], destroyed) -> out float [nsig][n].  STFT.hpp:178-199
+int32_t run_istft(Plan* p, float2* spec, int64_t nsig, int64_t F, int64_t n, float* out, int half)
+{
+  int64_t wave = wave_size(p, F, nsig, 1);
+  FB_CUDA(p, p->frames.ensure(sizeof(float) * (size_t) (wave * F * p->fft)));
+  for (int64_t s0 = 0; s0 < nsig; s0 += wave) {
+    int64_t ns = std::min(wave, nsig - s0);
+    cufftHandle h;
+    FB_TRY(get_fft_plan(p, CUFFT_C2R, ns * F, &h));
+    FB_CUFFT(p, cufftExecC2R(h, reinterpret_cast<cufftComplex*>(spec + s0 * F * p->bins), p->frames.as<float>()));
+    p->launches++;
+    launch_ola(p, p->frames.as<float>(), ns, F, n, out + s0 * n, half);
+  }
+  return FB200_OK;
+}
+
+int32_t alloc_nmf(Plan* p, NmfDev& d)
+{
+  FB_TRY(simt_configure(p, d));
+  FB_CUDA(p, p->V.ensure(sizeof(float) * (size_t) d.batch * d.Fp * d.Bp));
+  FB_CUDA(p, p->W.ensure(sizeof(float) * (size_t) d.batch * d.KP * d.Bp));
+  FB_CUDA(p, p->H.ensure(sizeof(float) * (size_t) d.batch * d.Fp * d.KP));
+  FB_CUDA(p, p->hden.ensure(sizeof(float) * (size_t) d.batch * d.KP));
+  d.V = p->V.as<float>(); d.W = p->W.as<float>(); d.H = p->H.as<float>(); d.hden = p->hden.as<float>();
+  d.wnum_part = nullptr; d.wden_part = nullptr;
+  return FB200_OK;
+}
+
+int32_t alloc_partials(Plan* p, NmfDev& d)
+{
+  FB_CUDA(p, p->wnum_part.ensure(sizeof(float) * (size_t) d.batch * d.ctas_per_buf * d.KP * d.Bp));
+  FB_CUDA(p, p->wden_part.ensure(sizeof(float) * (size_t) d.batch * d.ctas_per_buf * d.KP));
+  d.wnum_part = p->wnum_part.as<float>(); d.wden_part = p->wden_part.as<float>();
+  return FB200_OK;
+}
+
+// seeds (host) -> device; negative seeds are replaced by std::random_device draws (EigenRandom.hpp:80)
+int32_t upload_seeds(Plan* p, const int64_t* seeds, int64_t batch)
+{
+  FB_CUDA(p, p->seeds.ensure(sizeof(int64_t) * (size_t) batch));
+  std::vector<int64_t> s((size_t) batch);
+  std::random_device rd;
+  for (int64_t i = 0; i < batch; i++) {
+    int64_t v = seeds ? seeds[i] : -1;
+    if (v < 0) v = (int64_t) rd();
+    s[(size_t) i] = v;
+  }
+  FB_CUDA(p, cudaMemcpyAsync(p->seeds.p, s.data(), sizeof(int64_t) * (size_t) batch, cudaMemcpyHostToDevice, p->stream));
+  FB_CUDA(p, cudaStreamSynchronize(p->stream)); // `s` dies at scope exit
+  return FB200_OK;
+}
+
+// The multiplicative-update loop (NMF.hpp:154-181) on the device state in `d`.  Returns FB200_CANCELLED when the
+// progress callback asked to stop; W/H then hold the state after the last completed iteration, as in the reference.
+int32_t run_nmf_loop(Plan* p, NmfDev& d, int iters, bool upd_w, bool upd_h, fb200_progress_fn progress, void* user,
+                     int stride)
+{
+  if (iters <= 0 || (!upd_w && !upd_h)) {
+    // nothing changes W/H; the reference still calls the callbacks every iteration (:175-176)
+    for (int it = 1; progress && it <= iters; it++)
+      if (!progress(user, it)) return FB200_CANCELLED;
+    return FB200_OK;
+  }
+  if (upd_w) FB_TRY(alloc_partials(p, d));
+  if (progress) {
+    // exact per-iteration state so that a cancel leaves W,H as the reference would: no cross-iteration fusion
+    if (stride <= 0) stride = 1;
+    for (int it = 1; it <= iters; it++) {
+      if (upd_w) { simt_launch_tile(p, d, 0, 1, 1); simt_launch_w_finalize(p, d); }
+      if (upd_h) simt_launch_tile(p, d, 1, 0, 1);
+      if (it % stride == 0 || it == iters) {
+        FB_CUDA(p, cudaStreamSynchronize(p->stream));
+        for (int j = it - ((it - 1) % stride); j <= it; j++)
+          if (!progress(user, j)) return FB200_CANCELLED;
+      }
+    }
+    return FB200_OK;
+  }
+  if (upd_w && upd_h) {
+    simt_launch_tile(p, d, 0, 1, 1); // W-numerator of iteration 1
+    simt_launch_w_finalize(p, d);
+    for (int it = 1; it < iters; it++) {
+      simt_launch_tile(p, d, 1, 1, 1); // H-update of iteration `it` fused with the W-numerator of `it+1`
+      simt_launch_w_finalize(p, d);
+    }
+    simt_launch_tile(p, d, 1, 0, 1); // H-update of the last iteration
+  } else if (upd_w) {
+    for (int it = 0; it < iters; it++) { simt_launch_tile(p, d, 0, 1, 1); simt_launch_w_finalize(p, d); }
+  } else {
+    for (int it = 0; it < iters; it++) simt_launch_tile(p, d, 1, 0, 1);
+  }
+  return FB200_OK;
+}
+
+// host<->device helpers for caller arrays --------------------------------------------------------------------------
+// Brings a caller array (dtype/mem) of `count` elements to a device pointer of the same dtype.
+int32_t to_device_raw(Plan* p, const void* src, int mem, size_t bytes, DevBuf& stage, const void** out)
+{
+  if (mem == FB200_DEVICE) { *out = src; return FB200_OK; }
+  FB_CUDA(p, stage.ensure(bytes));
+  FB_CUDA(p, cudaMemcpyAsync(stage.p, src, bytes, cudaMemcpyHostToDevice, p->stream));
+  *out = stage.p;
+  return FB200_OK;
+}
+
+int32_t finish(Plan* p, StageTimer& t, int last_ev)
+{
+  FB_CUDA(p, cudaStreamSynchronize(p->stream));
+  FB_CUDA(p, cudaGetLastError());
+  p->stats.ms_total = t.ms(0, last_ev);
+  p->stats.launches_total = p->launches;
+  p->stats.launches_nmf = p->launches_nmf;
+  p->stats.backend_used = FB200_BACKEND_SIMT;
+  return FB200_OK;
+}
+
+} // namespace
+
+// =====================================================================================================================
+extern "C" {
+
+uint32_t fb200_abi_version(void) { return FB200_ABI_VERSION; }
+
+int32_t fb200_device_count(void)
+{
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int64_t fb200_num_frames(int64_t n_samples, int32_t win, int32_t hop)
+{ // STFT.hpp:94-99, NMFClient.hpp:111-113
+  if (hop <= 0) hop = win >> 1;
+  if (hop <= 0) return 0;
+  return (n_samples + win + hop - win) / hop;
+}
+
+int32_t fb200_resolve_fft(int32_t win, int32_t hop, int32_t fft, int32_t* out_hop, int32_t* out_fft, int32_t* out_bins)
+{ // ParameterTypes.hpp:295-313
+  if (win <= 0) return FB200_ERR_INVALID;
+  int32_t f = fft < 0 ? (int32_t) next_pow2_i64(win) : fft;
+  int32_t h = hop > 0 ? hop : (win >> 1);
+  if (f < win || (f & (f - 1)) != 0 || f < 4 || h <= 0) return FB200_ERR_INVALID;
+  if (out_hop) *out_hop = h;
+  if (out_fft) *out_fft = f;
+  if (out_bins) *out_bins = (f >> 1) + 1;
+  return FB200_OK;
+}
+
+void fb200_shard_range(int64_t total, int32_t world, int32_t rank, int64_t* begin, int64_t* count)
+{ // contiguous, balanced: the first (total % world) ranks take one extra buffer
+  if (world <= 0) world = 1;
+  int64_t base = total / world, rem = total % world;
+  int64_t b = rank * base + std::min<int64_t>(rank, rem);
+  int64_t c = base + (rank < rem ? 1 : 0);
+  if (begin) *begin = b;
+  if (count) *count = c;
+}
+
+int32_t fb200_plan_create(const fb200_config* cfg, fb200_plan** out)
+{
+  if (!cfg || !out || cfg->struct_size != sizeof(fb200_config)) { g_create_error = "bad config"; return FB200_ERR_INVALID; }
+  *out = nullptr;
+  int32_t hop, fft, bins;
+  if (fb200_resolve_fft(cfg->win, cfg->hop, cfg->fft, &hop, &fft, &bins) != FB200_OK) {
+    g_create_error = "invalid window/hop/fft: fft must be a power of two >= win";
+    return FB200_ERR_INVALID;
+  }
+  if (fb200_device_count() <= cfg->device || cfg->device < 0) { g_create_error = "no such CUDA device"; return FB200_ERR_NO_DEVICE; }
+  if (cudaSetDevice(cfg->device) != cudaSuccess) { g_create_error = "cudaSetDevice failed"; return FB200_ERR_CUDA; }
+  fb200_plan* p = new fb200_plan();
+  p->cfg = *cfg;
+  p->win = cfg->win; p->hop = hop; p->fft = fft; p->bins = bins;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, cfg->device) == cudaSuccess) p->sm_count = prop.multiProcessorCount;
+  bool ok = cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking) == cudaSuccess;
+  for (auto& e : p->ev) ok = ok && cudaEventCreate(&e) == cudaSuccess;
+  ok = ok && p->window.ensure(sizeof(float) * (size_t) p->win) == cudaSuccess;
+  if (!ok) {
+    g_create_error = std::string("CUDA setup failed: ") + cudaGetErrorString(cudaGetLastError());
+    fb200_plan_destroy(p);
+    return FB200_ERR_CUDA;
+  }
+  launch_hann(p);
+  if (cudaStreamSynchronize(p->stream) != cudaSuccess) {
+    g_create_error = std::string("kernel launch failed (is this an sm_100a device?): ") + cudaGetErrorString(cudaGetLastError());
+    fb200_plan_destroy(p);
+    return FB200_ERR_CUDA;
+  }
+  *out = p;
+  return FB200_OK;
+}
+
+void fb200_plan_destroy(fb200_plan* p)
+{
+  if (!p) return;
+  cudaSetDevice(p->cfg.device);
+  if (p->stream) cudaStreamSynchronize(p->stream);
+  for (auto& kv : p->fft_plans) cufftDestroy(kv.second);
+  DevBuf* bufs[] = {&p->window, &p->audio, &p->stage, &p->frames, &p->spec, &p->cspec, &p->V, &p->W, &p->H, &p->hden,
+                    &p->wnum_part, &p->wden_part, &p->rnd, &p->seeds, &p->scale, &p->out_a, &p->out_b};
+  for (auto* b : bufs) b->release();
+  p->pin_a.release(); p->pin_b.release();
+  for (auto& e : p->ev) if (e) cudaEventDestroy(e);
+  if (p->stream) cudaStreamDestroy(p->stream);
+  delete p;
+}
+
+const char* fb200_last_error(const fb200_plan* p) { return p ? p->err.c_str() : g_create_error.c_str(); }
+
+int32_t fb200_get_stats(const fb200_plan* p, fb200_stats* out)
+{
+  if (!p || !out) return FB200_ERR_INVALID;
+  *out = p->stats;
+  return FB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+int32_t fb200_stft(fb200_plan* p, const void* audio, int64_t batch, int64_t n, void* spectrum, void* magnitude,
+                   int32_t dtype, int32_t mem)
+{
+  if (!p) return FB200_ERR_INVALID;
+  if (!audio || batch <= 0 || n < 0 || (!spectrum && !magnitude)) { p->err = "fb200_stft: bad arguments"; return FB200_ERR_INVALID; }
+  FB_CUDA(p, cudaSetDevice(p->cfg.device));
+  StageTimer t(p);
+  t.mark(0);
+  const int B = p->bins;
+  const int64_t F = fb200_num_frames(n, p->win, p->hop);
+  const void* d_raw;
+  FB_TRY(to_device_raw(p, audio, mem, dsize(dtype) * (size_t) (batch * n), p->stage, &d_raw));
+  FB_CUDA(p, p->audio.ensure(sizeof(float) * (size_t) std::max<int64_t>(1, batch * n)));
+  launch_copy3d(p, d_raw, dtype, n, n, p->audio.p, FB200_F32, n, n, batch, 1, n, nullptr, 0);
+  t.mark(1);
+  FB_CUDA(p, p->cspec.ensure(sizeof(float2) * (size_t) (batch * F * B)));
+  float* mag = nullptr;
+  if (magnitude) {
+    FB_CUDA(p, p->V.ensure(sizeof(float) * (size_t) (batch * F * B)));
+    mag = p->V.as<float>();
+  }
+  FB_TRY(run_stft(p, p->audio.as<float>(), batch, n, F, mag, F, B, p->cspec.as<float2>(), p->win / 2));
+  t.mark(2);
+  // export
+  if (spectrum) {
+    size_t bytes = dsize(dtype) * 2 * (size_t) (batch * F * B);
+    void* dst = spectrum;
+    if (mem == FB200_HOST) { FB_CUDA(p, p->out_a.ensure(bytes)); dst = p->out_a.p; }
+    launch_copy3d(p, p->cspec.p, FB200_F32, F * B * 2, 2 * B, dst, dtype, F * B * 2, 2 * B, batch, F, 2 * B, nullptr, 0);
+    if (mem == FB200_HOST) FB_CUDA(p, cudaMemcpyAsync(spectrum, dst, bytes, cudaMemcpyDeviceToHost, p->stream));
+  }
+  if (magnitude) {
+    size_t bytes = dsize(dtype) * (size_t) (batch * F * B);
+    void* dst = magnitude;
+    if (mem == FB200_HOST) { FB_CUDA(p, p->out_b.ensure(bytes)); dst = p->out_b.p; }
+    launch_copy3d(p, mag, FB200_F32, F * B, B, dst, dtype, F * B, B, batch, F, B, nullptr, 0);
+    if (mem == FB200_HOST) FB_CUDA(p, cudaMemcpyAsync(magnitude, dst, bytes, cudaMemcpyDeviceToHost, p->stream));
+  }
+  t.mark(3);
+  FB_TRY(finish(p, t, 3));
+  p->stats.ms_h2d = t.ms(0, 1); p->stats.ms_stft = t.ms(1, 2); p->stats.ms_d2h = t.ms(2, 3);
+  return FB200_OK;
+}
+
+int32_t fb200_istft(fb200_plan* p, const void* spectrum, int64_t batch, int64_t F, void* audio, int64_t n,
+                    int32_t dtype, int32_t mem)
+{
+  if (!p) return FB200_ERR_INVALID;
+  if (!spectrum || !audio || batch <= 0 || F <= 0 || n <= 0) { p->err = "fb200_istft: bad arguments"; return FB200_ERR_INVALID; }
+  if (p->win / 2 + n > p->win + (F - 1) * p->hop + p->win + p->hop) { p->err = "fb200_istft: n_samples exceeds the overlap-add length"; return FB200_ERR_INVALID; }
+  FB_CUDA(p, cudaSetDevice(p->cfg.device));
+  StageTimer t(p);
+  t.mark(0);
+  const int B = p->bins;
+  const void* d_raw;
+  FB_TRY(to_device_raw(p, spectrum, mem, dsize(dtype) * 2 * (size_t) (batch * F * B), p->stage, &d_raw));
+  FB_CUDA(p, p->cspec.ensure(sizeof(float2) * (size_t) (batch * F * B)));
+  launch_copy3d(p, d_raw, dtype, F * B * 2, 2 * B, p->cspec.p, FB200_F32, F * B * 2, 2 * B, batch, F, 2 * B, nullptr, 0);
+  t.mark(1);
+  FB_CUDA(p, p->audio.ensure(sizeof(float) * (size_t) (batch * n)));
+  FB_TRY(run_istft(p, p->cspec.as<float2>(), batch, F, n, p->audio.as<float>(), p->win / 2));
+  t.mark(2);
+  size_t bytes = dsize(dtype) * (size_t) (batch * n);
+  void* dst = audio;
+  if (mem == FB200_HOST) { FB_CUDA(p, p->out_a.ensure(bytes)); dst = p->out_a.p; }
+  launch_copy3d(p, p->audio.p, FB200_F32, n, n, dst, dtype, n, n, batch, 1, n, nullptr, 0);
+  if (mem == FB200_HOST) FB_CUDA(p, cudaMemcpyAsync(audio, dst, bytes, cudaMemcpyDeviceToHost, p->stream));
+  t.mark(3);
+  FB_TRY(finish(p, t, 3));
+  p->stats.ms_h2d = t.ms(0, 1); p->stats.ms_resynth = t.ms(1, 2); p->stats.ms_d2h = t.ms(2, 3);
+  return FB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+int32_t fb200_nmf_process(fb200_plan* p, const fb200_nmf_args* a)
+{
+  if (!p) return FB200_ERR_INVALID;
+  if (!a || a->struct_size != sizeof(fb200_nmf_args) || !a->X || a->batch <= 0 || a->frames <= 0 || a->bins <= 0 ||
+      a->rank <= 0 || a->iterations < 0) {
+    p->err = "fb200_nmf_process: bad arguments";
+    return FB200_ERR_INVALID;
+  }
+  FB_CUDA(p, cudaSetDevice(p->cfg.device));
+  StageTimer t(p);
+  t.mark(0);
+  NmfDev d{};
+  d.batch = (int) a->batch; d.F = (int) a->frames; d.B = (int) a->bins; d.K = a->rank;
+  FB_TRY(alloc_nmf(p, d));
+  const int64_t F = d.F, B = d.B, K = d.K;
+  const size_t es = dsize(a->dtype);
+  // X -> V (zero padded)
+  const void* d_x;
+  FB_TRY(to_device_raw(p, a->X, a->mem, es * (size_t) (a->batch * F * B), p->stage, &d_x));
+  FB_CUDA(p, cudaMemsetAsync(d.V, 0, sizeof(float) * (size_t) d.batch * d.Fp * d.Bp, p->stream));
+  launch_copy3d(p, d_x, a->dtype, F * B, B, d.V, FB200_F32, (int64_t) d.Fp * d.Bp, d.Bp, a->batch, F, B, nullptr, 0);
+  // seeds / W0 / H0
+  const float* dW0 = nullptr; const float* dH0 = nullptr; const float* U = nullptr;
+  int64_t u_stride = std::max(B * K, K * F);
+  if (a->W0) {
+    const void* raw;
+    FB_TRY(to_device_raw(p, a->W0, a->mem, es * (size_t) (a->batch * K * B), p->out_a, &raw));
+    FB_CUDA(p, p->cspec.ensure(sizeof(float) * (size_t) (a->batch * K * B)));
+    launch_copy3d(p, raw, a->dtype, K * B, B, p->cspec.p, FB200_F32, K * B, B, a->batch, K, B, nullptr, 0);
+    dW0 = p->cspec.as<float>();
+  }
+  if (a->H0) {
+    const void* raw;
+    FB_TRY(to_device_raw(p, a->H0, a->mem, es * (size_t) (a->batch * F * K), p->out_b, &raw));
+    FB_CUDA(p, p->frames.ensure(sizeof(float) * (size_t) (a->batch * F * K)));
+    launch_copy3d(p, raw, a->dtype, F * K, K, p->frames.p, FB200_F32, F * K, K, a->batch, F, K, nullptr, 0);
+    dH0 = p->frames.as<float>();
+  }
+  if (!a->W0 || !a->H0) {
+    FB_TRY(upload_seeds(p, a->seeds, a->batch));
+    FB_CUDA(p, p->rnd.ensure(sizeof(float) * (size_t) (a->batch * u_stride)));
+    launch_mt_uniform(p, p->seeds.as<int64_t>(), a->batch, u_stride, p->rnd.as<float>());
+    U = p->rnd.as<float>();
+  }
+  t.mark(1);
+  launch_nmf_init(p, d, U, u_stride, dW0, dH0, 0);
+  t.mark(2);
+  int32_t st = run_nmf_loop(p, d, a->iterations, a->update_w != 0, a->update_h != 0, a->progress, a->progress_user,
+                            a->progress_stride);
+  if (st < 0) return st;
+  const bool cancelled = st == FB200_CANCELLED;
+  t.mark(3);
+  // outputs (NMF.hpp:127-133); cancelled -> V1 = X (:176 skips :182)
+  auto export_arr = [&](const float* src, int64_t s_b, int64_t s_r, void* user, int64_t rows, int64_t cols, DevBuf& tmp) -> int32_t {
+    size_t bytes = es * (size_t) (a->batch * rows * cols);
+    void* dst = user;
+    if (a->mem == FB200_HOST) { FB_CUDA(p, tmp.ensure(bytes)); dst = tmp.p; }
+    launch_copy3d(p, src, FB200_F32, s_b, s_r, dst, a->dtype, rows * cols, cols, a->batch, rows, cols, nullptr, 0);
+    if (a->mem == FB200_HOST) FB_CUDA(p, cudaMemcpyAsync(user, dst, bytes, cudaMemcpyDeviceToHost, p->stream));
+    return FB200_OK;
+  };
+  if (a->W1) FB_TRY(export_arr(d.W, (int64_t) d.KP * d.Bp, d.Bp, a->W1, K, B, p->out_a));
+  if (a->H1) FB_TRY(export_arr(d.H, (int64_t) d.Fp * d.KP, d.KP, a->H1, F, K, p->out_b));
+  if (a->V1) {
+    size_t bytes = es * (size_t) (a->batch * F * B);
+    if (cancelled) {
+      if (a->V1 != a->X) {
+        if (a->mem == FB200_HOST) std::memcpy(a->V1, a->X, bytes);
+        else FB_CUDA(p, cudaMemcpyAsync(a->V1, a->X, bytes, cudaMemcpyDeviceToDevice, p->stream));
+      }
+    } else {
+      void* dst = a->V1;
+      if (a->mem == FB200_HOST) { FB_CUDA(p, p->stage.ensure(bytes)); dst = p->stage.p; }
+      launch_vhat(p, d, dst, a->dtype);
+      if (a->mem == FB200_HOST) FB_CUDA(p, cudaMemcpyAsync(a->V1, dst, bytes, cudaMemcpyDeviceToHost, p->stream));
+    }
+  }
+  t.mark(4);
+  FB_TRY(finish(p, t, 4));
+  p->stats.ms_h2d = t.ms(0, 1); p->stats.ms_init = t.ms(1, 2); p->stats.ms_nmf = t.ms(2, 3); p->stats.ms_d2h = t.ms(3, 4);
+  return cancelled ? FB200_CANCELLED : FB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+int32_t fb200_nmf_process_frames(fb200_plan* p, const fb200_frames_args* a)
+{
+  if (!p) return FB200_ERR_INVALID;
+  if (!a || a->struct_size != sizeof(fb200_frames_args) || !a->X || !a->W0 || a->frames <= 0 || a->bins <= 0 ||
+      a->rank <= 0 || a->iterations < 0 || (!a->H && !a->V)) {
+    p->err = "fb200_nmf_process_frames: bad arguments";
+    return FB200_ERR_INVALID;
+  }
+  FB_CUDA(p, cudaSetDevice(p->cfg.device));
+  StageTimer t(p);
+  t.mark(0);
+  NmfDev d{};
+  d.batch = 1; d.F = (int) a->frames; d.B = (int) a->bins; d.K = a->rank; d.clamp_v = 1;
+  FB_TRY(alloc_nmf(p, d));
+  const int64_t F = d.F, B = d.B, K = d.K;
+  const size_t es = dsize(a->dtype);
+  const void* d_x;
+  FB_TRY(to_device_raw(p, a->X, a->mem, es * (size_t) (F * B), p->stage, &d_x));
+  FB_CUDA(p, cudaMemsetAsync(d.V, 0, sizeof(float) * (size_t) d.Fp * d.Bp, p->stream));
+  launch_copy3d(p, d_x, a->dtype, F * B, B, d.V, FB200_F32, (int64_t) d.Fp * d.Bp, d.Bp, 1, F, B, nullptr, 0);
+  const void* raw_w;
+  FB_TRY(to_device_raw(p, a->W0, a->mem, es * (size_t) (K * B), p->out_a, &raw_w));
+  FB_CUDA(p, p->cspec.ensure(sizeof(float) * (size_t) (K * B)));
+  launch_copy3d(p, raw_w, a->dtype, K * B, B, p->cspec.p, FB200_F32, K * B, B, 1, K, B, nullptr, 0);
+  int64_t seed = a->seed;
+  FB_TRY(upload_seeds(p, &seed, 1));
+  FB_CUDA(p, p->rnd.ensure(sizeof(float) * (size_t) K));
+  launch_mt_uniform(p, p->seeds.as<int64_t>(), 1, K, p->rnd.as<float>());
+  t.mark(1);
+  launch_nmf_init(p, d, p->rnd.as<float>(), K, p->cspec.as<float>(), nullptr, 1); // NMF.hpp:55-64
+  t.mark(2);
+  if (a->iterations > 0) simt_launch_tile(p, d, 1, 0, a->iterations);            // NMF.hpp:72-83
+  t.mark(3);
+  auto export_arr = [&](const float* src, int64_t s_r, void* user, int64_t rows, int64_t cols, DevBuf& tmp) -> int32_t {
+    size_t bytes = es * (size_t) (rows * cols);
+    void* dst = user;
+    if (a->mem == FB200_HOST) { FB_CUDA(p, tmp.ensure(bytes)); dst = tmp.p; }
+    launch_copy3d(p, src, FB200_F32, 0, s_r, dst, a->dtype, 0, cols, 1, rows, cols, nullptr, 0);
+    if (a->mem == FB200_HOST) FB_CUDA(p, cudaMemcpyAsync(user, dst, bytes, cudaMemcpyDeviceToHost, p->stream));
+    return FB200_OK;
+  };
+  if (a->H) FB_TRY(export_arr(d.H, d.KP, a->H, F, K, p->out_b));
+  if (a->W_norm) FB_TRY(export_arr(d.W, d.Bp, a->W_norm, K, B, p->out_a));
+  if (a->V) {
+    size_t bytes = es * (size_t) (F * B);
+    void* dst = a->V;
+    if (a->mem == FB200_HOST) { FB_CUDA(p, p->stage.ensure(bytes)); dst = p->stage.p; }
+    launch_vhat(p, d, dst, a->dtype);
+    if (a->mem == FB200_HOST) FB_CUDA(p, cudaMemcpyAsync(a->V, dst, bytes, cudaMemcpyDeviceToHost, p->stream));
+  }
+  t.mark(4);
+  FB_TRY(finish(p, t, 4));
+  p->stats.ms_h2d = t.ms(0, 1); p->stats.ms_init = t.ms(1, 2); p->stats.ms_nmf = t.ms(2, 3); p->stats.ms_d2h = t.ms(3, 4);
+  return FB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+int32_t fb200_bufnmf(fb200_plan* p, const fb200_bufnmf_args* a)
+{
+  if (!p) return FB200_ERR_INVALID;
+  if (!a || a->struct_size != sizeof(fb200_bufnmf_args) || !a->audio || a->batch <= 0 || a->n_samples <= 0 ||
+      a->rank <= 0 || a->iterations < 0 || a->bases_mode < 0 || a->bases_mode > 2 || a->acts_mode < 0 || a->acts_mode > 2) {
+    p->err = "fb200_bufnmf: bad arguments";
+    return FB200_ERR_INVALID;
+  }
+  // NMFClient.hpp:134-136, 164-167: seed/fixed modes need the corresponding buffer
+  if ((a->bases_mode > 0 && !a->bases_in) || (a->acts_mode > 0 && !a->acts_in)) {
+    p->err = "Bases/Activations mode set to Seed or Fix, but no buffer supplied";
+    return FB200_ERR_INVALID;
+  }
+  const bool fix_w = a->bases_mode == 2, fix_h = a->acts_mode == 2;
+  const bool needs_analysis = !(fix_w && fix_h);                        // :141
+  const bool resynth = a->resynth_out != nullptr;
+  if (!needs_analysis && !resynth) {                                     // :143-145
+    p->err = "Bases and Activations buffers both fixed, but resynthesis disabled: no work to do";
+    return FB200_WARN_NO_WORK;
+  }
+  FB_CUDA(p, cudaSetDevice(p->cfg.device));
+  StageTimer t(p);
+  t.mark(0);
+  const int64_t batch = a->batch, n = a->n_samples;
+  const int64_t F = fb200_num_frames(n, p->win, p->hop);
+  NmfDev d{};
+  d.batch = (int) batch; d.F = (int) F; d.B = p->bins; d.K = a->rank;
+  FB_TRY(alloc_nmf(p, d));
+  const int64_t B = d.B, K = d.K;
+  const int host = a->mem == FB200_HOST;
+
+  // audio in (float32, NMFClient.hpp:240)
+  const void* d_audio;
+  FB_TRY(to_device_raw(p, a->audio, a->mem, sizeof(float) * (size_t) (batch * n), p->audio, &d_audio));
+  const float* dW0 = nullptr; const float* dH0 = nullptr; const float* U = nullptr;
+  if (a->bases_mode > 0) {                                               // :248-252
+    const void* raw;
+    FB_TRY(to_device_raw(p, a->bases_in, a->mem, sizeof(float) * (size_t) (batch * K * B), p->out_a, &raw));
+    dW0 = (const float*) raw;
+  }
+  if (a->acts_mode > 0) {                                                // :253-257
+    const void* raw;
+    FB_TRY(to_device_raw(p, a->acts_in, a->mem, sizeof(float) * (size_t) (batch * F * K), p->out_b, &raw));
+    dH0 = (const float*) raw;
+  }
+  const int64_t u_stride = std::max(B * K, K * F);
+  if (!dW0 || !dH0) {
+    FB_TRY(upload_seeds(p, a->seeds, batch));
+    FB_CUDA(p, p->rnd.ensure(sizeof(float) * (size_t) (batch * u_stride)));
+  }
+  t.mark(1);
+  // STFT + |X|  (:241-242)
+  FB_CUDA(p, cudaMemsetAsync(d.V, 0, sizeof(float) * (size_t) d.batch * d.Fp * d.Bp, p->stream));
+  float2* spec_all = nullptr;
+  if (resynth) {
+    FB_CUDA(p, p->spec.ensure(sizeof(float2) * (size_t) (batch * F * B)));
+    spec_all = p->spec.as<float2>();
+  }
+  FB_TRY(run_stft(p, (const float*) d_audio, batch, n, F, d.V, d.Fp, d.Bp, spec_all, p->win / 2));
+  t.mark(2);
+  if (!dW0 || !dH0) {
+    launch_mt_uniform(p, p->seeds.as<int64_t>(), batch, u_stride, p->rnd.as<float>());
+    U = p->rnd.as<float>();
+  }
+  launch_nmf_init(p, d, U, u_stride, dW0, dH0, 0);
+  t.mark(3);
+  int32_t st = run_nmf_loop(p, d, a->iterations * (needs_analysis ? 1 : 0), !fix_w, !fix_h, a->progress,
+                            a->progress_user, a->progress_stride);      // :268-271
+  if (st < 0) return st;
+  t.mark(4);
+  if (st == FB200_CANCELLED) {                                           // :273-274
+    FB_TRY(finish(p, t, 4));
+    return FB200_CANCELLED;
+  }
+  // bases / activations out  (:277-300).  The seed uploads in out_a/out_b are consumed by now.
+  if (a->bases_out && !fix_w) {
+    size_t bytes = sizeof(float) * (size_t) (batch * K * B);
+    void* dst = a->bases_out;
+    if (host) { FB_CUDA(p, p->out_a.ensure(bytes)); dst = p->out_a.p; }
+    launch_copy3d(p, d.W, FB200_F32, (int64_t) d.KP * d.Bp, d.Bp, dst, FB200_F32, K * B, B, batch, K, B, nullptr, 0);
+    if (host) FB_CUDA(p, cudaMemcpyAsync(a->bases_out, dst, bytes, cudaMemcpyDeviceToHost, p->stream));
+  }
+  if (a->acts_out && !fix_h) {
+    size_t bytes = sizeof(float) * (size_t) (batch * F * K);
+    FB_CUDA(p, p->scale.ensure(sizeof(float) * (size_t) batch));
+    launch_h_max_scale(p, d, p->scale.as<float>());
+    void* dst = a->acts_out;
+    if (host) { FB_CUDA(p, p->out_b.ensure(bytes)); dst = p->out_b.p; }
+    launch_copy3d(p, d.H, FB200_F32, (int64_t) d.Fp * d.KP, d.KP, dst, FB200_F32, F * K, K, batch, F, K, p->scale.as<float>(), 0);
+    if (host) FB_CUDA(p, cudaMemcpyAsync(a->acts_out, dst, bytes, cudaMemcpyDeviceToHost, p->stream));
+  }
+  t.mark(5);
+  // resynthesis (:302-333): rank masked spectra per channel -> ISTFT
+  if (resynth) {
+    int64_t wave = std::max<int64_t>(1, wave_size(p, F, batch * K, 1) / K);
+    wave = std::min(wave, batch);
+    FB_CUDA(p, p->cspec.ensure(sizeof(float2) * (size_t) (wave * K * F * B)));
+    float* dst_all = a->resynth_out;
+    if (host) { FB_CUDA(p, p->stage.ensure(sizeof(float) * (size_t) (wave * K * n))); }
+    for (int64_t b0 = 0; b0 < batch; b0 += wave) {
+      int64_t nb = std::min(wave, batch - b0);
+      launch_mask(p, d, spec_all, b0, nb, p->cspec.as<float2>());
+      float* dst = host ? p->stage.as<float>() : dst_all + b0 * K * n;
+      FB_TRY(run_istft(p, p->cspec.as<float2>(), nb * K, F, n, dst, p->win / 2));
+      if (host) {
+        FB_CUDA(p, cudaMemcpyAsync(a->resynth_out + b0 * K * n, dst, sizeof(float) * (size_t) (nb * K * n), cudaMemcpyDeviceToHost, p->stream));
+        FB_CUDA(p, cudaStreamSynchronize(p->stream)); // staging buffer is reused by the next wave
+      }
+    }
+  }
+  t.mark(6);
+  FB_TRY(finish(p, t, 6));
+  p->stats.ms_h2d = t.ms(0, 1); p->stats.ms_stft = t.ms(1, 2); p->stats.ms_init = t.ms(2, 3); p->stats.ms_nmf = t.ms(3, 4);
+  p->stats.ms_post = t.ms(4, 5); p->stats.ms_resynth = t.ms(5, 6);
+  return FB200_OK;
+}
+
+int32_t fb200_nmf_filter(fb200_plan* p, const fb200_filter_args* a)
+{
+  if (!p) return FB200_ERR_INVALID;
+  (void) a;
+  p->err = "fb200_nmf_filter: not implemented yet";
+  return FB200_ERR_UNSUPPORTED;
+}
+
+const fb200_api* fb200_get_api(uint32_t abi_version)
+{
+  static const fb200_api api = {FB200_ABI_VERSION, (uint32_t) sizeof(fb200_api), fb200_device_count, fb200_plan_create,
+                                fb200_plan_destroy, fb200_last_error, fb200_num_frames, fb200_resolve_fft,
+                                fb200_shard_range, fb200_stft, fb200_istft, fb200_nmf_process, fb200_nmf_process_frames,
+                                fb200_bufnmf, fb200_nmf_filter, fb200_get_stats};
+  return abi_version == FB200_ABI_VERSION ? &api : nullptr;
+}
+
+} // extern "C"

@@ -1,0 +1,162 @@
+// Internal declarations shared by the translation units of libflucoma_b200.so.  Not part of the ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <cufft.h>
+#include <stdint.h>
+#include <map>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/flucoma_b200.h"
+
+namespace fb200 {
+
+constexpr float kEps = 2.220446049250313e-16f; // algorithms/util/AlgorithmUtils.hpp:19 (DBL_EPSILON), rounded to fp32
+
+inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+inline int rank_pad(int k)
+{ // compile-time rank variants of the update kernels; pad rows of W / columns of H are exact zeros
+  int kp = 4;
+  while (kp < k) kp <<= 1;
+  return kp;
+}
+
+// growable device allocation
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes)
+  {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e == cudaSuccess) cap = bytes;
+    return e;
+  }
+  void release()
+  {
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+  }
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct HostBuf { // pinned staging
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes)
+  {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr; cap = 0;
+    cudaError_t e = cudaMallocHost(&p, bytes);
+    if (e == cudaSuccess) cap = bytes;
+    return e;
+  }
+  void release()
+  {
+    if (p) cudaFreeHost(p);
+    p = nullptr; cap = 0;
+  }
+};
+
+// Device-side problem descriptor of one batched NMF factorisation (all fp32, zero padded).
+//   V [batch][Fp][Bp]   magnitudes, frames-major (== the reference's X[F][B] and its column-major B x F "V")
+//   W [batch][KP][Bp]   dictionary rows  (== column-major B x K "W" == output W1[K][B])
+//   H [batch][Fp][KP]   activations     (== column-major K x F "H" == output H1[F][K])
+struct NmfDev {
+  float* V; float* W; float* H;
+  float* hden;      // [batch][KP]       sum_b W[k][b]      (NMF.hpp:169)
+  float* wnum_part; // [batch][ctas][KP][Bp] per-CTA partials of (V/WH) H^T  (NMF.hpp:159)
+  float* wden_part; // [batch][ctas][KP]     per-CTA partials of sum_f H[f][k] (NMF.hpp:160)
+  int batch, F, B, K;
+  int Fp, Bp, KP;
+  int ctas_per_buf;   // grid.x of the tile kernel
+  int tiles_per_cta;  // consecutive 128-frame tiles handled by one CTA
+  int clamp_v;        // processFrame clamps the input magnitudes at eps (NMF.hpp:60)
+  int shared_w;       // 1: a single W (batch stride 0) shared by all buffers (processFrame path)
+};
+
+struct Plan {
+  fb200_config cfg{};
+  int win = 0, hop = 0, fft = 0, bins = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[10]{};
+  std::string err;
+  fb200_stats stats{};
+  int64_t launches = 0, launches_nmf = 0;
+  int sm_count = 148;
+  uint32_t attr_mask = 0; // which k_nmf_tile<KP> variants already have their dynamic-smem attribute set
+
+  DevBuf window;   // float[win]
+  DevBuf audio;    // float [batch][n]
+  DevBuf stage;    // raw upload/download staging (caller dtype)
+  DevBuf frames;   // float [wave*F][fft]  cuFFT real side
+  DevBuf spec;     // float2 [batch][F][B] (kept when resynthesis is requested) or [wave][F][B]
+  DevBuf cspec;    // float2 [wave][K][F][B] masked component spectra
+  DevBuf V, W, H, hden, wnum_part, wden_part, rnd, seeds, scale, out_a, out_b;
+  HostBuf pin_a, pin_b;
+  std::map<std::pair<int, int64_t>, cufftHandle> fft_plans; // (type, batch) -> handle
+
+  bool fail(int code, const std::string& msg) { err = msg; last_code = code; return false; }
+  int last_code = 0;
+};
+
+// error plumbing ------------------------------------------------------------------------------------------------
+#define FB_CUDA(plan, expr)                                                                                  \
+  do {                                                                                                       \
+    cudaError_t _e = (expr);                                                                                 \
+    if (_e != cudaSuccess) {                                                                                 \
+      (plan)->err = std::string("CUDA error: ") + cudaGetErrorString(_e) + " at " #expr;                     \
+      return FB200_ERR_CUDA;                                                                                 \
+    }                                                                                                        \
+  } while (0)
+
+#define FB_CUFFT(plan, expr)                                                                                 \
+  do {                                                                                                       \
+    cufftResult _r = (expr);                                                                                 \
+    if (_r != CUFFT_SUCCESS) {                                                                               \
+      (plan)->err = std::string("cuFFT error ") + std::to_string((int) _r) + " at " #expr;                   \
+      return FB200_ERR_CUFFT;                                                                                \
+    }                                                                                                        \
+  } while (0)
+
+#define FB_TRY(expr)                                                                                         \
+  do {                                                                                                       \
+    int32_t _s = (expr);                                                                                     \
+    if (_s < 0) return _s;                                                                                   \
+  } while (0)
+
+// kernels_util.cu -----------------------------------------------------------------------------------------------
+// dst[b][i][j] = scale_b * src[b][i][j] for i < rows, j < cols; element strides given per array. Converts dtype.
+void launch_copy3d(Plan* p, const void* src, int src_dtype, int64_t s_b, int64_t s_r, void* dst, int dst_dtype,
+                   int64_t d_b, int64_t d_r, int64_t batch, int64_t rows, int64_t cols, const float* scale_per_batch,
+                   int clamp_eps);
+// U[b][i] = i-th draw of uniform[0,1) from mt19937_64(seeds[b])  (EigenRandom.hpp:73-110 on libstdc++)
+void launch_mt_uniform(Plan* p, const int64_t* d_seeds, int64_t batch, int64_t count, float* U);
+// W/H initialisation: random or seeded, eps clamp, W row / H column L2 normalisation, hden (NMF.hpp:101-124,150-153)
+void launch_nmf_init(Plan* p, const NmfDev& d, const float* U, int64_t u_stride, const float* W0, const float* H0,
+                     int frame_mode);
+// per-buffer max over the real H entries -> scale[b] = 1/max  (NMFClient.hpp:289-291)
+void launch_h_max_scale(Plan* p, const NmfDev& d, float* scale);
+
+// kernels_nmf_simt.cu -------------------------------------------------------------------------------------------
+int32_t simt_configure(Plan* p, NmfDev& d); // chooses tiling, sizes partial buffers
+void simt_launch_tile(Plan* p, const NmfDev& d, int do_h, int do_w, int h_iters);
+void simt_launch_w_finalize(Plan* p, const NmfDev& d);
+// Vhat[b][f][bin] = sum_k H W  -> dst (dtype, dense [batch][F][B])
+void launch_vhat(Plan* p, const NmfDev& d, void* dst, int dst_dtype);
+
+// kernels_stft.cu -----------------------------------------------------------------------------------------------
+void launch_hann(Plan* p);
+void launch_frame_window(Plan* p, const float* audio, int64_t n, int64_t nbuf, int64_t F, float* frames, int half);
+// spec [nbuf*F][B] complex -> V[nbuf][Fp][Bp] magnitudes (+ zero imag of DC/Nyquist in place, FFT.hpp:99-101)
+void launch_magnitude(Plan* p, float2* spec, int64_t nbuf, int64_t F, float* V, int64_t Fp, int64_t Bp);
+// masked component spectra for buffers [b0, b0+nb): cspec[nb][K][F][B]  (NMF.hpp:33-42 + RatioMask.hpp:33-57)
+void launch_mask(Plan* p, const NmfDev& d, const float2* spec, int64_t b0, int64_t nb, float2* cspec);
+// overlap-add + normalise + trim (STFT.hpp:178-199): y [nsig][F][fft] -> out [nsig][n]
+void launch_ola(Plan* p, const float* y, int64_t nsig, int64_t F, int64_t n, float* out, int half);
+
+} // namespace fb200

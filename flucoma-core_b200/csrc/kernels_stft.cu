@@ -1,0 +1,166 @@
+// STFT / ISTFT side kernels: Hann table, frame gather + window, |X|, ratio masks, overlap-add.
+// cuFFT (R2C / C2R, batched) sits between them and is the only library call on the path.
+#include "common.cuh"
+
+namespace fb200 {
+
+// WindowFuncs.hpp:41-45 -- periodic Hann evaluated in fp64, rounded once to fp32
+__global__ void k_hann(float* __restrict__ w, int win)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < win) w[i] = (float) (0.5 - 0.5 * cos((3.14159265358979323846 * 2.0 * (double) i) / (double) win));
+}
+
+void launch_hann(Plan* p)
+{
+  k_hann<<<(p->win + 255) / 256, 256, 0, p->stream>>>(p->window.as<float>(), p->win);
+  p->launches++;
+}
+
+// STFT.hpp:92-105: frame i of buffer b = padded[i*hop : i*hop+win] * window, padded = [win/2 zeros | audio | zeros];
+// written zero-extended to `fft` samples (FFT.hpp:97: htl::rfft zero-pads a short input).
+// `half` is the left padding: win/2 for STFT::process, win for the streaming clients (BufferedProcess.hpp:75-93).
+__global__ void __launch_bounds__(256) k_frame_window(const float* __restrict__ audio, int64_t n, int64_t nbuf, int64_t F,
+                                                      const float* __restrict__ window, int win, int fft, int hop,
+                                                      int half, float* __restrict__ frames)
+{
+  int64_t total = nbuf * F * (int64_t) (fft / 4);
+  for (int64_t e = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; e < total; e += (int64_t) gridDim.x * blockDim.x) {
+    int j4 = (int) (e % (fft / 4));
+    int64_t fr = e / (fft / 4);
+    int64_t i = fr % F, b = fr / F;
+    const float* a = audio + b * n;
+    float o[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      int j = 4 * j4 + q;
+      int64_t t = i * hop + j - half;
+      o[q] = (j < win && t >= 0 && t < n) ? a[t] * window[j] : 0.f;
+    }
+    *reinterpret_cast<float4*>(frames + fr * fft + 4 * j4) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+void launch_frame_window(Plan* p, const float* audio, int64_t n, int64_t nbuf, int64_t F, float* frames, int half)
+{
+  int64_t total = nbuf * F * (int64_t) (p->fft / 4);
+  if (total <= 0) return;
+  int grid = (int) std::min<int64_t>((total + 255) / 256, (int64_t) p->sm_count * 32);
+  k_frame_window<<<grid, 256, 0, p->stream>>>(audio, n, nbuf, F, p->window.as<float>(), p->win, p->fft, p->hop, half, frames);
+  p->launches++;
+}
+
+// STFT.hpp:61-66 |X|, with Im(DC) = Im(Nyquist) = 0 as FFT.hpp:99-101 leaves them.  spec [nbuf*F][B] -> V [nbuf][Fp][Bp]
+__global__ void __launch_bounds__(256) k_magnitude(float2* __restrict__ spec, int64_t nbuf, int64_t F, int B,
+                                                   float* __restrict__ V, int64_t Fp, int64_t Bp)
+{
+  int64_t total = nbuf * F * B;
+  for (int64_t e = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; e < total; e += (int64_t) gridDim.x * blockDim.x) {
+    int bin = (int) (e % B);
+    int64_t fr = e / B;
+    int64_t f = fr % F, b = fr / F;
+    float2 x = spec[e];
+    if (bin == 0 || bin == B - 1) {
+      x.y = 0.f;
+      spec[e] = x;
+    }
+    if (V) V[(b * Fp + f) * Bp + bin] = hypotf(x.x, x.y);
+  }
+}
+
+void launch_magnitude(Plan* p, float2* spec, int64_t nbuf, int64_t F, float* V, int64_t Fp, int64_t Bp)
+{
+  int64_t total = nbuf * F * p->bins;
+  if (total <= 0) return;
+  int grid = (int) std::min<int64_t>((total + 255) / 256, (int64_t) p->sm_count * 32);
+  k_magnitude<<<grid, 256, 0, p->stream>>>(spec, nbuf, F, p->bins, V, Fp, Bp);
+  p->launches++;
+}
+
+// NMF::estimate (NMF.hpp:33-42) + RatioMask::init/process with exponent 1 (RatioMask.hpp:33-57), all components at once:
+//   out_k[f][b] = S[f][b] * min(1, H[f][k] W[k][b] * (1 / max(sum_j H[f][j] W[j][b], eps)))
+// spec holds buffers [0, batch); this launch handles [b0, b0+nb) and writes cspec[nb][K][F][B].
+template <int KMAX>
+__global__ void __launch_bounds__(256) k_mask(NmfDev d, const float2* __restrict__ spec, int64_t b0, int64_t nb,
+                                              float2* __restrict__ cspec)
+{
+  extern __shared__ float hs[]; // [8][KP] activations of the 8 frames of this block
+  const int B = d.B, K = d.K, KP = d.KP;
+  const int64_t F = d.F;
+  int64_t bl = blockIdx.y;           // buffer within the wave
+  int64_t buf = b0 + bl;
+  int64_t f0 = (int64_t) blockIdx.x * 8;
+  const float* __restrict__ W = d.W + (d.shared_w ? (int64_t) 0 : buf * KP * d.Bp);
+  const float* __restrict__ H = d.H + (buf * d.Fp + f0) * KP;
+  int nf = (int) min((int64_t) 8, F - f0);
+  for (int e = threadIdx.x; e < 8 * KP; e += 256) hs[e] = e < nf * KP ? H[e] : 0.f;
+  __syncthreads();
+  for (int bin = threadIdx.x; bin < B; bin += 256) {
+    float w[KMAX];
+#pragma unroll
+    for (int k = 0; k < KMAX; k++) w[k] = k < K ? W[(int64_t) k * d.Bp + bin] : 0.f;
+    for (int i = 0; i < nf; i++) {
+      float v = 0.f;
+#pragma unroll
+      for (int k = 0; k < KMAX; k++) v = fmaf(hs[i * KP + (k < KP ? k : 0)], w[k], v);
+      float mult = 1.0f / fmaxf(v, kEps);
+      float2 s = spec[(buf * F + f0 + i) * B + bin];
+#pragma unroll
+      for (int k = 0; k < KMAX; k++) {
+        if (k < K) {
+          float m = fminf(1.0f, hs[i * KP + k] * w[k] * mult);
+          cspec[((bl * K + k) * F + f0 + i) * B + bin] = make_float2(s.x * m, s.y * m);
+        }
+      }
+    }
+  }
+}
+
+void launch_mask(Plan* p, const NmfDev& d, const float2* spec, int64_t b0, int64_t nb, float2* cspec)
+{
+  dim3 grid((unsigned) ((d.F + 7) / 8), (unsigned) nb);
+  size_t smem = sizeof(float) * 8 * d.KP;
+  if (d.KP <= 4) k_mask<4><<<grid, 256, smem, p->stream>>>(d, spec, b0, nb, cspec);
+  else if (d.KP <= 8) k_mask<8><<<grid, 256, smem, p->stream>>>(d, spec, b0, nb, cspec);
+  else if (d.KP <= 16) k_mask<16><<<grid, 256, smem, p->stream>>>(d, spec, b0, nb, cspec);
+  else if (d.KP <= 32) k_mask<32><<<grid, 256, smem, p->stream>>>(d, spec, b0, nb, cspec);
+  else k_mask<64><<<grid, 256, smem, p->stream>>>(d, spec, b0, nb, cspec);
+  p->launches++;
+}
+
+// ISTFT::process (STFT.hpp:178-199) as a gather: sample t of signal s sums the <= ceil(win/hop) frames covering
+// padded position t+half, each * (1/fft) * window, then / max(sum window^2, eps).  y [nsig][F][fft] (cuFFT C2R output).
+__global__ void __launch_bounds__(256) k_ola(const float* __restrict__ y, int64_t nsig, int64_t F, int64_t n,
+                                             const float* __restrict__ window, int win, int fft, int hop, int half,
+                                             float* __restrict__ out)
+{
+  int64_t total = nsig * n;
+  const float scale = 1.0f / (float) fft;
+  for (int64_t e = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; e < total; e += (int64_t) gridDim.x * blockDim.x) {
+    int64_t t = e % n, s = e / n;
+    int64_t pos = t + half;
+    int64_t i_hi = pos / hop;
+    if (i_hi > F - 1) i_hi = F - 1;
+    int64_t i_lo = pos - win + 1 <= 0 ? 0 : (pos - win + hop) / hop; // ceil((pos-win+1)/hop)
+    float acc = 0.f, nrm = 0.f;
+    const float* ys = y + s * F * fft;
+    for (int64_t i = i_lo; i <= i_hi; i++) {
+      int j = (int) (pos - i * hop);
+      float w = window[j];
+      acc = fmaf(ys[i * fft + j] * scale, w, acc);
+      nrm = fmaf(w, w, nrm);
+    }
+    out[e] = acc / fmaxf(nrm, kEps);
+  }
+}
+
+void launch_ola(Plan* p, const float* y, int64_t nsig, int64_t F, int64_t n, float* out, int half)
+{
+  int64_t total = nsig * n;
+  if (total <= 0) return;
+  int grid = (int) std::min<int64_t>((total + 255) / 256, (int64_t) p->sm_count * 32);
+  k_ola<<<grid, 256, 0, p->stream>>>(y, nsig, F, n, p->window.as<float>(), p->win, p->fft, p->hop, half, out);
+  p->launches++;
+}
+
+} // namespace fb200

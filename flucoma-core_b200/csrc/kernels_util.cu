@@ -1,0 +1,210 @@
+// Utility kernels: strided dtype-converting copies, device-side mt19937_64, W/H initialisation, activation scaling.
+#include "common.cuh"
+
+namespace fb200 {
+
+// ------------------------------------------------------------------------------------------------------------
+// copy3d
+// ------------------------------------------------------------------------------------------------------------
+template <class S, class D>
+__global__ void __launch_bounds__(256) k_copy3d(const S* __restrict__ src, int64_t s_b, int64_t s_r, D* __restrict__ dst,
+                                                int64_t d_b, int64_t d_r, int64_t batch, int64_t rows, int64_t cols,
+                                                const float* __restrict__ scale, int clamp_eps)
+{
+  int64_t total = batch * rows * cols;
+  for (int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; i < total; i += (int64_t) gridDim.x * blockDim.x) {
+    int64_t j = i % cols;
+    int64_t r = (i / cols) % rows;
+    int64_t b = i / (cols * rows);
+    float v = (float) src[b * s_b + r * s_r + j];
+    if (clamp_eps) v = fmaxf(v, kEps);
+    if (scale) v *= scale[b];
+    dst[b * d_b + r * d_r + j] = (D) v;
+  }
+}
+
+void launch_copy3d(Plan* p, const void* src, int src_dtype, int64_t s_b, int64_t s_r, void* dst, int dst_dtype,
+                   int64_t d_b, int64_t d_r, int64_t batch, int64_t rows, int64_t cols, const float* scale, int clamp_eps)
+{
+  int64_t total = batch * rows * cols;
+  if (total <= 0) return;
+  int grid = (int) std::min<int64_t>((total + 255) / 256, (int64_t) p->sm_count * 16);
+  if (src_dtype == FB200_F32 && dst_dtype == FB200_F32)
+    k_copy3d<float, float><<<grid, 256, 0, p->stream>>>((const float*) src, s_b, s_r, (float*) dst, d_b, d_r, batch, rows, cols, scale, clamp_eps);
+  else if (src_dtype == FB200_F64 && dst_dtype == FB200_F32)
+    k_copy3d<double, float><<<grid, 256, 0, p->stream>>>((const double*) src, s_b, s_r, (float*) dst, d_b, d_r, batch, rows, cols, scale, clamp_eps);
+  else if (src_dtype == FB200_F32 && dst_dtype == FB200_F64)
+    k_copy3d<float, double><<<grid, 256, 0, p->stream>>>((const float*) src, s_b, s_r, (double*) dst, d_b, d_r, batch, rows, cols, scale, clamp_eps);
+  else
+    k_copy3d<double, double><<<grid, 256, 0, p->stream>>>((const double*) src, s_b, s_r, (double*) dst, d_b, d_r, batch, rows, cols, scale, clamp_eps);
+  p->launches++;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// mt19937_64 + libstdc++ uniform_real_distribution<double>(0,1): value = double(raw) / 2^64, 1.0 -> nextafter(1,0).
+// algorithms/util/EigenRandom.hpp:73-110.  One thread per seed (sequential generator); the twist of the 312-word
+// state lives in local memory.  Cheap next to the update loop (B*K draws per buffer).
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) k_mt_uniform(const int64_t* __restrict__ seeds, int64_t batch, int64_t count,
+                                                   float* __restrict__ U)
+{
+  int64_t b = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  unsigned long long mt[312];
+  mt[0] = (unsigned long long) seeds[b];
+  for (int i = 1; i < 312; i++) mt[i] = 6364136223846793005ULL * (mt[i - 1] ^ (mt[i - 1] >> 62)) + (unsigned long long) i;
+  int idx = 312;
+  float* out = U + b * count;
+  for (int64_t n = 0; n < count; n++) {
+    if (idx >= 312) {
+      for (int i = 0; i < 312; i++) {
+        int i1 = i + 1 == 312 ? 0 : i + 1;
+        int im = i + 156 >= 312 ? i + 156 - 312 : i + 156;
+        unsigned long long x = (mt[i] & 0xFFFFFFFF80000000ULL) | (mt[i1] & 0x7FFFFFFFULL);
+        mt[i] = mt[im] ^ (x >> 1) ^ ((x & 1ULL) ? 0xB5026F5AA96619E9ULL : 0ULL);
+      }
+      idx = 0;
+    }
+    unsigned long long x = mt[idx++];
+    x ^= (x >> 29) & 0x5555555555555555ULL;
+    x ^= (x << 17) & 0x71D67FFFEDA60000ULL;
+    x ^= (x << 37) & 0xFFF7EEE000000000ULL;
+    x ^= (x >> 43);
+    double r = __ull2double_rn(x) * 5.42101086242752217e-20; // 2^-64
+    if (r >= 1.0) r = 0.99999999999999989;
+    out[n] = (float) r;
+  }
+}
+
+void launch_mt_uniform(Plan* p, const int64_t* d_seeds, int64_t batch, int64_t count, float* U)
+{
+  if (batch <= 0 || count <= 0) return;
+  k_mt_uniform<<<(unsigned) ((batch + 31) / 32), 32, 0, p->stream>>>(d_seeds, batch, count, U);
+  p->launches++;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// NMF initialisation.  NMF.hpp:101-124 (random: column-major fill, W and H both restart the stream; or seeds),
+// :150-153 (eps clamp, W column / H row L2 normalise -- in our layouts: rows of W[KP][Bp], columns of H[Fp][KP]).
+// Pad entries (k >= K, b >= B, f >= F) are exact zeros and stay zero under the updates.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_init_w(NmfDev d, const float* __restrict__ U, int64_t u_stride,
+                                                const float* __restrict__ W0)
+{
+  int buf = blockIdx.x;
+  float* W = d.W + (int64_t) buf * d.KP * d.Bp;
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int k = warp; k < d.KP; k += 8) {
+    float* row = W + (int64_t) k * d.Bp;
+    float ss = 0.f;
+    for (int b = lane; b < d.Bp; b += 32) {
+      float w = 0.f;
+      if (k < d.K && b < d.B) {
+        w = W0 ? W0[((int64_t) buf * d.K + k) * d.B + b] : U[(int64_t) buf * u_stride + (int64_t) k * d.B + b];
+        w = fmaxf(w, kEps);
+      }
+      row[b] = w;
+      ss += w * w;
+    }
+    for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    float inv = ss > 0.f ? 1.0f / sqrtf(ss) : 0.f;
+    float sum = 0.f;
+    for (int b = lane; b < d.Bp; b += 32) {
+      float w = row[b] * inv;
+      row[b] = w;
+      sum += w;
+    }
+    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0) d.hden[(int64_t) buf * d.KP + k] = sum;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_init_h(NmfDev d, const float* __restrict__ U, int64_t u_stride,
+                                                const float* __restrict__ H0)
+{
+  __shared__ float red[256];
+  __shared__ float inv[64];
+  int buf = blockIdx.x;
+  float* H = d.H + (int64_t) buf * d.Fp * d.KP;
+  int64_t total = (int64_t) d.Fp * d.KP;
+  int k = threadIdx.x % d.KP; // 256 % KP == 0, so a thread always sees the same column
+  float ss = 0.f;
+  for (int64_t e = threadIdx.x; e < total; e += 256) {
+    int64_t f = e / d.KP;
+    float h = 0.f;
+    if (k < d.K && f < d.F) {
+      h = H0 ? H0[((int64_t) buf * d.F + f) * d.K + k] : U[(int64_t) buf * u_stride + f * d.K + k];
+      h = fmaxf(h, kEps);
+    }
+    H[e] = h;
+    ss += h * h;
+  }
+  red[threadIdx.x] = ss;
+  __syncthreads();
+  if (threadIdx.x < d.KP) {
+    float s = 0.f;
+    for (int t = threadIdx.x; t < 256; t += d.KP) s += red[t];
+    inv[threadIdx.x] = s > 0.f ? 1.0f / sqrtf(s) : 0.f;
+  }
+  __syncthreads();
+  float sc = inv[k];
+  for (int64_t e = threadIdx.x; e < total; e += 256) H[e] *= sc;
+}
+
+// processFrame: every frame starts from the same h0 = max(U(K), eps), not normalised (NMF.hpp:55,59)
+__global__ void __launch_bounds__(256) k_init_h_frames(NmfDev d, const float* __restrict__ U)
+{
+  int64_t total = (int64_t) d.batch * d.Fp * d.KP;
+  for (int64_t e = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; e < total; e += (int64_t) gridDim.x * blockDim.x) {
+    int k = (int) (e % d.KP);
+    int64_t f = (e / d.KP) % d.Fp;
+    d.H[e] = (k < d.K && f < d.F) ? fmaxf(U[k], kEps) : 0.f;
+  }
+}
+
+void launch_nmf_init(Plan* p, const NmfDev& d, const float* U, int64_t u_stride, const float* W0, const float* H0,
+                     int frame_mode)
+{
+  int nW = d.shared_w ? 1 : d.batch;
+  k_init_w<<<nW, 256, 0, p->stream>>>(d, U, u_stride, W0);
+  p->launches++;
+  if (frame_mode) {
+    int64_t total = (int64_t) d.batch * d.Fp * d.KP;
+    int grid = (int) std::min<int64_t>((total + 255) / 256, (int64_t) p->sm_count * 16);
+    k_init_h_frames<<<grid, 256, 0, p->stream>>>(d, U);
+  } else {
+    k_init_h<<<d.batch, 256, 0, p->stream>>>(d, U, u_stride, H0);
+  }
+  p->launches++;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// scale[b] = 1 / max_{f<F,k<K} H   (NMFClient.hpp:289-291)
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_h_max_scale(NmfDev d, float* __restrict__ scale)
+{
+  __shared__ float red[256];
+  int buf = blockIdx.x;
+  const float* H = d.H + (int64_t) buf * d.Fp * d.KP;
+  int64_t total = (int64_t) d.F * d.KP;
+  float m = -INFINITY;
+  for (int64_t e = threadIdx.x; e < total; e += 256) {
+    int k = (int) (e % d.KP);
+    if (k < d.K) m = fmaxf(m, H[e]);
+  }
+  red[threadIdx.x] = m;
+  __syncthreads();
+  for (int s = 128; s; s >>= 1) {
+    if (threadIdx.x < s) red[threadIdx.x] = fmaxf(red[threadIdx.x], red[threadIdx.x + s]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) scale[buf] = (float) (1.0 / (double) red[0]);
+}
+
+void launch_h_max_scale(Plan* p, const NmfDev& d, float* scale)
+{
+  k_h_max_scale<<<d.batch, 256, 0, p->stream>>>(d, scale);
+  p->launches++;
+}
+
+} // namespace fb200

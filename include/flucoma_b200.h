@@ -1,0 +1,212 @@
+/*
+ * flucoma_b200.h -- C ABI of libflucoma_b200.so: the B200 (sm_100a) implementation of flucoma-core's
+ * STFT -> |X| -> NMF multiplicative updates -> ratio-mask -> ISTFT hot path, batched over many buffers.
+ *
+ * This is the drop-in boundary.  Plain C, plain pointers and sizes, no C++/torch types.
+ * Every entry point names the reference interface it replaces; paths are relative to
+ * /root/reference/include/flucoma.  INTEGRATION.md shows the reference-side binding.
+ *
+ * Conventions
+ *   - All matrices are dense row-major in the reference's own FluidTensor orientation:
+ *       X / V / magnitude [F][B], spectrum [F][B] interleaved (re,im), W / bases [K][B], H / activations [F][K],
+ *     with a leading batch axis (buffers or channels).  F = frames (nWindows), B = bins = fft/2+1, K = rank.
+ *   - dtype: host/device element type of the caller's arrays (FB200_F32 or FB200_F64).  The device always computes
+ *     in fp32 (tensor-core operands are split-bf16 pairs, accumulate fp32); FB200_F64 arrays are converted on the
+ *     device.  The reference computes in fp64; agreement is to 1e-4 relative (tests/test_gpu_parity.py).
+ *   - mem: where the caller's arrays live.  FB200_HOST pointers are copied by the library (pinned staging inside
+ *     the plan); FB200_DEVICE pointers must be on the plan's device and are used in place.
+ *   - Every call is synchronous: outputs are complete when it returns.
+ *   - Return value: 0 ok, >0 warning, <0 error (fb200_status).  fb200_last_error() gives the text.  No exceptions
+ *     or CUDA/cuFFT errors escape (reference convention: Result{Status,msg}, clients/common/Result.hpp:21-81).
+ *   - A plan binds one device and one stream; calls on distinct plans are thread-safe, one plan is not re-entrant
+ *     (same rule as one client instance: clients/common/FluidNRTClientWrapper.hpp:868-872).
+ *   - The library never retains caller pointers after a call returns.
+ */
+#ifndef FLUCOMA_B200_H
+#define FLUCOMA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FB200_ABI_VERSION 1u
+
+#if defined(_WIN32)
+#define FB200_API __declspec(dllexport)
+#else
+#define FB200_API __attribute__((visibility("default")))
+#endif
+
+typedef enum fb200_status {
+  FB200_OK = 0,
+  FB200_WARN_NO_WORK = 1,       /* NMFClient.hpp:143-145 "no work to do" */
+  FB200_CANCELLED = 2,          /* Result::Status::kCancelled (progress callback returned 0) */
+  FB200_ERR_INVALID = -1,       /* bad argument / shape (the reference asserts or returns kError) */
+  FB200_ERR_CUDA = -2,
+  FB200_ERR_CUFFT = -3,
+  FB200_ERR_NOMEM = -4,
+  FB200_ERR_UNSUPPORTED = -5,
+  FB200_ERR_NO_DEVICE = -6
+} fb200_status;
+
+typedef enum fb200_dtype { FB200_F32 = 0, FB200_F64 = 1 } fb200_dtype;
+typedef enum fb200_mem { FB200_HOST = 0, FB200_DEVICE = 1 } fb200_mem;
+
+/* NMF update engine. AUTO picks TCGEN05 when the shape qualifies, else SIMT. */
+typedef enum fb200_backend { FB200_BACKEND_AUTO = 0, FB200_BACKEND_SIMT = 1, FB200_BACKEND_TCGEN05 = 2 } fb200_backend;
+
+typedef struct fb200_plan fb200_plan; /* opaque; owns device memory, cuFFT plans, stream, pinned staging */
+
+/* Replaces the constructor arguments of algorithm::STFT / ISTFT (algorithms/public/STFT.hpp:36-47,154-164) and the
+ * FFTParams size rules (clients/common/ParameterTypes.hpp:295-313): hop <= 0 -> win/2, fft < 0 -> nextPow2(win). */
+typedef struct fb200_config {
+  uint32_t struct_size;   /* = sizeof(fb200_config) */
+  int32_t device;         /* CUDA ordinal */
+  int32_t win, hop, fft;  /* window, hop, fft size (fft must be a power of two >= win) */
+  int32_t max_rank;       /* largest K any call will use */
+  int64_t max_batch;      /* largest number of buffers/channels per call */
+  int64_t max_samples;    /* largest samples per buffer (or, for frame APIs, max_frames = fb200_num_frames()) */
+  int32_t backend;        /* fb200_backend */
+  int32_t reserved;
+} fb200_config;
+
+/* progress callback: NMF::addProgressCallback (algorithms/public/NMF.hpp:31,136-139,175-176).
+ * Called with iteration 1..n (host thread, between device launches); return 0 to cancel. */
+typedef int (*fb200_progress_fn)(void* user, int64_t iteration);
+
+/* ---- plan management ------------------------------------------------------------------------------------- */
+FB200_API uint32_t fb200_abi_version(void);
+FB200_API int32_t fb200_device_count(void);
+FB200_API int32_t fb200_plan_create(const fb200_config* cfg, fb200_plan** out);
+FB200_API void fb200_plan_destroy(fb200_plan* plan);
+FB200_API const char* fb200_last_error(const fb200_plan* plan); /* plan may be NULL: last create error */
+
+/* size rules: ParameterTypes.hpp:295-313; NMFClient.hpp:111-113 / STFT.hpp:94-99 */
+FB200_API int64_t fb200_num_frames(int64_t n_samples, int32_t win, int32_t hop);
+FB200_API int32_t fb200_resolve_fft(int32_t win, int32_t hop, int32_t fft, int32_t* out_hop, int32_t* out_fft,
+                                    int32_t* out_bins);
+
+/* contiguous shard of `total` independent buffers owned by `rank` of `world` */
+FB200_API void fb200_shard_range(int64_t total, int32_t world, int32_t rank, int64_t* begin, int64_t* count);
+
+/* ---- STFT::process + STFT::magnitude  (STFT.hpp:90-108, 61-66) ---------------------------------------------- */
+/* audio [batch][n_samples] -> spectrum [batch][F][B] complex (may be NULL) and/or magnitude [batch][F][B] (may be NULL) */
+FB200_API int32_t fb200_stft(fb200_plan* plan, const void* audio, int64_t batch, int64_t n_samples, void* spectrum,
+                             void* magnitude, int32_t dtype, int32_t mem);
+
+/* ---- ISTFT::process  (STFT.hpp:178-199) -------------------------------------------------------------------- */
+/* spectrum [batch][n_frames][B] complex -> audio [batch][n_samples] */
+FB200_API int32_t fb200_istft(fb200_plan* plan, const void* spectrum, int64_t batch, int64_t n_frames, void* audio,
+                              int64_t n_samples, int32_t dtype, int32_t mem);
+
+/* ---- NMF::process  (algorithms/public/NMF.hpp:91-134, 144-183) ---------------------------------------------- */
+typedef struct fb200_nmf_args {
+  uint32_t struct_size;
+  int32_t dtype, mem;
+  int64_t batch, frames, bins;  /* X is [batch][frames][bins] */
+  int32_t rank, iterations;
+  int32_t update_w, update_h;   /* NMF.hpp:92-93 */
+  const void* X;                /* magnitudes, >= 0 */
+  const int64_t* seeds;         /* [batch] host array; seed < 0 -> nondeterministic (EigenRandom.hpp:14-17,80); NULL -> all -1 */
+  const void* W0;               /* optional [batch][rank][bins]  (NMF.hpp:94, 102-112); NULL -> random */
+  const void* H0;               /* optional [batch][frames][rank] (NMF.hpp:95, 114-124); NULL -> random */
+  void* W1;                     /* out [batch][rank][bins]   (may be NULL) */
+  void* H1;                     /* out [batch][frames][rank] (may be NULL) */
+  void* V1;                     /* out [batch][frames][bins] = W*H (may be NULL); untouched copy of X if cancelled */
+  fb200_progress_fn progress;   /* optional */
+  void* progress_user;
+  int32_t progress_stride;      /* iterations per host poll when progress != NULL (<=0 -> 1, the reference's cadence) */
+  int32_t reserved;
+} fb200_nmf_args;
+FB200_API int32_t fb200_nmf_process(fb200_plan* plan, const fb200_nmf_args* args);
+
+/* ---- NMF::processFrame over many frames, fixed dictionary  (NMF.hpp:45-89; NMFMatchClient.hpp:106-118) ------ */
+typedef struct fb200_frames_args {
+  uint32_t struct_size;
+  int32_t dtype, mem;
+  int64_t frames, bins;
+  int32_t rank, iterations;     /* NMFMatch hard-codes 10 (NMFMatchClient.hpp:115) */
+  int64_t seed;                 /* h0 = U(K) from this seed, identical for every frame when >= 0 */
+  const void* X;                /* [frames][bins] magnitudes */
+  const void* W0;               /* [rank][bins]; used as given (clamped + row-normalised internally, NMF.hpp:58,63-64) */
+  void* W_norm;                 /* optional out [rank][bins]: the mutated W0 the reference leaves behind */
+  void* H;                      /* out [frames][rank] */
+  void* V;                      /* optional out [frames][bins] = W^T h (NMF.hpp:88) */
+} fb200_frames_args;
+FB200_API int32_t fb200_nmf_process_frames(fb200_plan* plan, const fb200_frames_args* args);
+
+/* ---- BufNMF: NMFClient::process per channel  (clients/nrt/NMFClient.hpp:233-335) ---------------------------- */
+typedef struct fb200_bufnmf_args {
+  uint32_t struct_size;
+  int32_t mem;                  /* audio & outputs are float32, like BufferAdaptor (BufferAdaptor.hpp:49-66) */
+  int64_t batch, n_samples;     /* `batch` channels/buffers of equal length, planar [batch][n_samples] */
+  int32_t rank, iterations;
+  int32_t bases_mode, acts_mode; /* 0 none / 1 seed / 2 fixed (NMFClient.hpp:63-67) */
+  const float* audio;
+  const int64_t* seeds;         /* [batch] host; NULL -> -1 */
+  const float* bases_in;        /* [batch][rank][bins] when bases_mode > 0 */
+  const float* acts_in;         /* [batch][frames][rank] when acts_mode > 0 */
+  float* bases_out;             /* [batch][rank][bins]; not written when bases_mode == 2 (NMFClient.hpp:277) */
+  float* acts_out;              /* [batch][frames][rank], scaled by 1/max(H) per channel (:289-298); not written when acts_mode == 2 */
+  float* resynth_out;           /* optional [batch][rank][n_samples] (:302-333) */
+  fb200_progress_fn progress;
+  void* progress_user;
+  int32_t progress_stride;
+  int32_t reserved;
+} fb200_bufnmf_args;
+FB200_API int32_t fb200_bufnmf(fb200_plan* plan, const fb200_bufnmf_args* args);
+
+/* ---- NMFFilter over a stream  (clients/rt/NMFFilterClient.hpp:98-117 + BufferedProcess.hpp:187-241) ---------- */
+/* audio [n_samples] mono stream -> out [rank][n_samples], the `rank` masked resyntheses, as the streaming client
+ * produces them but without its `win` samples of latency (frame f covers [f*hop-win, f*hop)). */
+typedef struct fb200_filter_args {
+  uint32_t struct_size;
+  int32_t mem;
+  int64_t n_samples;
+  int32_t rank, iterations;
+  int64_t seed;
+  const float* audio;
+  const float* bases;           /* [rank][bins] */
+  float* out;                   /* [rank][n_samples] */
+  float* acts_out;              /* optional [frames][rank] (what NMFMatch would output) */
+} fb200_filter_args;
+FB200_API int32_t fb200_nmf_filter(fb200_plan* plan, const fb200_filter_args* args);
+
+/* ---- instrumentation (bench.py roofline) ------------------------------------------------------------------- */
+typedef struct fb200_stats {
+  float ms_h2d, ms_stft, ms_init, ms_nmf, ms_post, ms_resynth, ms_d2h, ms_total; /* CUDA-event times of the last call */
+  int64_t launches_total;   /* kernels of this library launched by the last call (cuFFT launches counted as 1 per exec) */
+  int64_t launches_nmf;     /* ... of which NMF update-loop kernels */
+  int32_t backend_used;     /* fb200_backend actually run */
+  int32_t reserved;
+} fb200_stats;
+FB200_API int32_t fb200_get_stats(const fb200_plan* plan, fb200_stats* out);
+
+/* ---- dlsym'd function table (north_star: "one .so, dlsym'd function table") -------------------------------- */
+typedef struct fb200_api {
+  uint32_t abi_version;
+  uint32_t struct_size;
+  int32_t (*device_count)(void);
+  int32_t (*plan_create)(const fb200_config*, fb200_plan**);
+  void (*plan_destroy)(fb200_plan*);
+  const char* (*last_error)(const fb200_plan*);
+  int64_t (*num_frames)(int64_t, int32_t, int32_t);
+  int32_t (*resolve_fft)(int32_t, int32_t, int32_t, int32_t*, int32_t*, int32_t*);
+  void (*shard_range)(int64_t, int32_t, int32_t, int64_t*, int64_t*);
+  int32_t (*stft)(fb200_plan*, const void*, int64_t, int64_t, void*, void*, int32_t, int32_t);
+  int32_t (*istft)(fb200_plan*, const void*, int64_t, int64_t, void*, int64_t, int32_t, int32_t);
+  int32_t (*nmf_process)(fb200_plan*, const fb200_nmf_args*);
+  int32_t (*nmf_process_frames)(fb200_plan*, const fb200_frames_args*);
+  int32_t (*bufnmf)(fb200_plan*, const fb200_bufnmf_args*);
+  int32_t (*nmf_filter)(fb200_plan*, const fb200_filter_args*);
+  int32_t (*get_stats)(const fb200_plan*, fb200_stats*);
+} fb200_api;
+/* returns NULL when abi_version is not supported */
+FB200_API const fb200_api* fb200_get_api(uint32_t abi_version);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLUCOMA_B200_H */

@@ -1,0 +1,286 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (ctypes -> libflucoma_b200.so), against the fp64 oracle.
+
+Tolerance (BASELINE.json north_star): 1e-4 relative on W, H and the resynthesis; we measure it as the Frobenius-relative
+error per buffer, ||gpu - oracle|| / ||oracle||, because individual near-zero entries of W/H carry no relative meaning.
+The GPU computes in fp32 (the reference in fp64), so the STFT stage is held to 2e-6 and the long iterations to 1e-4.
+Run on the B200 box:  python -m pytest tests -m gpu -x -q
+"""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4
+
+
+def rel(a, b):
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+@pytest.fixture(scope="module")
+def fb():
+    import flucoma_b200
+    flucoma_b200.load()
+    assert flucoma_b200.device_count() >= 1, "no CUDA device: the product path has no CPU fallback"
+    return flucoma_b200
+
+
+@pytest.fixture(scope="module")
+def synth():
+    from tests.golden.make_golden import synth_audio
+    return synth_audio
+
+
+# ------------------------------------------------------------------------------------------------ STFT / ISTFT
+@pytest.mark.parametrize("n,win,fft,hop", [(3000, 256, 256, 64), (3000, 200, 256, 50), (1000, 128, 512, 128),
+                                           (5, 64, 64, 16), (130816, 1024, 1024, 256)])
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_stft_parity(fb, oracle, n, win, fft, hop, dt):
+    rng = np.random.default_rng(n)
+    x = rng.standard_normal((3, n)).astype(dt)
+    with fb.Plan(win=win, hop=hop, fft=fft) as plan:
+        spec, mag = plan.stft(x, want_spectrum=True, want_magnitude=True)
+    F = oracle.num_frames(n, win, hop)
+    assert spec.shape == (3, F, fft // 2 + 1) and mag.shape == spec.shape
+    for b in range(3):
+        S = oracle.stft(x[b].astype(np.float64), win, fft, hop)
+        assert rel(spec[b], S) < 2e-6
+        assert rel(mag[b], np.abs(S)) < 2e-6
+    assert np.all(spec[..., 0].imag == 0) and np.all(spec[..., -1].imag == 0)  # FFT.hpp:99-101
+
+
+def test_stft_impulse_and_sine_kat(fb, oracle):
+    n, win = 4096, 1024
+    with fb.Plan(win=win, hop=256, fft=win) as plan:
+        x = np.zeros(n, np.float32); x[0] = 1.0
+        spec, _ = plan.stft(x)
+        assert np.allclose(np.abs(spec[0, 0]), oracle.hann(win)[win // 2], atol=1e-6)  # first frame centred on sample 0
+        k = 37
+        s = np.sin(2 * np.pi * k * np.arange(n) / win).astype(np.float32)
+        _, mag = plan.stft(s, want_spectrum=False, want_magnitude=True)
+        f = 6  # a frame fully inside the signal
+        assert abs(mag[0, f, k] - 0.25 * win) < 1e-2 and abs(mag[0, f, k + 1] - 0.125 * win) < 1e-2
+
+
+@pytest.mark.parametrize("win,hop", [(256, 64), (1024, 256), (1024, 512), (64, 32)])
+def test_stft_istft_identity(fb, win, hop):
+    n = 20000
+    x = np.random.default_rng(1).standard_normal((2, n)).astype(np.float32)
+    with fb.Plan(win=win, hop=hop, fft=win) as plan:
+        spec, _ = plan.stft(x)
+        y = plan.istft(spec, n)
+    assert np.abs(y - x).max() < 5e-6 * np.abs(x).max() * np.sqrt(win)
+
+
+def test_istft_parity(fb, oracle):
+    rng = np.random.default_rng(5)
+    F, win, hop = 40, 256, 64
+    S = (rng.standard_normal((2, F, 129)) + 1j * rng.standard_normal((2, F, 129)))
+    n = (F - 1) * hop
+    with fb.Plan(win=win, hop=hop, fft=win) as plan:
+        y64 = plan.istft(S, n)
+        y32 = plan.istft(S.astype(np.complex64), n)
+    for b in range(2):
+        ref = oracle.istft(S[b], win, win, hop, n)
+        assert rel(y64[b], ref) < 2e-6 and rel(y32[b], ref) < 2e-6
+
+
+# ------------------------------------------------------------------------------------------------ NMF::process
+def test_nmf_reference_test_replica(fb, oracle):
+    # tests/algorithms/public/TestNMF.cpp:11-46 through the C ABI
+    X = np.array([[1, 2, 3], [4, 5, 6], [7, 8, 9]], dtype=np.float64)
+    with fb.Plan(win=64) as plan:
+        r = [plan.nmf_process(X, 2, 1, True, True, seeds=s) for s in (42, 42, 5063, 5063)]
+    for i, j in ((0, 1), (2, 3)):
+        for a, b in zip(r[i][:3], r[j][:3]):
+            assert np.array_equal(a, b)
+    for a, b in zip(r[1][:3], r[2][:3]):
+        assert not np.array_equal(a, b)
+    for res, seed in ((r[0], 42), (r[2], 5063)):
+        W, H, V, _ = oracle.nmf_process(X, 2, 1, True, True, seed)
+        assert rel(res[0], W) < 1e-5 and rel(res[1], H) < 1e-5 and rel(res[2], V) < 1e-5
+    assert r[0][0].shape == (2, 3) and r[0][1].shape == (3, 2) and r[0][2].shape == (3, 3)
+
+
+@pytest.mark.parametrize("tag,uw,uh", [("wh", True, True), ("w", True, False), ("h", False, True)])
+def test_nmf_golden_small(fb, golden_dir, tag, uw, uh):
+    g = np.load(os.path.join(golden_dir, "nmf_small.npz"))
+    with fb.Plan(win=256, hop=64) as plan:
+        W, H, V, st = plan.nmf_process(g["mag"], 5, 40, uw, uh, seeds=3)
+        W32, H32, V32, _ = plan.nmf_process(g["mag"].astype(np.float32), 5, 40, uw, uh, seeds=3)
+    assert st == 0
+    assert rel(W, g[f"W_{tag}"]) < TOL and rel(H, g[f"H_{tag}"]) < TOL and rel(V, g[f"V_{tag}"]) < TOL
+    assert rel(W32, g[f"W_{tag}"]) < TOL and rel(H32, g[f"H_{tag}"]) < TOL
+
+
+def test_nmf_seeded_w0_h0(fb, golden_dir):
+    g = np.load(os.path.join(golden_dir, "nmf_small.npz"))
+    with fb.Plan(win=256, hop=64) as plan:
+        W, H, V, _ = plan.nmf_process(g["mag"], 5, 25, True, True, W0=g["W0"], H0=g["H0"])
+    assert rel(W, g["W_seeded"]) < TOL and rel(H, g["H_seeded"]) < TOL and rel(V, g["V_seeded"]) < TOL
+
+
+@pytest.mark.parametrize("F,B,K,iters", [(7, 5, 1, 3), (130, 33, 3, 20), (300, 257, 8, 30), (129, 513, 16, 30),
+                                         (64, 2049, 20, 10), (256, 129, 64, 10)])
+def test_nmf_shapes_vs_oracle(fb, oracle, F, B, K, iters):
+    rng = np.random.default_rng(F * 1000 + B)
+    kk = max(2, min(K, 6))
+    X = (rng.random((2, F, kk)) ** 3) @ (rng.random((2, kk, B)) ** 3) + 1e-3 * rng.random((2, F, B))
+    with fb.Plan(win=64) as plan:
+        W, H, V, _ = plan.nmf_process(X, K, iters, True, True, seeds=[11, 12])
+    for b in range(2):
+        Wo, Ho, Vo, _ = oracle.nmf_process(X[b], K, iters, True, True, 11 + b)
+        assert rel(W[b], Wo) < TOL and rel(H[b], Ho) < TOL and rel(V[b], Vo) < TOL
+
+
+def test_nmf_zero_iterations_and_no_updates(fb, oracle):
+    rng = np.random.default_rng(0)
+    X = rng.random((6, 5)); W0 = rng.random((2, 5)); H0 = rng.random((6, 2)); H0[0, 0] = 0.0
+    with fb.Plan(win=64) as plan:
+        W, H, V, _ = plan.nmf_process(X, 2, 0, True, True, W0=W0, H0=H0)
+        W2, H2, V2, _ = plan.nmf_process(X, 2, 5, False, False, W0=W0, H0=H0)
+    Wo, Ho, Vo, _ = oracle.nmf_process(X, 2, 0, True, True, -1, W0=W0, H0=H0)
+    for a, b in ((W, Wo), (H, Ho), (V, Vo), (W2, Wo), (H2, Ho), (V2, Vo)):
+        assert rel(a, b) < 1e-6
+    assert H[0, 0] > 0  # eps clamp (NMF.hpp:150)
+
+
+def test_nmf_progress_and_cancel(fb, oracle):
+    X = np.random.default_rng(0).random((40, 30))
+    seen = []
+    with fb.Plan(win=64) as plan:
+        W, H, V, st = plan.nmf_process(X, 3, 10, True, True, seeds=1, progress=lambda it: seen.append(it) or it < 4)
+        Wf, Hf, Vf, stf = plan.nmf_process(X, 3, 10, True, True, seeds=1, progress=lambda it: True)
+        Wn, Hn, Vn, _ = plan.nmf_process(X, 3, 10, True, True, seeds=1)
+    assert st == fb.CANCELLED and seen == [1, 2, 3, 4]
+    assert np.array_equal(V, X)  # NMF.hpp:175-176 skips :182
+    Wo, Ho, _, _ = oracle.nmf_process(X, 3, 4, True, True, 1)
+    assert rel(W, Wo) < TOL and rel(H, Ho) < TOL
+    assert stf == 0
+    # the fused schedule (no callback) and the per-iteration schedule agree
+    assert rel(Wf, Wn) < 1e-5 and rel(Hf, Hn) < 1e-5 and rel(Vf, Vn) < 1e-5
+
+
+def test_nmf_device_arrays_and_repeatability(fb, oracle):
+    import torch
+    rng = np.random.default_rng(9)
+    X = rng.random((4, 200, 65)).astype(np.float32)
+    Xd = torch.from_numpy(X).cuda()
+    with fb.Plan(win=128) as plan:
+        Wd, Hd, Vd, _ = plan.nmf_process(Xd, 4, 50, True, True, seeds=[1, 2, 3, 4])
+        Wh, Hh, Vh, _ = plan.nmf_process(X, 4, 50, True, True, seeds=[1, 2, 3, 4])
+        Wd2, Hd2, _, _ = plan.nmf_process(Xd, 4, 50, True, True, seeds=[1, 2, 3, 4])
+    assert Wd.is_cuda and np.array_equal(Wd.cpu().numpy(), Wh) and np.array_equal(Hd.cpu().numpy(), Hh)
+    assert torch.equal(Wd, Wd2) and torch.equal(Hd, Hd2)  # bitwise repeatable (TestNMF.cpp:31-39)
+    Wo, Ho, _, _ = oracle.nmf_process(X[2].astype(np.float64), 4, 50, True, True, 3)
+    assert rel(Wh[2], Wo) < TOL and rel(Hh[2], Ho) < TOL
+
+
+# ------------------------------------------------------------------------------------------------ NMF::processFrame
+def test_process_frames_parity(fb, oracle, golden_dir):
+    g = np.load(os.path.join(golden_dir, "nmf_small.npz"))
+    mags, W = g["mag"], g["W_wh"]
+    with fb.Plan(win=256, hop=64) as plan:
+        H, V, Wn = plan.nmf_process_frames(mags, W, 10, 42, want_v=True, want_w=True)
+        H0, _, _ = plan.nmf_process_frames(mags, W, 0, 42)
+    acts = oracle.nmfmatch_frames(mags, W, 10, 42)
+    assert rel(H, acts) < TOL
+    h, v, Wm = oracle.nmf_process_frame(mags[20], W, 10, 42)
+    assert rel(H[20], h) < TOL and rel(V[20], v) < TOL and rel(Wn, Wm) < 1e-6
+    assert rel(H[20], g["pf_h"]) < TOL
+    assert np.allclose(H0, np.maximum(oracle.random_uniform(42, 5), 2.2e-16)[None, :], rtol=1e-6)  # TestNMF.cpp:48-73
+
+
+def test_process_frame_reference_test_replica(fb):
+    x = np.array([[1, 0, 1, 0.0]]); W = np.array([[0, 0, 1, 0], [1, 0, 0, 0.0]])
+    with fb.Plan(win=64) as plan:
+        a, _, _ = plan.nmf_process_frames(x, W, 0, 42)
+        b, _, _ = plan.nmf_process_frames(x, W, 0, 42)
+        c, _, _ = plan.nmf_process_frames(x, W, 0, 7863)
+    assert np.array_equal(a, b) and not np.array_equal(b, c)
+
+
+# ------------------------------------------------------------------------------------------------ BufNMF
+def test_bufnmf_golden_wav(fb, golden_dir):
+    g = np.load(os.path.join(golden_dir, "bufnmf_wav.npz"))
+    with fb.Plan(win=1024, hop=256, fft=1024) as plan:
+        r = plan.bufnmf(g["audio"], 4, 100, seeds=42, resynth=True)
+        st = plan.stats()
+    assert r["status"] == 0
+    assert rel(r["bases"][0], g["bases"]) < TOL and rel(r["acts"][0], g["acts"]) < TOL
+    assert rel(r["resynth"][0], g["resynth"]) < TOL
+    assert r["acts"].max() == pytest.approx(1.0, abs=1e-6)
+    assert np.abs(r["resynth"][0].sum(0) - g["audio"]).max() < 1e-4  # masks sum to one
+    assert st["launches_nmf"] > 0 and st["launches_total"] > st["launches_nmf"]
+
+
+def test_bufnmf_batch_vs_oracle(fb, oracle, synth):
+    a = np.stack([synth(1000 + b, 9000) for b in range(5)])
+    with fb.Plan(win=512, hop=128, fft=512) as plan:
+        r = plan.bufnmf(a, 6, 60, seeds=[0, 1, 2, 3, 4], resynth=True)
+    for b in range(5):
+        o = oracle.bufnmf_channel(a[b], 512, 512, 128, 6, 60, b, resynth=True)
+        assert rel(r["bases"][b], o["bases"]) < TOL and rel(r["acts"][b], o["acts"]) < TOL
+        assert rel(r["resynth"][b], o["resynth"]) < TOL
+
+
+def test_bufnmf_seed_and_fixed_modes(fb, oracle, synth):
+    a = synth(1003, 8000)[None, :]
+    win, hop, K = 256, 64, 3
+    base = oracle.bufnmf_channel(a[0], win, win, hop, K, 30, 7)
+    with fb.Plan(win=win, hop=hop, fft=win) as plan:
+        r_fix = plan.bufnmf(a, K, 30, seeds=7, bases_mode=2, bases_in=base["bases"][None])
+        r_seed = plan.bufnmf(a, K, 30, seeds=7, bases_mode=1, bases_in=base["bases"][None], acts_mode=1,
+                             acts_in=base["acts"][None], resynth=True)
+        with pytest.raises(fb.FlucomaB200Error):
+            plan.bufnmf(a, K, 30, seeds=7, bases_mode=1)
+        r_none = plan.bufnmf(a, K, 30, seeds=7, bases_mode=2, bases_in=base["bases"][None], acts_mode=2,
+                             acts_in=base["acts"][None])
+    assert r_fix["bases"] is None
+    o_fix = oracle.bufnmf_channel(a[0], win, win, hop, K, 30, 7, bases_mode=2, bases_in=base["bases"])
+    assert rel(r_fix["acts"][0], o_fix["acts"]) < TOL
+    o_seed = oracle.bufnmf_channel(a[0], win, win, hop, K, 30, 7, bases_mode=1, bases_in=base["bases"], acts_mode=1,
+                                   acts_in=base["acts"], resynth=True)
+    assert rel(r_seed["bases"][0], o_seed["bases"]) < TOL and rel(r_seed["acts"][0], o_seed["acts"]) < TOL
+    assert rel(r_seed["resynth"][0], o_seed["resynth"]) < TOL
+    assert r_none["status"] == fb.WARN_NO_WORK  # NMFClient.hpp:143-145
+
+
+def test_bufnmf_device_memory_matches_host(fb, synth):
+    import torch
+    a = np.stack([synth(2000 + b, 6000) for b in range(3)])
+    with fb.Plan(win=256, hop=64, fft=256) as plan:
+        rh = plan.bufnmf(a, 4, 20, seeds=[5, 6, 7], resynth=True)
+        rd = plan.bufnmf(torch.from_numpy(a).cuda(), 4, 20, seeds=[5, 6, 7], resynth=True)
+    for k in ("bases", "acts", "resynth"):
+        assert np.array_equal(rd[k].cpu().numpy(), rh[k])
+
+
+# ------------------------------------------------------------------------------------------------ full size (config 2)
+def test_config2_full_size_properties(fb, oracle, synth):
+    """BASELINE config 2 shape (fft 1024, hop 256, F=512, K=16, 200 iters) at batch 128 on device memory:
+    size-independent properties + two buffers spot-checked against the oracle."""
+    import torch
+    batch, n, K, iters = 128, 130816, 16, 200
+    a = np.stack([synth(1000 + b, n) for b in range(8)])
+    a = np.concatenate([a] * (batch // 8))  # 8 distinct buffers repeated; NMF seeds differ per buffer
+    ad = torch.from_numpy(a).cuda()
+    with fb.Plan(win=1024, hop=256, fft=1024) as plan:
+        r = plan.bufnmf(ad, K, iters, seeds=np.arange(batch))
+        r2 = plan.bufnmf(ad[:4], K, iters, seeds=np.arange(4), resynth=True)
+    bases = r["bases"].cpu().numpy(); acts = r["acts"].cpu().numpy()
+    assert bases.shape == (batch, K, 513) and acts.shape == (batch, 512, K)
+    assert np.isfinite(bases).all() and np.isfinite(acts).all() and (bases >= 0).all() and (acts >= 0).all()
+    assert np.allclose(np.linalg.norm(bases.astype(np.float64), axis=2), 1.0, atol=1e-4)   # NMF.hpp:162
+    assert np.allclose(acts.reshape(batch, -1).max(1), 1.0, atol=1e-6)                    # NMFClient.hpp:289-298
+    # same audio + same seed => same factorisation regardless of the position in the batch
+    assert np.array_equal(r2["bases"].cpu().numpy(), bases[:4])
+    rs = r2["resynth"].cpu().numpy()
+    assert np.abs(rs.sum(1) - a[:4]).max() < 2e-4                                         # ratio masks sum to one
+    for b in (0, 3):
+        o = oracle.bufnmf_channel(a[b], 1024, 1024, 256, K, iters, b, resynth=True)
+        assert rel(bases[b], o["bases"]) < TOL and rel(acts[b], o["acts"]) < TOL
+        assert rel(rs[b], o["resynth"]) < TOL
