@@ -52,7 +52,7 @@ struct StageTimer {
   Plan* p;
   explicit StageTimer(Plan* pl) : p(pl)
   {
-    p->launches = 0; p->launches_nmf = 0;
+    p->launches = 0; p->launches_nmf = 0; p->kev_used = 0;
     std::memset(&p->stats, 0, sizeof(p->stats));
   }
   void mark(int i) { cudaEventRecord(p->ev[i], p->stream); }
@@ -203,6 +203,13 @@ int32_t finish(Plan* p, StageTimer& t, int last_ev)
   p->stats.launches_total = p->launches;
   p->stats.launches_nmf = p->launches_nmf;
   p->stats.backend_used = FB200_BACKEND_SIMT;
+  float sum = 0.f;
+  for (size_t i = 0; i + 1 < p->kev_used; i += 2) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, p->kev[i], p->kev[i + 1]) == cudaSuccess) sum += ms;
+  }
+  p->stats.ms_update_kernel = sum;
+  p->stats.update_kernel_launches = (int32_t) (p->kev_used / 2);
   return FB200_OK;
 }
 
@@ -294,6 +301,7 @@ void fb200_plan_destroy(fb200_plan* p)
   for (auto* b : bufs) b->release();
   p->pin_a.release(); p->pin_b.release();
   for (auto& e : p->ev) if (e) cudaEventDestroy(e);
+  for (auto& e : p->kev) cudaEventDestroy(e);
   if (p->stream) cudaStreamDestroy(p->stream);
   delete p;
 }

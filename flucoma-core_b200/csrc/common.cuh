@@ -88,6 +88,8 @@ struct Plan {
   fb200_stats stats{};
   int64_t launches = 0, launches_nmf = 0;
   int sm_count = 148;
+  std::vector<cudaEvent_t> kev; // event pairs around every update-kernel launch of the current call
+  size_t kev_used = 0;
   uint32_t attr_mask = 0; // which k_nmf_tile<KP> variants already have their dynamic-smem attribute set
 
   DevBuf window;   // float[win]

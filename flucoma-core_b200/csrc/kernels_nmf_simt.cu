@@ -357,8 +357,19 @@ int32_t simt_configure(Plan* p, NmfDev& d)
   return FB200_OK;
 }
 
+static cudaEvent_t next_kernel_event(Plan* p)
+{
+  if (p->kev_used == p->kev.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    p->kev.push_back(e);
+  }
+  return p->kev[p->kev_used++];
+}
+
 void simt_launch_tile(Plan* p, const NmfDev& d, int do_h, int do_w, int h_iters)
 {
+  cudaEventRecord(next_kernel_event(p), p->stream);
   switch (d.KP) {
   case 4: launch_tile_t<4>(p, d, do_h, do_w, h_iters); break;
   case 8: launch_tile_t<8>(p, d, do_h, do_w, h_iters); break;
@@ -366,6 +377,7 @@ void simt_launch_tile(Plan* p, const NmfDev& d, int do_h, int do_w, int h_iters)
   case 32: launch_tile_t<32>(p, d, do_h, do_w, h_iters); break;
   default: launch_tile_t<64>(p, d, do_h, do_w, h_iters); break;
   }
+  cudaEventRecord(next_kernel_event(p), p->stream);
   p->launches++; p->launches_nmf++;
 }
 

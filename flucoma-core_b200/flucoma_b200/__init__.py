@@ -68,7 +68,8 @@ class FilterArgs(C.Structure):
 class Stats(C.Structure):
     _fields_ = [(n, C.c_float) for n in ("ms_h2d", "ms_stft", "ms_init", "ms_nmf", "ms_post", "ms_resynth", "ms_d2h",
                                          "ms_total")] + [("launches_total", C.c_int64), ("launches_nmf", C.c_int64),
-                                                         ("backend_used", C.c_int32), ("reserved", C.c_int32)]
+                                                         ("backend_used", C.c_int32), ("update_kernel_launches", C.c_int32),
+                                                         ("ms_update_kernel", C.c_float), ("reserved", C.c_float)]
 
 
 # every symbol include/flucoma_b200.h declares (tests check the .so exports all of them)

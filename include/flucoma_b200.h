@@ -180,7 +180,9 @@ typedef struct fb200_stats {
   int64_t launches_total;   /* kernels of this library launched by the last call (cuFFT launches counted as 1 per exec) */
   int64_t launches_nmf;     /* ... of which NMF update-loop kernels */
   int32_t backend_used;     /* fb200_backend actually run */
-  int32_t reserved;
+  int32_t update_kernel_launches; /* launches of the dominant NMF update kernel (tile kernel) in the last call */
+  float ms_update_kernel;   /* sum of their device durations, each bracketed by CUDA events on the plan's stream */
+  float reserved;
 } fb200_stats;
 FB200_API int32_t fb200_get_stats(const fb200_plan* plan, fb200_stats* out);
 

@@ -48,7 +48,7 @@ def test_struct_sizes_match_header_layout(fb):
     assert C.sizeof(fb.NmfArgs) == 136
     assert C.sizeof(fb.FramesArgs) == 88
     assert C.sizeof(fb.BufNmfArgs) == 120
-    assert C.sizeof(fb.Stats) == 56
+    assert C.sizeof(fb.Stats) == 64
 
 
 def test_size_rules(fb, oracle):

@@ -16,7 +16,9 @@ TOL = 1e-4
 
 
 def rel(a, b):
-    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    a = np.asarray(a); b = np.asarray(b)
+    ct = np.complex128 if (np.iscomplexobj(a) or np.iscomplexobj(b)) else np.float64
+    a = a.astype(ct); b = b.astype(ct)
     return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
 
 
