@@ -206,7 +206,17 @@ __global__ void __launch_bounds__(NT) k_nmf_tile(NmfDev d, int do_h, int do_w, i
       for (int f = 0; f < TF; f++) s += Hs[f * KP + tid];
       d.wden_part[(int64_t) cta * KP + tid] = s;
     }
-    const int fs = tid % FS, bg = (tid / FS) & 15, kg = tid / (FS * 16);
+    // thread bit-fields (LSB first): bg_lo[3] fsl[log2 FSL] bg_hi[1] fsh[log2 FSH] kg[log2 KG].  Eight consecutive lanes
+    // read eight consecutive float4 of one R row (conflict free); up to four frame splits sit at lane strides 8/16 so
+    // their reduction is a warp shuffle; further splits (KP <= 8) are combined through shared memory.
+    constexpr int FSL = FS < 4 ? FS : 4;
+    constexpr int FSH = FS / FSL;
+    constexpr int LSH = FSL == 4 ? 2 : (FSL == 2 ? 1 : 0);
+    const int bg = (tid & 7) | (((tid >> (3 + LSH)) & 1) << 3);
+    const int fsl = (tid >> 3) & (FSL - 1);
+    const int rest = tid >> (4 + LSH);
+    const int fsh = rest % FSH, kg = rest / FSH;
+    const int fs = fsh * FSL + fsl;
     float* __restrict__ part = d.wnum_part + (int64_t) cta * KP * Bp;
     load_w_chunk_regs<KP>(W, Bp, 0, tid, wr);
     store_w_chunk<KP>(Wc, tid, wr);
@@ -238,12 +248,30 @@ __global__ void __launch_bounds__(NT) k_nmf_tile(NmfDev d, int do_h, int do_w, i
         }
       }
 #pragma unroll
-      for (int o = 1; o < FS; o <<= 1)
+      for (int o = 1; o < FSL; o <<= 1)
 #pragma unroll
         for (int kk = 0; kk < 4; kk++)
 #pragma unroll
-          for (int q = 0; q < 4; q++) a2[kk][q] += __shfl_xor_sync(0xffffffffu, a2[kk][q], o);
+          for (int q = 0; q < 4; q++) a2[kk][q] += __shfl_xor_sync(0xffffffffu, a2[kk][q], o * 8);
       int bin = c * BC + 4 * bg;
+      if (FSH > 1) { // combine the cross-warp frame splits through shared memory (the R tile is free after the sync)
+        __syncthreads();
+        float* red = Rt; // [FSH][KG][16 bg][16]
+        if (fsl == 0) {
+#pragma unroll
+          for (int kk = 0; kk < 4; kk++)
+            *reinterpret_cast<float4*>(red + ((fsh * KG + kg) * 16 + bg) * 16 + 4 * kk) = make_float4(a2[kk][0], a2[kk][1], a2[kk][2], a2[kk][3]);
+        }
+        __syncthreads();
+        if (fs == 0) {
+          for (int h = 1; h < FSH; h++)
+#pragma unroll
+            for (int kk = 0; kk < 4; kk++) {
+              float4 o4 = *reinterpret_cast<const float4*>(red + ((h * KG + kg) * 16 + bg) * 16 + 4 * kk);
+              a2[kk][0] += o4.x; a2[kk][1] += o4.y; a2[kk][2] += o4.z; a2[kk][3] += o4.w;
+            }
+        }
+      }
       if (fs == 0 && bin < Bp) {
 #pragma unroll
         for (int kk = 0; kk < 4; kk++)
