@@ -1,0 +1,65 @@
+"""C++17 host mirror of the reference interface (flucoma-core_b200/host/flucoma/...): containers on the CPU, the
+algorithm/client shims on the GPU (TestNMF.cpp replica compiled against our headers)."""
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST = os.path.join(ROOT, "flucoma-core_b200", "host")
+LIB = os.path.join(ROOT, "flucoma-core_b200", "lib", "libflucoma_b200.so")
+
+
+def compile_cpp(src, out):
+    cmd = ["/usr/bin/g++", "-std=c++17", "-O1", "-Wall", "-I", HOST, "-I", ROOT, os.path.join(ROOT, "tests", "cpp", src),
+           "-ldl", "-o", out]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return out
+
+
+def test_host_containers_cpu():
+    with tempfile.TemporaryDirectory() as t:
+        exe = compile_cpp("test_host_containers.cpp", os.path.join(t, "a"))
+        r = subprocess.run([exe], capture_output=True, text=True)
+        assert r.returncode == 0 and "host containers ok" in r.stdout, r.stdout + r.stderr
+
+
+def test_shims_compile_and_fail_loudly_without_gpu():
+    import torch
+    with tempfile.TemporaryDirectory() as t:
+        exe = compile_cpp("test_shims_gpu.cpp", os.path.join(t, "a"))
+        if torch.cuda.is_available():
+            pytest.skip("GPU present: covered by the gpu test")
+        r = subprocess.run([exe], capture_output=True, text=True, env=dict(os.environ, FLUCOMA_B200_LIB=LIB))
+        assert r.returncode != 0 and "no such CUDA device" in (r.stdout + r.stderr)  # no CPU fallback
+
+
+def _read_dump(path):
+    out = []
+    with open(path, "rb") as f:
+        for _ in range(4):
+            r, c = np.frombuffer(f.read(16), np.int64)
+            out.append(np.frombuffer(f.read(4 * r * c), np.float32).reshape(r, c))
+    return out
+
+
+@pytest.mark.gpu
+def test_shims_gpu_vs_oracle(oracle):
+    with tempfile.TemporaryDirectory() as t:
+        exe = compile_cpp("test_shims_gpu.cpp", os.path.join(t, "a"))
+        dump = os.path.join(t, "dump.bin")
+        r = subprocess.run([exe, dump], capture_output=True, text=True, env=dict(os.environ, FLUCOMA_B200_LIB=LIB))
+        assert r.returncode == 0 and "host shims ok" in r.stdout, r.stdout + r.stderr
+        src, bases, acts, res = _read_dump(dump)
+    n, chans = src.shape
+    rank = bases.shape[1] // chans
+    for c in range(chans):
+        o = oracle.bufnmf_channel(np.ascontiguousarray(src[:, c]), 256, 256, 64, rank, 30, 7, resynth=True)
+        for j in range(rank):
+            ch = c * rank + j  # NMFClient.hpp:277-300: component j of channel c lives in buffer channel c*rank+j
+            assert np.linalg.norm(bases[:, ch] - o["bases"][j]) / np.linalg.norm(o["bases"][j]) < 1e-4
+            assert np.linalg.norm(acts[:, ch] - o["acts"][:, j]) / np.linalg.norm(o["acts"][:, j]) < 1e-4
+            assert np.linalg.norm(res[:, ch] - o["resynth"][j]) / max(np.linalg.norm(o["resynth"][j]), 1e-12) < 1e-4
