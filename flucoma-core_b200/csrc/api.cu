@@ -656,6 +656,25 @@ int32_t fb200_nmf_filter(fb200_plan* p, const fb200_filter_args* a)
   return FB200_ERR_UNSUPPORTED;
 }
 
+int32_t fb200_selftest_tcgen05(fb200_plan* p, const float* in, int64_t n_in, float* out, int64_t n_out)
+{
+  if (!p) return FB200_ERR_INVALID;
+  const int64_t need_in = 128 * 16 + 16 * 64 + 128 * 64 + 16 * 128 + 64 * 16 + 128 * 64 + 128 * 68;
+  const int64_t need_out = 128 * 64 + 128 * 16 + 128 * 64 + 128 * 16 + 128 * 32;
+  if (!in || !out || n_in != need_in || n_out != need_out) { p->err = "fb200_selftest_tcgen05: bad sizes"; return FB200_ERR_INVALID; }
+  FB_CUDA(p, cudaSetDevice(p->cfg.device));
+  StageTimer t(p);
+  t.mark(0);
+  FB_CUDA(p, p->stage.ensure(sizeof(float) * (size_t) n_in));
+  FB_CUDA(p, p->out_a.ensure(sizeof(float) * (size_t) n_out));
+  FB_CUDA(p, cudaMemcpyAsync(p->stage.p, in, sizeof(float) * (size_t) n_in, cudaMemcpyHostToDevice, p->stream));
+  FB_CUDA(p, cudaMemsetAsync(p->out_a.p, 0, sizeof(float) * (size_t) n_out, p->stream));
+  FB_TRY(run_tc_selftest(p, p->stage.as<float>(), p->out_a.as<float>()));
+  FB_CUDA(p, cudaMemcpyAsync(out, p->out_a.p, sizeof(float) * (size_t) n_out, cudaMemcpyDeviceToHost, p->stream));
+  t.mark(1);
+  return finish(p, t, 1);
+}
+
 const fb200_api* fb200_get_api(uint32_t abi_version)
 {
   static const fb200_api api = {FB200_ABI_VERSION, (uint32_t) sizeof(fb200_api), fb200_device_count, fb200_plan_create,

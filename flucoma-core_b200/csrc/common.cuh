@@ -161,4 +161,8 @@ void launch_mask(Plan* p, const NmfDev& d, const float2* spec, int64_t b0, int64
 // overlap-add + normalise + trim (STFT.hpp:178-199): y [nsig][F][fft] -> out [nsig][n]
 void launch_ola(Plan* p, const float* y, int64_t nsig, int64_t F, int64_t n, float* out, int half);
 
+// kernels_tc_selftest.cu ---------------------------------------------------------------------------------------
+int32_t make_v_tensor_map(Plan* p, void* tmap_out, const float* V, int64_t Bp, int64_t Fp, int64_t batch, int box_rows);
+int32_t run_tc_selftest(Plan* p, const float* in, float* out);
+
 } // namespace fb200

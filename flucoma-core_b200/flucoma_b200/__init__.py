@@ -76,7 +76,7 @@ class Stats(C.Structure):
 SYMBOLS = ["fb200_abi_version", "fb200_device_count", "fb200_plan_create", "fb200_plan_destroy", "fb200_last_error",
            "fb200_num_frames", "fb200_resolve_fft", "fb200_shard_range", "fb200_stft", "fb200_istft",
            "fb200_nmf_process", "fb200_nmf_process_frames", "fb200_bufnmf", "fb200_nmf_filter", "fb200_get_stats",
-           "fb200_get_api"]
+           "fb200_get_api", "fb200_selftest_tcgen05"]
 
 _lib = None
 
@@ -122,6 +122,8 @@ def load(path: str | None = None):
         fn.argtypes = [C.c_void_p, C.POINTER(T)]
     L.fb200_get_stats.restype = C.c_int32
     L.fb200_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
+    L.fb200_selftest_tcgen05.restype = C.c_int32
+    L.fb200_selftest_tcgen05.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]
     L.fb200_get_api.restype = C.c_void_p
     L.fb200_get_api.argtypes = [C.c_uint32]
     if path is None:
@@ -224,6 +226,12 @@ class Plan:
         if _is_torch(x):
             return x.contiguous()
         return np.ascontiguousarray(x)
+
+    def selftest_tcgen05(self, inputs: "np.ndarray") -> "np.ndarray":
+        inp = np.ascontiguousarray(inputs, dtype=np.float32)
+        out = np.zeros(128 * 64 + 128 * 16 + 128 * 64 + 128 * 16 + 128 * 32, np.float32)
+        self._check(self._L.fb200_selftest_tcgen05(self._h, _ptr(inp), inp.size, _ptr(out), out.size))
+        return out
 
     # -- STFT::process (+ magnitude) -------------------------------------------------------------------------------
     def stft(self, audio, want_spectrum=True, want_magnitude=False):

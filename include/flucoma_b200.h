@@ -186,6 +186,11 @@ typedef struct fb200_stats {
 } fb200_stats;
 FB200_API int32_t fb200_get_stats(const fb200_plan* plan, fb200_stats* out);
 
+/* ---- diagnostics: exercises the tcgen05/TMEM/TMA building blocks of the tensor-core engine on small known matrices.
+ * in  (host float): H1[128x16] W1[16x64] R1[128x64] W2[16x128] H2[64x16] R2[128x64] V[128x68]   (n_in  = 31488)
+ * out (host float): H1*W1 [128x64], R1*W1^T [128x16], W2^T*H2^T [128x64], R2*H2 [128x16], V[:,32:64] [128x32] (n_out = 24576) */
+FB200_API int32_t fb200_selftest_tcgen05(fb200_plan* plan, const float* in, int64_t n_in, float* out, int64_t n_out);
+
 /* ---- dlsym'd function table (north_star: "one .so, dlsym'd function table") -------------------------------- */
 typedef struct fb200_api {
   uint32_t abi_version;
