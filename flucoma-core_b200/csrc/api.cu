@@ -52,7 +52,7 @@ struct StageTimer {
   Plan* p;
   explicit StageTimer(Plan* pl) : p(pl)
   {
-    p->launches = 0; p->launches_nmf = 0; p->kev_used = 0;
+    p->launches = 0; p->launches_nmf = 0; p->kev_used = 0; p->backend_used = FB200_BACKEND_SIMT;
     std::memset(&p->stats, 0, sizeof(p->stats));
   }
   void mark(int i) { cudaEventRecord(p->ev[i], p->stream); }
@@ -153,6 +153,15 @@ int32_t run_nmf_loop(Plan* p, NmfDev& d, int iters, bool upd_w, bool upd_h, fb20
       if (!progress(user, it)) return FB200_CANCELLED;
     return FB200_OK;
   }
+  // tensor-core engine: whole loop in one persistent launch (no per-iteration host polling, hence no callbacks)
+  if (!progress && p->cfg.backend != FB200_BACKEND_SIMT && tc_eligible(d)) {
+    p->backend_used = FB200_BACKEND_TCGEN05;
+    return tc_run(p, d, iters, upd_w, upd_h);
+  }
+  if (p->cfg.backend == FB200_BACKEND_TCGEN05) {
+    p->err = "FB200_BACKEND_TCGEN05 requested but the shape does not qualify (rank 16, bins = 128k+1 <= 513, frames <= 512, no callback)";
+    return FB200_ERR_UNSUPPORTED;
+  }
   if (upd_w) FB_TRY(alloc_partials(p, d));
   if (progress) {
     // exact per-iteration state so that a cancel leaves W,H as the reference would: no cross-iteration fusion
@@ -202,7 +211,7 @@ int32_t finish(Plan* p, StageTimer& t, int last_ev)
   p->stats.ms_total = t.ms(0, last_ev);
   p->stats.launches_total = p->launches;
   p->stats.launches_nmf = p->launches_nmf;
-  p->stats.backend_used = FB200_BACKEND_SIMT;
+  p->stats.backend_used = p->backend_used;
   float sum = 0.f;
   for (size_t i = 0; i + 1 < p->kev_used; i += 2) {
     float ms = 0.f;

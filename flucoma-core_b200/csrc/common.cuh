@@ -90,6 +90,7 @@ struct Plan {
   int sm_count = 148;
   std::vector<cudaEvent_t> kev; // event pairs around every update-kernel launch of the current call
   size_t kev_used = 0;
+  int backend_used = FB200_BACKEND_SIMT; // engine that ran the update loop of the current call
   uint32_t attr_mask = 0; // which k_nmf_tile<KP> variants already have their dynamic-smem attribute set
 
   DevBuf window;   // float[win]
@@ -164,5 +165,9 @@ void launch_ola(Plan* p, const float* y, int64_t nsig, int64_t F, int64_t n, flo
 // kernels_tc_selftest.cu ---------------------------------------------------------------------------------------
 int32_t make_v_tensor_map(Plan* p, void* tmap_out, const float* V, int64_t Bp, int64_t Fp, int64_t batch, int box_rows);
 int32_t run_tc_selftest(Plan* p, const float* in, float* out);
+
+// kernels_nmf_tc.cu ---------------------------------------------------------------------------------------------
+bool tc_eligible(const NmfDev& d);
+int32_t tc_run(Plan* p, const NmfDev& d, int iters, bool upd_w, bool upd_h);
 
 } // namespace fb200

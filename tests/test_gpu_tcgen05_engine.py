@@ -1,0 +1,70 @@
+"""GPU tests of the tcgen05 NMF engine (kernels_nmf_tc.cu) forced through FB200_BACKEND_TCGEN05: parity against the
+fp64 oracle (1e-4 Frobenius-relative, the north_star bar), agreement with the SIMT engine, repeatability."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def rel(a, b):
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+@pytest.fixture(scope="module")
+def fb():
+    import flucoma_b200
+    return flucoma_b200
+
+
+def lowrank(rng, batch, F, B, kk=6):
+    return (rng.random((batch, F, kk)) ** 3) @ (rng.random((batch, kk, B)) ** 3) + 1e-3 * rng.random((batch, F, B))
+
+
+@pytest.mark.parametrize("F,B,iters,uw,uh", [(128, 129, 5, True, True), (200, 257, 20, True, True), (512, 513, 30, True, True),
+                                             (384, 513, 12, True, False), (256, 513, 12, False, True), (130, 513, 1, True, True)])
+def test_tc_engine_vs_oracle(fb, oracle, F, B, iters, uw, uh):
+    rng = np.random.default_rng(F + B)
+    X = lowrank(rng, 3, F, B)
+    with fb.Plan(win=64, backend=fb.BACKEND_TCGEN05) as plan:
+        W, H, V, _ = plan.nmf_process(X, 16, iters, uw, uh, seeds=[3, 4, 5])
+        assert plan.stats()["backend_used"] == fb.BACKEND_TCGEN05
+    for b in range(3):
+        Wo, Ho, Vo, _ = oracle.nmf_process(X[b], 16, iters, uw, uh, 3 + b)
+        assert rel(W[b], Wo) < TOL and rel(H[b], Ho) < TOL and rel(V[b], Vo) < TOL
+
+
+def test_tc_engine_matches_simt_and_is_repeatable(fb):
+    rng = np.random.default_rng(1)
+    X = lowrank(rng, 5, 512, 513).astype(np.float32)
+    with fb.Plan(win=64, backend=fb.BACKEND_TCGEN05) as pt, fb.Plan(win=64, backend=fb.BACKEND_SIMT) as ps:
+        Wt, Ht, Vt, _ = pt.nmf_process(X, 16, 50, True, True, seeds=np.arange(5))
+        Wt2, Ht2, _, _ = pt.nmf_process(X, 16, 50, True, True, seeds=np.arange(5))
+        Ws, Hs, Vs, _ = ps.nmf_process(X, 16, 50, True, True, seeds=np.arange(5))
+        assert ps.stats()["backend_used"] == fb.BACKEND_SIMT
+    assert np.array_equal(Wt, Wt2) and np.array_equal(Ht, Ht2)
+    for b in range(5):
+        assert rel(Wt[b], Ws[b]) < TOL and rel(Ht[b], Hs[b]) < TOL and rel(Vt[b], Vs[b]) < TOL
+
+
+def test_tc_engine_many_buffers_persistent_loop(fb, oracle):
+    """more buffers than SMs: every CTA walks several buffers, barrier phases carry over"""
+    rng = np.random.default_rng(2)
+    base = lowrank(rng, 4, 256, 257)
+    X = np.concatenate([base] * 80)[:310]
+    seeds = np.arange(310) % 7
+    with fb.Plan(win=64, backend=fb.BACKEND_TCGEN05) as plan:
+        W, H, _, _ = plan.nmf_process(X, 16, 8, True, True, seeds=seeds, want_v=False)
+    for b in (0, 5, 151, 309):
+        Wo, Ho, _, _ = oracle.nmf_process(X[b], 16, 8, True, True, int(seeds[b]))
+        assert rel(W[b], Wo) < TOL and rel(H[b], Ho) < TOL
+    # identical (audio, seed) pairs give identical results wherever they sit in the batch
+    assert np.array_equal(W[0], W[28]) and np.array_equal(H[3], H[31])
+
+
+def test_tc_engine_rejects_unqualified_shapes(fb):
+    X = np.random.default_rng(0).random((1, 64, 100))
+    with fb.Plan(win=64, backend=fb.BACKEND_TCGEN05) as plan:
+        with pytest.raises(fb.FlucomaB200Error):
+            plan.nmf_process(X, 16, 3, True, True, seeds=1)
