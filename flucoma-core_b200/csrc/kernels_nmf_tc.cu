@@ -1,25 +1,32 @@
 // tcgen05 / TMEM / TMA engine for the NMF multiplicative updates (algorithms/public/NMF.hpp:144-183), rank 16.
 //
-// One persistent CTA owns one buffer for ALL iterations: W and H live in shared memory (fp32 masters + split-bf16
-// hi/lo operand copies in UMMA core-matrix layout), V = |X| is streamed by TMA (128B swizzle) exactly once per phase,
-// WH is accumulated in TMEM, the ratio V / max(WH, eps) is computed by the epilogue warps straight out of TMEM and
-// written back to TMEM as the A operand of the second MMA -- neither WH nor the ratio ever touch shared or global
-// memory, and there is no inter-CTA communication at all.
+// One persistent CTA owns one buffer for ALL iterations.  W and H live in shared memory as exact three-way bf16
+// splits (x = hi + mid + lo reproduces the fp32 value), stored directly in UMMA core-matrix layout, so the operand
+// copies ARE the state.  V = |X| is streamed by TMA (128B swizzle) once per phase, WH is accumulated in TMEM, the ratio
+// V / max(WH, eps) is computed by the epilogue warps straight out of TMEM and written back to TMEM (again as a 3-way
+// split) as the A operand of the second MMA -- neither WH nor the ratio ever touch shared or global memory, and there
+// is no inter-CTA communication.
 //
 //   phase 1 (H-update of a 128-frame tile t, NMF.hpp:165-170), per 64-bin chunk c:
-//       P[f][b]   = H_t W_c            tcgen05.mma SS   A = H blocks (K-major)   B = W blocks (MN-major)   M128 N64 K16
-//       R[f][b]   = V / max(P, eps)    epilogue: tcgen05.ld, swizzled LDS of the TMA tile, MUFU rcp, bf16 hi/lo, tcgen05.st
-//       hnum[f][k] += R W_c^T          tcgen05.mma TS   A = R (TMEM)             B = W blocks (K-major)    M128 N16 K64
+//       P[f][b]    = H_t W_c           tcgen05.mma SS   A = H blocks (K-major)   B = W blocks (MN-major)   M128 N64 K16
+//       R[f][b]    = V / max(P, eps)   epilogue: tcgen05.ld, swizzled LDS of the TMA tile, rcp, 3-way split, tcgen05.st
+//       hnum[f][k] += R W_c^T          tcgen05.mma TS   A = R (TMEM)             B = W blocks (K-major)    M128 N32/16 K64
 //     then H <- H * hnum / max(hden, eps) for the tile.
 //   phase 2 (this tile's share of the next W-update, NMF.hpp:158-160), per 128-bin tile m and 64-frame half s:
-//       P[b][f]   = W_m^T H_ts^T       SS   A = W blocks (MN-major)  B = H blocks (K-major)    M128 N64 K16
-//       R[b][f]   = V / max(P, eps)
-//       wnum[b][k] += R H_ts           TS   A = R (TMEM)             B = H blocks (MN-major)   M128 N16 K64
+//       P[b][f]    = W_m^T H_ts^T      SS   A = W blocks (MN-major)  B = H blocks (K-major)    M128 N64 K16
+//       R[b][f]    = V / max(P, eps)
+//       wnum[b][k] += R H_ts           TS   A = R (TMEM)             B = H blocks (MN-major)   M128 N32/16 K64
 //   after the last tile: W <- W * wnum / max(wden, eps), conditional column normalisation (:161-162), hden = sum_b W.
-// Every product is evaluated as hi*hi + hi*lo + lo*hi on bf16 pairs (x ~ hi + lo, 16 mantissa bits): plain bf16 misses
-// the 1e-4 parity bar, the three-term split meets it with fp32-like margins.
-// The Nyquist bin (B = 2^m + 1) does not fit the 128-wide tiles; its column is carried on the SIMT side of the
-// epilogue (a 16-term dot product per frame), so the tensor tiles cover bins 0 .. B-2 exactly.
+//
+// Precision: a product of two 3-way splits keeps the six terms above 2^-24 (hh, hm, mh, hl, lh, mm), i.e. fp32-grade
+// operands with fp32 accumulation.  (A 2-way split, 16-17 mantissa bits, measured 1.3e-4 against the fp64 oracle after
+// 200 iterations -- the NMF dynamics amplify the per-iteration error about 100x -- and missed the 1e-4 bar.)
+// For the second MMA the three parts of the B operand sit next to each other in shared memory, so one instruction
+// with N = 32 multiplies a ratio part by [X_hi | X_mid] at once; the accumulator is 32 columns wide and its two halves
+// are added by the epilogue.
+//
+// The Nyquist bin (B = 2^m + 1) does not fit the 128-wide tiles; its column is carried on the SIMT side of the epilogue
+// (a 16-term dot product per frame), so the tensor tiles cover bins 0 .. B-2 exactly.
 //
 // Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM owner), warps 2-9 = two epilogue
 // warpgroups that alternate steps (ping-pong on two P/R TMEM buffers).  All reductions are fixed-order: results are
@@ -35,42 +42,65 @@ using namespace tc;
 namespace tcn {
 constexpr int K = 16;
 constexpr int KB = 2;            // 8-component blocks
-constexpr int NS = 2;            // V ring stages of 32 KB
+constexpr int NS = 3;            // V ring stages of 32 KB
 constexpr int STAGE = 32768;
 constexpr int BT_MAX = 512;      // tensor bins (B - 1)
 constexpr int FP_MAX = 512;      // padded frames
-constexpr int WPITCH = BT_MAX + 4;
 constexpr int NTHREADS = 320;
+constexpr uint32_t ROWB = 3 * KB * 128; // bytes per 8-bin (W) / 8-frame (H) block row: 3 parts x 2 component blocks
 
 // TMEM columns
-constexpr uint32_t TM_P = 0;     // + 64 g
-constexpr uint32_t TM_R = 128;   // + 64 g : hi [0,32) lo [32,64)
-constexpr uint32_t TM_HNUM = 256;
-constexpr uint32_t TM_WNUM = 272; // + 16 m
+constexpr uint32_t TM_P = 0;      // + 64 g
+constexpr uint32_t TM_R = 128;    // + 96 g : hi [0,32) mid [32,64) lo [64,96)
+constexpr uint32_t TM_ACC = 320;  // + 32 g : per-step partial of the second MMA, [0,16) leading term, [16,32) corrections
+constexpr uint32_t TM_WSUM = 384; // + 64 wg + 16 m : fp32 running sums of the W numerator, added by the epilogue (RN)
 
 // shared memory map (bytes)
 constexpr int OFF_V = 0;
-constexpr int OFF_WHI = OFF_V + NS * STAGE;
-constexpr int OFF_WLO = OFF_WHI + K * BT_MAX * 2;
-constexpr int OFF_HHI = OFF_WLO + K * BT_MAX * 2;
-constexpr int OFF_HLO = OFF_HHI + FP_MAX * K * 2;
-constexpr int OFF_WM = OFF_HLO + FP_MAX * K * 2;      // float [K][WPITCH]
-constexpr int OFF_HM = OFF_WM + K * WPITCH * 4;       // float [FP_MAX][K]
-constexpr int OFF_VN = OFF_HM + FP_MAX * K * 4;       // float [FP_MAX]  Nyquist column of V
-constexpr int OFF_WN = OFF_VN + FP_MAX * 4;           // float [K]       Nyquist row of W
-constexpr int OFF_HDEN = OFF_WN + K * 4;              // float [K]
-constexpr int OFF_PART = OFF_HDEN + K * 4;            // float [4 tiles][8 warps][32]
-constexpr int OFF_RED = OFF_PART + 4 * 8 * 32 * 4;    // float [8 warps][36]
-constexpr int OFF_FIN = OFF_RED + 8 * 36 * 4;         // float [64]
-constexpr int OFF_BAR = OFF_FIN + 64 * 4;             // mbarriers
-constexpr int NBAR = 2 * NS + 2 + 2 + 1 + 3;
+constexpr int OFF_WOP = OFF_V + NS * STAGE;                 // bf16 [BT/8][3][KB][8][8]
+constexpr int OFF_HOP = OFF_WOP + (BT_MAX / 8) * (int) ROWB; // bf16 [Fp/8][3][KB][8][8]
+constexpr int OFF_VN = OFF_HOP + (FP_MAX / 8) * (int) ROWB;  // float [FP_MAX]  Nyquist column of V
+constexpr int OFF_WN = OFF_VN + FP_MAX * 4;                 // float [K]       Nyquist row of W
+constexpr int OFF_HDEN = OFF_WN + K * 4;                    // float [K]
+constexpr int OFF_PART = OFF_HDEN + K * 4;                  // float [4 tiles][8 warps][32]
+constexpr int OFF_RED = OFF_PART + 4 * 8 * 32 * 4;          // float [8 warps][36]
+constexpr int OFF_FIN = OFF_RED + 8 * 36 * 4;               // float [64]
+constexpr int OFF_HS = OFF_FIN + 64 * 4;                    // float [2 wg][128][16] per-warpgroup partial H numerators
+constexpr int OFF_BAR = OFF_HS + 2 * 128 * 16 * 4;          // mbarriers
+constexpr int NBAR = 2 * NS + 2 + 2 + 2 + 3;
 constexpr int OFF_SLOT = OFF_BAR + NBAR * 8;
 constexpr int SMEM_BYTES = OFF_SLOT + 16;
 
-__device__ __forceinline__ int wop_index(int k, int b) { return ((b >> 3) * KB + (k >> 3)) * 64 + (k & 7) * 8 + (b & 7); }
-__device__ __forceinline__ int hop_index(int f, int k) { return ((f >> 3) * KB + (k >> 3)) * 64 + (f & 7) * 8 + (k & 7); }
+// element index (in bf16 units) of W[k][b] / H[f][k], split part `part`
+__device__ __forceinline__ int wop_index(int part, int k, int b) { return ((((b >> 3) * 3 + part) * KB + (k >> 3)) << 6) + ((k & 7) << 3) + (b & 7); }
+__device__ __forceinline__ int hop_index(int part, int f, int k) { return ((((f >> 3) * 3 + part) * KB + (k >> 3)) << 6) + ((f & 7) << 3) + (k & 7); }
 
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// packed convert: low half <- a, high half <- b (F2FP.BF16.F32.PACK_AB, full-rate; the C++ intrinsic compiled to two
+// scalar F2F on the XU pipe)
+__device__ __forceinline__ uint32_t cvt2(float a, float b)
+{
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+__device__ __forceinline__ float rcp_fast(float x)
+{
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+// exact 3-way split of a pair: x = hi + mid + lo (each bf16), packed pairwise
+__device__ __forceinline__ void split3(float x0, float x1, uint32_t& h, uint32_t& m, uint32_t& l)
+{
+  h = cvt2(x0, x1);
+  x0 -= bf16lo_to_f(h); x1 -= bf16hi_to_f(h);
+  m = cvt2(x0, x1);
+  x0 -= bf16lo_to_f(m); x1 -= bf16hi_to_f(m);
+  l = cvt2(x0, x1);
+}
+__device__ __forceinline__ float bf16_bits_to_f(unsigned short u) { return __uint_as_float((uint32_t) u << 16); }
 
 struct Sched {
   int npass, both, upd_w, upd_h, iters;
@@ -85,26 +115,23 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_constant__ CUtensorMap tmap2, int iters, int upd_w, int upd_h)
 {
   extern __shared__ __align__(1024) uint8_t smem[];
-  __nv_bfloat16* whi = reinterpret_cast<__nv_bfloat16*>(smem + OFF_WHI);
-  __nv_bfloat16* wlo = reinterpret_cast<__nv_bfloat16*>(smem + OFF_WLO);
-  __nv_bfloat16* hhi = reinterpret_cast<__nv_bfloat16*>(smem + OFF_HHI);
-  __nv_bfloat16* hlo = reinterpret_cast<__nv_bfloat16*>(smem + OFF_HLO);
-  float* Wm = reinterpret_cast<float*>(smem + OFF_WM);
-  float* Hm = reinterpret_cast<float*>(smem + OFF_HM);
+  __nv_bfloat16* wop = reinterpret_cast<__nv_bfloat16*>(smem + OFF_WOP);
+  __nv_bfloat16* hop = reinterpret_cast<__nv_bfloat16*>(smem + OFF_HOP);
   float* VN = reinterpret_cast<float*>(smem + OFF_VN);
   float* WN = reinterpret_cast<float*>(smem + OFF_WN);
   float* hden = reinterpret_cast<float*>(smem + OFF_HDEN);
   float* part = reinterpret_cast<float*>(smem + OFF_PART);
   float* red = reinterpret_cast<float*>(smem + OFF_RED);
   float* fin = reinterpret_cast<float*>(smem + OFF_FIN);
+  float* hs = reinterpret_cast<float*>(smem + OFF_HS);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint64_t* v_full = bars;            // [NS]
   uint64_t* v_empty = bars + NS;      // [NS]
   uint64_t* p_full = bars + 2 * NS;   // [2]
   uint64_t* r_full = p_full + 2;      // [2]
-  uint64_t* acc_full = r_full + 2;    // [1]
+  uint64_t* b_full = r_full + 2;      // [2] second MMA of a step retired: its partial sits in TM_ACC + 32 g
   // three separate "operands ready" barriers so that two completions can never pile up unobserved on one of them
-  uint64_t* buf_ready = acc_full + 1;   // buffer prologue done
+  uint64_t* buf_ready = b_full + 2;     // buffer prologue done
   uint64_t* prep_ready = buf_ready + 1; // tile prep (H-update) done
   uint64_t* w_ready = prep_ready + 1;   // W-update done
   uint32_t* slot = reinterpret_cast<uint32_t*>(smem + OFF_SLOT);
@@ -118,8 +145,7 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
 
   if (tid == 0) {
     for (int i = 0; i < NS; i++) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 4); }
-    for (int i = 0; i < 2; i++) { mbar_init(&p_full[i], 1); mbar_init(&r_full[i], 4); }
-    mbar_init(acc_full, 1);
+    for (int i = 0; i < 2; i++) { mbar_init(&p_full[i], 1); mbar_init(&r_full[i], 4); mbar_init(&b_full[i], 1); }
     mbar_init(buf_ready, 8);
     mbar_init(prep_ready, 8);
     mbar_init(w_ready, 8);
@@ -167,42 +193,49 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
   } else if (warp == 1) {
     // =========================================== MMA issuer =============================================
     if (lane == 0) {
-      const uint32_t whi_a = smem_u32(whi), wlo_a = smem_u32(wlo), hhi_a = smem_u32(hhi), hlo_a = smem_u32(hlo);
+      const uint32_t wop_a = smem_u32(wop), hop_a = smem_u32(hop);
       constexpr uint32_t ID_P1A = make_idesc_bf16(128, 64, 0, 1);
-      constexpr uint32_t ID_P1B = make_idesc_bf16(128, 16, 0, 0);
+      constexpr uint32_t ID_P1B32 = make_idesc_bf16(128, 32, 0, 0), ID_P1B16 = make_idesc_bf16(128, 16, 0, 0);
       constexpr uint32_t ID_P2A = make_idesc_bf16(128, 64, 1, 0);
-      constexpr uint32_t ID_P2B = make_idesc_bf16(128, 16, 0, 1);
+      constexpr uint32_t ID_P2B32 = make_idesc_bf16(128, 32, 0, 1), ID_P2B16 = make_idesc_bf16(128, 16, 0, 1);
       uint32_t n = 0, buf_cnt = 0, prep_cnt = 0, w_cnt = 0;
       // pending second-stage MMA (issued one step late so the next step's first MMA overlaps this step's epilogue)
-      int pend_valid = 0, pend_phase = 0, pend_g = 0, pend_blk = 0, pend_acc = 0, pend_m = 0;
+      int pend_valid = 0, pend_phase = 0, pend_g = 0, pend_blk = 0;
       uint32_t pend_k = 0;
       auto issue_b = [&]() {
         if (!pend_valid) return;
         mbar_wait(&r_full[pend_g], pend_k & 1);
         tc_fence_after();
-        const uint32_t rhi = tbase + TM_R + 64 * pend_g, rlo = rhi + 32;
-        if (pend_phase == 1) { // hnum += R W_c^T : B = W blocks K-major, K-step j = bin blocks pend_blk + 2j
-          const uint32_t dacc = tbase + TM_HNUM;
+        const uint32_t rh = tbase + TM_R + 96 * pend_g, rm = rh + 32, rl = rh + 64;
+        const bool ph1 = pend_phase == 1;
+        const uint32_t dacc = tbase + TM_ACC + 32 * pend_g;
+        const uint32_t base = ph1 ? wop_a : hop_a;
+        const uint32_t id32 = ph1 ? ID_P1B32 : ID_P2B32, id16 = ph1 ? ID_P1B16 : ID_P2B16;
 #pragma unroll
-          for (int j = 0; j < 4; j++) {
-            const uint32_t off = (uint32_t) (pend_blk + 2 * j) * 256;
-            const uint64_t bh = make_smem_desc(whi_a + off, 256, 128), bl = make_smem_desc(wlo_a + off, 256, 128);
-            mma_ts(dacc, rhi + 8 * j, bh, ID_P1B, (pend_acc || j) ? 1u : 0u);
-            mma_ts(dacc, rhi + 8 * j, bl, ID_P1B, 1u);
-            mma_ts(dacc, rlo + 8 * j, bh, ID_P1B, 1u);
-          }
-        } else { // wnum[m] += R H_ts : B = H blocks MN-major, K-step j = frame blocks pend_blk + 2j
-          const uint32_t dacc = tbase + TM_WNUM + 16 * pend_m;
-#pragma unroll
-          for (int j = 0; j < 4; j++) {
-            const uint32_t off = (uint32_t) (pend_blk + 2 * j) * 256;
-            const uint64_t bh = make_smem_desc(hhi_a + off, 256, 128), bl = make_smem_desc(hlo_a + off, 256, 128);
-            mma_ts(dacc, rhi + 8 * j, bh, ID_P2B, (pend_acc || j) ? 1u : 0u);
-            mma_ts(dacc, rhi + 8 * j, bl, ID_P2B, 1u);
-            mma_ts(dacc, rlo + 8 * j, bh, ID_P2B, 1u);
-          }
+        for (int j = 0; j < 4; j++) { // K-step j = 16 bins (phase 1) / 16 frames (phase 2) = block rows pend_blk + 2j, +1
+          const uint32_t off = (uint32_t) (pend_blk + 2 * j) * ROWB;
+          // The tensor core adds into the fp32 accumulator with truncation, so every accumulate costs up to one ulp of
+          // the accumulator, always in the same direction.  Columns [0,16) therefore receive ONLY the leading term
+          // R_hi X_hi (one add per K-step); all correction terms go to the small-magnitude columns [16,32).
+          const uint64_t b0 = make_smem_desc(base + off, ROWB, 128);                // parts hi, mid side by side along N
+          const uint64_t b1 = make_smem_desc(base + off + 1 * KB * 128, ROWB, 128); // part mid
+          const uint64_t b2 = make_smem_desc(base + off + 2 * KB * 128, ROWB, 128); // part lo
+          mma_ts(dacc, rh + 8 * j, b0, id32, j ? 1u : 0u);                       // R_hi  [X_hi | X_mid]
+          mma_ts(dacc + 16, rm + 8 * j, b0, id16, 1u);                           // R_mid  X_hi
+          mma_ts(dacc + 16, rm + 8 * j, b1, id16, 1u);                           // R_mid  X_mid
+          mma_ts(dacc + 16, rl + 8 * j, b0, id16, 1u);                           // R_lo   X_hi
+          mma_ts(dacc + 16, rh + 8 * j, b2, id16, 1u);                           // R_hi   X_lo
         }
+        mma_commit(&b_full[pend_g]); // the epilogue adds this partial to its fp32 running sums
         pend_valid = 0;
+      };
+      // first-stage MMA: six significant terms of (A_hi + A_mid + A_lo)(B_hi + B_mid + B_lo)
+      auto issue_a = [&](uint32_t dP, uint32_t a_base, uint32_t b_base, uint32_t idesc) {
+        constexpr int pa[6] = {0, 0, 1, 0, 2, 1}, pb[6] = {0, 1, 0, 2, 0, 1};
+#pragma unroll
+        for (int i = 0; i < 6; i++)
+          mma_ss(dP, make_smem_desc(a_base + pa[i] * KB * 128, 128, ROWB), make_smem_desc(b_base + pb[i] * KB * 128, 128, ROWB), idesc,
+                 i ? 1u : 0u);
       };
       for (int buf = blockIdx.x; buf < d.batch; buf += gridDim.x) {
         mbar_wait(buf_ready, buf_cnt & 1); buf_cnt++; // operands of this buffer are in shared memory
@@ -213,19 +246,12 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
             if (p1) {
               for (int c = 0; c < C1; c++, n++) {
                 const int g = n & 1;
-                const uint32_t dP = tbase + TM_P + 64 * g;
-                const uint32_t aoff = (uint32_t) (16 * t) * 256, boff = (uint32_t) (8 * c) * 256;
-                const uint64_t ah = make_smem_desc(hhi_a + aoff, 128, 256), al = make_smem_desc(hlo_a + aoff, 128, 256);
-                const uint64_t bh = make_smem_desc(whi_a + boff, 128, 256), bl = make_smem_desc(wlo_a + boff, 128, 256);
-                mma_ss(dP, ah, bh, ID_P1A, 0u);
-                mma_ss(dP, ah, bl, ID_P1A, 1u);
-                mma_ss(dP, al, bh, ID_P1A, 1u);
+                issue_a(tbase + TM_P + 64 * g, hop_a + (uint32_t) (16 * t) * ROWB, wop_a + (uint32_t) (8 * c) * ROWB, ID_P1A);
                 mma_commit(&p_full[g]);
                 issue_b();
-                pend_valid = 1; pend_phase = 1; pend_g = g; pend_k = n >> 1; pend_blk = 8 * c; pend_acc = c > 0; pend_m = 0;
+                pend_valid = 1; pend_phase = 1; pend_g = g; pend_k = n >> 1; pend_blk = 8 * c;
               }
-              issue_b();
-              mma_commit(acc_full); // hnum of tile t complete (and every MMA reading H_op(t) has retired)
+              issue_b(); // the tile's H numerator must be complete before the tile prep
             }
             mbar_wait(prep_ready, prep_cnt & 1); prep_cnt++; // tile prep done: H_op(t) updated
             tc_fence_after();
@@ -233,26 +259,16 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
               for (int m = 0; m < MT; m++)
                 for (int s = 0; s < 2; s++, n++) {
                   const int g = n & 1;
-                  const uint32_t dP = tbase + TM_P + 64 * g;
-                  const uint32_t aoff = (uint32_t) (16 * m) * 256, boff = (uint32_t) (16 * t + 8 * s) * 256;
-                  const uint64_t ah = make_smem_desc(whi_a + aoff, 128, 256), al = make_smem_desc(wlo_a + aoff, 128, 256);
-                  const uint64_t bh = make_smem_desc(hhi_a + boff, 128, 256), bl = make_smem_desc(hlo_a + boff, 128, 256);
-                  mma_ss(dP, ah, bh, ID_P2A, 0u);
-                  mma_ss(dP, ah, bl, ID_P2A, 1u);
-                  mma_ss(dP, al, bh, ID_P2A, 1u);
+                  issue_a(tbase + TM_P + 64 * g, wop_a + (uint32_t) (16 * m) * ROWB, hop_a + (uint32_t) (16 * t + 8 * s) * ROWB, ID_P2A);
                   mma_commit(&p_full[g]);
                   issue_b();
                   pend_valid = 1; pend_phase = 2; pend_g = g; pend_k = n >> 1; pend_blk = 16 * t + 8 * s;
-                  pend_acc = (t > 0 || s > 0); pend_m = m;
                 }
-              if (!sc.p1(pass) || t == T - 1) { // nothing else will flush it before the accumulators are read
-                issue_b();
-              }
+              if (!p1 || t == T - 1) issue_b();
             }
           }
           if (p2) {
             issue_b();
-            mma_commit(acc_full); // wnum complete
             mbar_wait(w_ready, w_cnt & 1); w_cnt++; // W-update done: W_op rewritten
             tc_fence_after();
           }
@@ -268,26 +284,65 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
     const int r = 32 * q + lane;           // row (frame or bin) inside a 128-row tile
     const uint32_t lane_off = (uint32_t) (32 * q) << 16;
     const uint32_t tP = tbase + TM_P + 64 * wg + lane_off;
-    const uint32_t tRhi = tbase + TM_R + 64 * wg + lane_off, tRlo = tRhi + 32;
-    uint32_t n = 0, acc_cnt = 0;
+    const uint32_t tR = tbase + TM_R + 96 * wg + lane_off;
+    const uint32_t tAcc = tbase + TM_ACC + 32 * wg + lane_off;
+    const uint32_t tWsum = tbase + TM_WSUM + 64 * wg + lane_off; // + 16 m
+    uint32_t n = 0;
+    // The tensor core truncates when it adds into its fp32 accumulator, so long in-TMEM accumulation chains drift in
+    // one direction; the NMF problem has nearly flat directions (almost identical components) along which such a
+    // persistent bias piles up over the iterations.  Each step's second MMA therefore starts a fresh partial (4
+    // K-steps), and the partials are summed here with round-to-nearest fp32 adds: hsum in registers for phase 1,
+    // TM_WSUM columns for phase 2.
+    float hsum[16];
+#pragma unroll
+    for (int k = 0; k < K; k++) hsum[k] = 0.f;
+    int out_valid = 0, out_phase = 0, out_m = 0, out_first = 0; // this warpgroup's step whose partial is not yet collected
+    uint32_t out_par = 0;
+    auto drain = [&]() {
+      if (!out_valid) return;
+      mbar_wait(&b_full[wg], out_par);
+      tc_fence_after();
+      uint32_t a[32];
+      tmem_ld32(tAcc, a);
+      if (out_phase == 1) {
+        tmem_wait_ld();
+#pragma unroll
+        for (int k = 0; k < K; k++) hsum[k] += __uint_as_float(a[k]) + __uint_as_float(a[16 + k]);
+      } else {
+        uint32_t w[16];
+        if (!out_first) tmem_ld16(tWsum + 16 * out_m, w);
+        tmem_wait_ld();
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+          float x = __uint_as_float(a[k]) + __uint_as_float(a[16 + k]);
+          w[k] = __float_as_uint(out_first ? x : __uint_as_float(w[k]) + x);
+        }
+        tmem_st16(tWsum + 16 * out_m, w);
+        tmem_wait_st();
+      }
+      out_valid = 0;
+    };
+    // phase-2 V addressing: byte offset inside a 128-byte tile row for (frame & 7) = x
+    uint32_t voff[8];
+#pragma unroll
+    for (int x = 0; x < 8; x++) voff[x] = (uint32_t) ((((lane >> 2) ^ x) << 4) + ((lane & 3) << 2));
 
-    // ratio of 32 consecutive columns held in p[] against 32 values v[] -> packed bf16 hi/lo, stored to TMEM
+    // ratio of 32 consecutive columns held in p[] against 32 values v[] -> 3-way split, stored to TMEM
     auto ratio_store = [&](const uint32_t (&p)[32], const float (&v)[32], int h) {
-      uint32_t ph[16], pl[16];
+      uint32_t ph[16], pm[16], pl[16];
 #pragma unroll
       for (int j = 0; j < 16; j++) {
-        float r0 = __fdividef(v[2 * j], fmaxf(__uint_as_float(p[2 * j]), kEps));
-        float r1 = __fdividef(v[2 * j + 1], fmaxf(__uint_as_float(p[2 * j + 1]), kEps));
-        uint32_t hi = pack_bf16x2(r0, r1);
-        ph[j] = hi;
-        pl[j] = pack_bf16x2(r0 - bf16lo_to_f(hi), r1 - bf16hi_to_f(hi));
+        float r0 = v[2 * j] * rcp_fast(fmaxf(__uint_as_float(p[2 * j]), kEps));
+        float r1 = v[2 * j + 1] * rcp_fast(fmaxf(__uint_as_float(p[2 * j + 1]), kEps));
+        split3(r0, r1, ph[j], pm[j], pl[j]);
       }
-      tmem_st16(tRhi + 16 * h, ph);
-      tmem_st16(tRlo + 16 * h, pl);
+      tmem_st16(tR + 16 * h, ph);
+      tmem_st16(tR + 32 + 16 * h, pm);
+      tmem_st16(tR + 64 + 16 * h, pl);
     };
 
     for (int buf = blockIdx.x; buf < d.batch; buf += gridDim.x) {
-      // ---------------- buffer prologue: masters + operand copies -----------------------------------------------
+      // ---------------- buffer prologue: state -> 3-way split operands --------------------------------------------
       const float* gW = d.W + (int64_t) buf * K * Bp;
       const float* gH = d.H + (int64_t) buf * Fp * K;
       const float* gV = d.V + (int64_t) buf * Fp * Bp;
@@ -295,23 +350,23 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
         int k = e / Bp, b = e - k * Bp;
         float w = gW[e];
         if (b < BT) {
-          Wm[k * WPITCH + b] = w;
-          __nv_bfloat16 hi, lo;
-          split_bf16(w, hi, lo);
-          whi[wop_index(k, b)] = hi;
-          wlo[wop_index(k, b)] = lo;
+          __nv_bfloat16 hi = __float2bfloat16_rn(w);
+          float r1 = w - __bfloat162float(hi);
+          __nv_bfloat16 mi = __float2bfloat16_rn(r1);
+          __nv_bfloat16 lo = __float2bfloat16_rn(r1 - __bfloat162float(mi));
+          wop[wop_index(0, k, b)] = hi; wop[wop_index(1, k, b)] = mi; wop[wop_index(2, k, b)] = lo;
         } else if (b == BT) {
           WN[k] = w;
         }
       }
       for (int e = et; e < Fp * K; e += 256) {
         float h = gH[e];
-        Hm[e] = h;
-        __nv_bfloat16 hi, lo;
-        split_bf16(h, hi, lo);
         int f = e >> 4, k = e & 15;
-        hhi[hop_index(f, k)] = hi;
-        hlo[hop_index(f, k)] = lo;
+        __nv_bfloat16 hi = __float2bfloat16_rn(h);
+        float r1 = h - __bfloat162float(hi);
+        __nv_bfloat16 mi = __float2bfloat16_rn(r1);
+        __nv_bfloat16 lo = __float2bfloat16_rn(r1 - __bfloat162float(mi));
+        hop[hop_index(0, f, k)] = hi; hop[hop_index(1, f, k)] = mi; hop[hop_index(2, f, k)] = lo;
       }
       for (int f = et; f < Fp; f += 256) VN[f] = gV[(int64_t) f * Bp + BT];
       if (et < K) hden[et] = d.hden[(int64_t) buf * K + et];
@@ -327,6 +382,7 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
             for (int c = 0; c < C1; c++, n++) {
               if ((int) (n & 1) != wg) continue;
               const uint32_t st = n % NS;
+              drain(); // collect the previous step's partial before its accumulator columns are reused
               mbar_wait(&p_full[wg], (n >> 1) & 1);
               mbar_wait(&v_full[st], (n / NS) & 1);
               tc_fence_after();
@@ -349,14 +405,18 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
               tc_fence_before();
               __syncwarp();
               if (lane == 0) { mbar_arrive(&r_full[wg]); mbar_arrive(&v_empty[st]); }
+              out_valid = 1; out_phase = 1; out_par = (n >> 1) & 1;
             }
-            mbar_wait(acc_full, acc_cnt & 1); acc_cnt++;
-            tc_fence_after();
+            drain(); // H numerator of this warpgroup's chunks complete (all MMAs reading H_op(t) have retired)
+#pragma unroll
+            for (int j4 = 0; j4 < 4; j4++)
+              *reinterpret_cast<float4*>(hs + (wg * 128 + r) * 16 + 4 * j4) = make_float4(hsum[4 * j4], hsum[4 * j4 + 1], hsum[4 * j4 + 2], hsum[4 * j4 + 3]);
+#pragma unroll
+            for (int k = 0; k < K; k++) hsum[k] = 0.f;
+            epi_bar();
           }
           // ---------------- tile prep: H-update (if p1), W-denominator / Nyquist partials (if p2) ----------------
           {
-            uint32_t hn[16];
-            if (p1) { tmem_ld16(tbase + TM_HNUM + lane_off, hn); tmem_wait_ld(); }
             const int f = 128 * t + r;
             float contrib[32];
 #pragma unroll
@@ -364,9 +424,18 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
             if ((lane & 1) == wg) { // the two warpgroups split the rows of the tile
               float h[16];
 #pragma unroll
-              for (int j4 = 0; j4 < 4; j4++) {
-                float4 x = *reinterpret_cast<const float4*>(Hm + f * K + 4 * j4);
-                h[4 * j4] = x.x; h[4 * j4 + 1] = x.y; h[4 * j4 + 2] = x.z; h[4 * j4 + 3] = x.w;
+              for (int kb = 0; kb < KB; kb++) { // H[f][8kb..8kb+7] = hi + mid + lo, one 16-byte row per core matrix
+                float acc8[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) acc8[j] = 0.f;
+#pragma unroll
+                for (int pt = 2; pt >= 0; pt--) { // small parts first
+                  const uint4 u = *reinterpret_cast<const uint4*>(hop + hop_index(pt, f, 8 * kb));
+                  acc8[0] += bf16lo_to_f(u.x); acc8[1] += bf16hi_to_f(u.x); acc8[2] += bf16lo_to_f(u.y); acc8[3] += bf16hi_to_f(u.y);
+                  acc8[4] += bf16lo_to_f(u.z); acc8[5] += bf16hi_to_f(u.z); acc8[6] += bf16lo_to_f(u.w); acc8[7] += bf16hi_to_f(u.w);
+                }
+#pragma unroll
+                for (int j = 0; j < 8; j++) h[8 * kb + j] = acc8[j];
               }
               const float vn = VN[f];
               if (p1) {
@@ -376,24 +445,18 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
                 const float rn = vn / fmaxf(pn, kEps);
 #pragma unroll
                 for (int k = 0; k < K; k++) {
-                  float num = fmaf(rn, WN[k], __uint_as_float(hn[k]));
+                  float num = hs[r * 16 + k] + hs[(128 + r) * 16 + k]; // even + odd chunks
+                  num = fmaf(rn, WN[k], num);
                   h[k] = h[k] * num / fmaxf(hden[k], kEps);      // NMF.hpp:170
                 }
-                uint32_t ph[8], pl[8];
 #pragma unroll
-                for (int j = 0; j < 8; j++) {
-                  uint32_t hi = pack_bf16x2(h[2 * j], h[2 * j + 1]);
-                  ph[j] = hi;
-                  pl[j] = pack_bf16x2(h[2 * j] - bf16lo_to_f(hi), h[2 * j + 1] - bf16hi_to_f(hi));
-                }
+                for (int kb = 0; kb < KB; kb++) {
+                  uint32_t ph[4], pm[4], pl[4];
 #pragma unroll
-                for (int j4 = 0; j4 < 4; j4++)
-                  *reinterpret_cast<float4*>(Hm + f * K + 4 * j4) = make_float4(h[4 * j4], h[4 * j4 + 1], h[4 * j4 + 2], h[4 * j4 + 3]);
-#pragma unroll
-                for (int kb = 0; kb < KB; kb++) { // one 16-byte row of each core matrix
-                  const int idx = ((f >> 3) * KB + kb) * 64 + (f & 7) * 8;
-                  *reinterpret_cast<uint4*>(hhi + idx) = make_uint4(ph[4 * kb], ph[4 * kb + 1], ph[4 * kb + 2], ph[4 * kb + 3]);
-                  *reinterpret_cast<uint4*>(hlo + idx) = make_uint4(pl[4 * kb], pl[4 * kb + 1], pl[4 * kb + 2], pl[4 * kb + 3]);
+                  for (int j = 0; j < 4; j++) split3(h[8 * kb + 2 * j], h[8 * kb + 2 * j + 1], ph[j], pm[j], pl[j]);
+                  *reinterpret_cast<uint4*>(hop + hop_index(0, f, 8 * kb)) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+                  *reinterpret_cast<uint4*>(hop + hop_index(1, f, 8 * kb)) = make_uint4(pm[0], pm[1], pm[2], pm[3]);
+                  *reinterpret_cast<uint4*>(hop + hop_index(2, f, 8 * kb)) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
                 }
               }
               if (p2) {
@@ -429,6 +492,7 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
               for (int s = 0; s < 2; s++, n++) {
                 if ((int) (n & 1) != wg) continue;
                 const uint32_t st = n % NS;
+                drain();
                 mbar_wait(&p_full[wg], (n >> 1) & 1);
                 mbar_wait(&v_full[st], (n / NS) & 1);
                 tc_fence_after();
@@ -438,11 +502,9 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
                   uint32_t p[32];
                   tmem_ld32(tP + 32 * h, p);
                   float v[32];
+                  const uint8_t* vh = vt + h * 32 * 128;
 #pragma unroll
-                  for (int j = 0; j < 32; j++) {
-                    const int fr = 32 * h + j;
-                    v[j] = *reinterpret_cast<const float*>(vt + fr * 128 + ((((lane >> 2) ^ (fr & 7))) << 4) + ((lane & 3) << 2));
-                  }
+                  for (int j = 0; j < 32; j++) v[j] = *reinterpret_cast<const float*>(vh + j * 128 + voff[j & 7]);
                   tmem_wait_ld();
                   ratio_store(p, v, h);
                 }
@@ -450,14 +512,16 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) { mbar_arrive(&r_full[wg]); mbar_arrive(&v_empty[st]); }
+                out_valid = 1; out_phase = 2; out_m = m; out_first = (t == 0); out_par = (n >> 1) & 1;
               }
           }
         }
         // ---------------- W-update (NMF.hpp:161-162) + hden refresh (:169) --------------------------------------
         if (p2) {
-          mbar_wait(acc_full, acc_cnt & 1); acc_cnt++;
+          drain(); // last outstanding W-numerator partial of this warpgroup
+          tc_fence_before();
+          epi_bar(); // all partials of all tiles written, both warpgroups' running sums complete
           tc_fence_after();
-          epi_bar(); // all partials of all tiles written
           if (et < 32) {
             float s = 0.f;
             for (int i = 0; i < T * 8; i++) s += part[i * 32 + et];
@@ -472,13 +536,17 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
           for (int i = 0; i < 2; i++) {
             const int m = wg + 2 * i;
             if (m < MT) {
-              uint32_t wn[16];
-              tmem_ld16(tbase + TM_WNUM + 16 * m + lane_off, wn);
+              uint32_t wn[32]; // running sums of the two warpgroups (each saw one 64-frame half of every tile)
+              tmem_ld16(tbase + TM_WSUM + 16 * m + lane_off, *reinterpret_cast<uint32_t(*)[16]>(&wn[0]));
+              tmem_ld16(tbase + TM_WSUM + 64 + 16 * m + lane_off, *reinterpret_cast<uint32_t(*)[16]>(&wn[16]));
               tmem_wait_ld();
               const int b = 128 * m + r;
+              const unsigned short* wp = reinterpret_cast<const unsigned short*>(wop);
 #pragma unroll
               for (int k = 0; k < K; k++) {
-                float w = Wm[k * WPITCH + b] * __uint_as_float(wn[k]) / fmaxf(fin[k], kEps);
+                float wold = bf16_bits_to_f(wp[wop_index(2, k, b)]) + bf16_bits_to_f(wp[wop_index(1, k, b)]) + bf16_bits_to_f(wp[wop_index(0, k, b)]);
+                float num = __uint_as_float(wn[k]) + __uint_as_float(wn[16 + k]);
+                float w = wold * num / fmaxf(fin[k], kEps);
                 wnew[i][k] = w;
                 ss[k] = fmaf(w, w, ss[k]);
                 sm[k] += w;
@@ -530,11 +598,11 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
 #pragma unroll
               for (int k = 0; k < K; k++) {
                 float w = wnew[i][k] * fin[32 + k];
-                Wm[k * WPITCH + b] = w;
-                __nv_bfloat16 hi, lo;
-                split_bf16(w, hi, lo);
-                whi[wop_index(k, b)] = hi;
-                wlo[wop_index(k, b)] = lo;
+                __nv_bfloat16 hi = __float2bfloat16_rn(w);
+                float r1 = w - __bfloat162float(hi);
+                __nv_bfloat16 mi = __float2bfloat16_rn(r1);
+                __nv_bfloat16 lo = __float2bfloat16_rn(r1 - __bfloat162float(mi));
+                wop[wop_index(0, k, b)] = hi; wop[wop_index(1, k, b)] = mi; wop[wop_index(2, k, b)] = lo;
               }
             }
           }
@@ -548,16 +616,24 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
           if (lane == 0) mbar_arrive(w_ready);
         }
       }
-      // ---------------- buffer epilogue: masters back to global --------------------------------------------------
+      // ---------------- buffer epilogue: state back to global ----------------------------------------------------
       epi_bar();
       float* oW = d.W + (int64_t) buf * K * Bp;
       float* oH = d.H + (int64_t) buf * Fp * K;
+      const unsigned short* wp = reinterpret_cast<const unsigned short*>(wop);
+      const unsigned short* hp = reinterpret_cast<const unsigned short*>(hop);
       for (int e = et; e < K * Bp; e += 256) {
         int k = e / Bp, b = e - k * Bp;
-        oW[e] = b < BT ? Wm[k * WPITCH + b] : (b == BT ? WN[k] : 0.f);
+        float w = 0.f;
+        if (b < BT) w = bf16_bits_to_f(wp[wop_index(2, k, b)]) + bf16_bits_to_f(wp[wop_index(1, k, b)]) + bf16_bits_to_f(wp[wop_index(0, k, b)]);
+        else if (b == BT) w = WN[k];
+        oW[e] = w;
       }
-      for (int e = et; e < Fp * K; e += 256) oH[e] = Hm[e];
-      epi_bar(); // masters are overwritten by the next buffer's prologue
+      for (int e = et; e < Fp * K; e += 256) {
+        int f = e >> 4, k = e & 15;
+        oH[e] = bf16_bits_to_f(hp[hop_index(2, f, k)]) + bf16_bits_to_f(hp[hop_index(1, f, k)]) + bf16_bits_to_f(hp[hop_index(0, f, k)]);
+      }
+      epi_bar(); // operands are overwritten by the next buffer's prologue
     }
   }
 
@@ -584,9 +660,7 @@ int32_t tc_run(Plan* p, const NmfDev& d, int iters, bool upd_w, bool upd_h)
     p->attr_mask |= 0x10000u;
   }
   int grid = std::min(d.batch, p->sm_count);
-  if (p->kev.size() < p->kev_used + 2) {
-    while (p->kev.size() < p->kev_used + 2) { cudaEvent_t e; cudaEventCreate(&e); p->kev.push_back(e); }
-  }
+  while (p->kev.size() < p->kev_used + 2) { cudaEvent_t e; cudaEventCreate(&e); p->kev.push_back(e); }
   cudaEventRecord(p->kev[p->kev_used++], p->stream);
   k_nmf_tc<<<grid, NTHREADS, SMEM_BYTES, p->stream>>>(d, tmap1, tmap2, iters, upd_w ? 1 : 0, upd_h ? 1 : 0);
   cudaEventRecord(p->kev[p->kev_used++], p->stream);
