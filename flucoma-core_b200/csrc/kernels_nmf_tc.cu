@@ -46,12 +46,14 @@ constexpr int NS = 3;            // V ring stages of 32 KB
 constexpr int STAGE = 32768;
 constexpr int BT_MAX = 512;      // tensor bins (B - 1)
 constexpr int FP_MAX = 512;      // padded frames
-constexpr int NTHREADS = 320;
+constexpr int NTHREADS = 384;    // warpgroup 0: producer, issuer, 2 idle warps; warpgroups 1, 2: epilogue
 constexpr uint32_t ROWB = 3 * KB * 128; // bytes per 8-bin (W) / 8-frame (H) block row: 3 parts x 2 component blocks
 
 // TMEM columns
 constexpr uint32_t TM_P = 0;      // + 64 g
-constexpr uint32_t TM_R = 128;    // + 96 g : hi [0,32) mid [32,64) lo [64,96)
+constexpr int RP = 2;             // parts of the ratio operand R written to TMEM (3 = exact fp32, 2 = hi + lo)
+constexpr uint32_t RCOLS = 32 * RP;
+constexpr uint32_t TM_R = 128;    // + RCOLS g : hi [0,32) mid [32,64) lo [64,96)
 constexpr uint32_t TM_ACC = 320;  // + 32 g : per-step partial of the second MMA, [0,16) leading term, [16,32) corrections
 constexpr uint32_t TM_WSUM = 384; // + 64 wg + 16 m : fp32 running sums of the W numerator, added by the epilogue (RN)
 
@@ -67,7 +69,7 @@ constexpr int OFF_RED = OFF_PART + 4 * 8 * 32 * 4;          // float [8 warps][3
 constexpr int OFF_FIN = OFF_RED + 8 * 36 * 4;               // float [64]
 constexpr int OFF_HS = OFF_FIN + 64 * 4;                    // float [2 wg][128][16] per-warpgroup partial H numerators
 constexpr int OFF_BAR = OFF_HS + 2 * 128 * 16 * 4;          // mbarriers
-constexpr int NBAR = 2 * NS + 2 + 2 + 2 + 3;
+constexpr int NBAR = 2 * NS + 2 + 2 + 2 + 2 + 3;
 constexpr int OFF_SLOT = OFF_BAR + NBAR * 8;
 constexpr int SMEM_BYTES = OFF_SLOT + 16;
 
@@ -76,6 +78,9 @@ __device__ __forceinline__ int wop_index(int part, int k, int b) { return ((((b 
 __device__ __forceinline__ int hop_index(int part, int f, int k) { return ((((f >> 3) * 3 + part) * KB + (k >> 3)) << 6) + ((f & 7) << 3) + (k & 7); }
 
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+// register re-distribution between the control warpgroup and the epilogue warpgroups (whole warpgroup executes it)
+__device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 88;" ::: "memory"); }
+__device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 208;" ::: "memory"); }
 
 // packed convert: low half <- a, high half <- b (F2FP.BF16.F32.PACK_AB, full-rate; the C++ intrinsic compiled to two
 // scalar F2F on the XU pipe)
@@ -131,7 +136,8 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
   uint64_t* r_full = p_full + 2;      // [2]
   uint64_t* b_full = r_full + 2;      // [2] second MMA of a step retired: its partial sits in TM_ACC + 32 g
   // three separate "operands ready" barriers so that two completions can never pile up unobserved on one of them
-  uint64_t* buf_ready = b_full + 2;     // buffer prologue done
+  uint64_t* p_free = b_full + 2;      // [2] the epilogue holds P of its current step in registers: buffer reusable
+  uint64_t* buf_ready = p_free + 2;     // buffer prologue done
   uint64_t* prep_ready = buf_ready + 1; // tile prep (H-update) done
   uint64_t* w_ready = prep_ready + 1;   // W-update done
   uint32_t* slot = reinterpret_cast<uint32_t*>(smem + OFF_SLOT);
@@ -145,7 +151,7 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
 
   if (tid == 0) {
     for (int i = 0; i < NS; i++) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 4); }
-    for (int i = 0; i < 2; i++) { mbar_init(&p_full[i], 1); mbar_init(&r_full[i], 4); mbar_init(&b_full[i], 1); }
+    for (int i = 0; i < 2; i++) { mbar_init(&p_full[i], 1); mbar_init(&r_full[i], 4); mbar_init(&b_full[i], 1); mbar_init(&p_free[i], 4); }
     mbar_init(buf_ready, 8);
     mbar_init(prep_ready, 8);
     mbar_init(w_ready, 8);
@@ -159,6 +165,8 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
   tc_fence_after();
   const uint32_t tbase = *slot;
 
+  if (warp < 4) {
+  reg_dec(); // control warpgroup gives registers back; the epilogue warpgroups take them
   if (warp == 0) {
     // =========================================== TMA producer ===========================================
     if (lane == 0) {
@@ -199,43 +207,64 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
       constexpr uint32_t ID_P2A = make_idesc_bf16(128, 64, 1, 0);
       constexpr uint32_t ID_P2B32 = make_idesc_bf16(128, 32, 0, 1), ID_P2B16 = make_idesc_bf16(128, 16, 0, 1);
       uint32_t n = 0, buf_cnt = 0, prep_cnt = 0, w_cnt = 0;
-      // pending second-stage MMA (issued one step late so the next step's first MMA overlaps this step's epilogue)
-      int pend_valid = 0, pend_phase = 0, pend_g = 0, pend_blk = 0;
-      uint32_t pend_k = 0;
-      auto issue_b = [&]() {
-        if (!pend_valid) return;
-        mbar_wait(&r_full[pend_g], pend_k & 1);
+      // Second-stage MMAs are issued two steps late: A(n) [needs P buffer g free: p_free(n-2), signalled as soon as the
+      // epilogue has pulled P(n-2) into registers], then B(n-2) [needs R(n-2): r_full].  So the first MMA of step n
+      // runs while step n-2's ratio is still being computed, and each warpgroup finds its next P tile ready.
+      struct Pend { int phase, g, blk; uint32_t k; };
+      Pend f0{}, f1{}; // oldest, newest (explicit slots: an indexed array would live in local memory)
+      int npend = 0;
+      auto issue_b_one = [&]() {
+        const Pend pd = f0;
+        f0 = f1;
+        npend--;
+        mbar_wait(&r_full[pd.g], pd.k & 1);
         tc_fence_after();
-        const uint32_t rh = tbase + TM_R + 96 * pend_g, rm = rh + 32, rl = rh + 64;
-        const bool ph1 = pend_phase == 1;
-        const uint32_t dacc = tbase + TM_ACC + 32 * pend_g;
+        const uint32_t rbase = tbase + TM_R + RCOLS * pd.g;
+        const bool ph1 = pd.phase == 1;
+        const uint32_t dacc = tbase + TM_ACC + 32 * pd.g;
         const uint32_t base = ph1 ? wop_a : hop_a;
         const uint32_t id32 = ph1 ? ID_P1B32 : ID_P2B32, id16 = ph1 ? ID_P1B16 : ID_P2B16;
 #pragma unroll
-        for (int j = 0; j < 4; j++) { // K-step j = 16 bins (phase 1) / 16 frames (phase 2) = block rows pend_blk + 2j, +1
-          const uint32_t off = (uint32_t) (pend_blk + 2 * j) * ROWB;
+        for (int j = 0; j < 4; j++) { // K-step j = 16 bins (phase 1) / 16 frames (phase 2) = block rows blk + 2j, +1
+          const uint32_t off = (uint32_t) (pd.blk + 2 * j) * ROWB;
           // The tensor core adds into the fp32 accumulator with truncation, so every accumulate costs up to one ulp of
           // the accumulator, always in the same direction.  Columns [0,16) therefore receive ONLY the leading term
           // R_hi X_hi (one add per K-step); all correction terms go to the small-magnitude columns [16,32).
           const uint64_t b0 = make_smem_desc(base + off, ROWB, 128);                // parts hi, mid side by side along N
           const uint64_t b1 = make_smem_desc(base + off + 1 * KB * 128, ROWB, 128); // part mid
           const uint64_t b2 = make_smem_desc(base + off + 2 * KB * 128, ROWB, 128); // part lo
-          mma_ts(dacc, rh + 8 * j, b0, id32, j ? 1u : 0u);                       // R_hi  [X_hi | X_mid]
-          mma_ts(dacc + 16, rm + 8 * j, b0, id16, 1u);                           // R_mid  X_hi
-          mma_ts(dacc + 16, rm + 8 * j, b1, id16, 1u);                           // R_mid  X_mid
-          mma_ts(dacc + 16, rl + 8 * j, b0, id16, 1u);                           // R_lo   X_hi
-          mma_ts(dacc + 16, rh + 8 * j, b2, id16, 1u);                           // R_hi   X_lo
+          const uint32_t rh = rbase + 8 * j;
+          mma_ts(dacc, rh, b0, id32, j ? 1u : 0u);                               // R_hi  [X_hi | X_mid]
+          mma_ts(dacc + 16, rh, b2, id16, 1u);                                   // R_hi   X_lo
+          if (RP == 3) {
+            mma_ts(dacc + 16, rh + 32, b0, id16, 1u);                            // R_mid  X_hi
+            mma_ts(dacc + 16, rh + 32, b1, id16, 1u);                            // R_mid  X_mid
+            mma_ts(dacc + 16, rh + 64, b0, id16, 1u);                            // R_lo   X_hi
+          } else {
+            mma_ts(dacc + 16, rh + 32, b0, id16, 1u);                            // R_lo   X_hi
+            mma_ts(dacc + 16, rh + 32, b1, id16, 1u);                            // R_lo   X_mid
+          }
         }
-        mma_commit(&b_full[pend_g]); // the epilogue adds this partial to its fp32 running sums
-        pend_valid = 0;
+        mma_commit(&b_full[pd.g]); // the epilogue adds this partial to its fp32 running sums
       };
+      auto flush_b = [&]() { while (npend) issue_b_one(); };
       // first-stage MMA: six significant terms of (A_hi + A_mid + A_lo)(B_hi + B_mid + B_lo)
-      auto issue_a = [&](uint32_t dP, uint32_t a_base, uint32_t b_base, uint32_t idesc) {
+      auto issue_step = [&](int phase, int blk, uint32_t a_base, uint32_t b_base, uint32_t idesc) {
+        const int g = n & 1;
+        if (n >= 2) mbar_wait(&p_free[g], ((n - 2) >> 1) & 1); // P(n-2) is in the epilogue's registers
+        tc_fence_after();
+        const uint32_t dP = tbase + TM_P + 64 * g;
         constexpr int pa[6] = {0, 0, 1, 0, 2, 1}, pb[6] = {0, 1, 0, 2, 0, 1};
 #pragma unroll
         for (int i = 0; i < 6; i++)
           mma_ss(dP, make_smem_desc(a_base + pa[i] * KB * 128, 128, ROWB), make_smem_desc(b_base + pb[i] * KB * 128, 128, ROWB), idesc,
                  i ? 1u : 0u);
+        mma_commit(&p_full[g]);
+        if (npend == 2) issue_b_one();
+        Pend nw; nw.phase = phase; nw.g = g; nw.blk = blk; nw.k = n >> 1;
+        if (npend == 0) f0 = nw; else f1 = nw;
+        npend++;
+        n++;
       };
       for (int buf = blockIdx.x; buf < d.batch; buf += gridDim.x) {
         mbar_wait(buf_ready, buf_cnt & 1); buf_cnt++; // operands of this buffer are in shared memory
@@ -244,47 +273,39 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
           const bool p1 = sc.p1(pass), p2 = sc.p2(pass);
           for (int t = 0; t < T; t++) {
             if (p1) {
-              for (int c = 0; c < C1; c++, n++) {
-                const int g = n & 1;
-                issue_a(tbase + TM_P + 64 * g, hop_a + (uint32_t) (16 * t) * ROWB, wop_a + (uint32_t) (8 * c) * ROWB, ID_P1A);
-                mma_commit(&p_full[g]);
-                issue_b();
-                pend_valid = 1; pend_phase = 1; pend_g = g; pend_k = n >> 1; pend_blk = 8 * c;
-              }
-              issue_b(); // the tile's H numerator must be complete before the tile prep
+              for (int c = 0; c < C1; c++)
+                issue_step(1, 8 * c, hop_a + (uint32_t) (16 * t) * ROWB, wop_a + (uint32_t) (8 * c) * ROWB, ID_P1A);
+              flush_b(); // the tile's H numerator must be complete before the tile prep
             }
             mbar_wait(prep_ready, prep_cnt & 1); prep_cnt++; // tile prep done: H_op(t) updated
             tc_fence_after();
             if (p2) {
               for (int m = 0; m < MT; m++)
-                for (int s = 0; s < 2; s++, n++) {
-                  const int g = n & 1;
-                  issue_a(tbase + TM_P + 64 * g, wop_a + (uint32_t) (16 * m) * ROWB, hop_a + (uint32_t) (16 * t + 8 * s) * ROWB, ID_P2A);
-                  mma_commit(&p_full[g]);
-                  issue_b();
-                  pend_valid = 1; pend_phase = 2; pend_g = g; pend_k = n >> 1; pend_blk = 16 * t + 8 * s;
-                }
-              if (!p1 || t == T - 1) issue_b();
+                for (int s = 0; s < 2; s++)
+                  issue_step(2, 16 * t + 8 * s, wop_a + (uint32_t) (16 * m) * ROWB, hop_a + (uint32_t) (16 * t + 8 * s) * ROWB, ID_P2A);
+              if (!p1 || t == T - 1) flush_b();
             }
           }
           if (p2) {
-            issue_b();
+            flush_b();
             mbar_wait(w_ready, w_cnt & 1); w_cnt++; // W-update done: W_op rewritten
             tc_fence_after();
           }
         }
       }
     }
+  }
   } else {
+    reg_inc();
     // =========================================== epilogue warps =========================================
-    const int et = tid - 64;               // 0..255
-    const int wg = (warp - 2) >> 2;        // epilogue warpgroup 0/1
-    const int ew = warp - 2;               // 0..7
+    const int et = tid - 128;              // 0..255
+    const int wg = (warp - 4) >> 2;        // epilogue warpgroup 0/1
+    const int ew = warp - 4;               // 0..7
     const int q = warp & 3;                // TMEM lane quarter this warp may access
     const int r = 32 * q + lane;           // row (frame or bin) inside a 128-row tile
     const uint32_t lane_off = (uint32_t) (32 * q) << 16;
     const uint32_t tP = tbase + TM_P + 64 * wg + lane_off;
-    const uint32_t tR = tbase + TM_R + 96 * wg + lane_off;
+    const uint32_t tR = tbase + TM_R + RCOLS * wg + lane_off;
     const uint32_t tAcc = tbase + TM_ACC + 32 * wg + lane_off;
     const uint32_t tWsum = tbase + TM_WSUM + 64 * wg + lane_off; // + 16 m
     uint32_t n = 0;
@@ -328,17 +349,22 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
     for (int x = 0; x < 8; x++) voff[x] = (uint32_t) ((((lane >> 2) ^ x) << 4) + ((lane & 3) << 2));
 
     // ratio of 32 consecutive columns held in p[] against 32 values v[] -> 3-way split, stored to TMEM
-    auto ratio_store = [&](const uint32_t (&p)[32], const float (&v)[32], int h) {
+    auto ratio_store = [&](const uint32_t* p, const float (&v)[32], int h) {
       uint32_t ph[16], pm[16], pl[16];
 #pragma unroll
       for (int j = 0; j < 16; j++) {
         float r0 = v[2 * j] * rcp_fast(fmaxf(__uint_as_float(p[2 * j]), kEps));
         float r1 = v[2 * j + 1] * rcp_fast(fmaxf(__uint_as_float(p[2 * j + 1]), kEps));
-        split3(r0, r1, ph[j], pm[j], pl[j]);
+        if (RP == 3) {
+          split3(r0, r1, ph[j], pm[j], pl[j]);
+        } else {
+          ph[j] = cvt2(r0, r1);
+          pm[j] = cvt2(r0 - bf16lo_to_f(ph[j]), r1 - bf16hi_to_f(ph[j]));
+        }
       }
       tmem_st16(tR + 16 * h, ph);
       tmem_st16(tR + 32 + 16 * h, pm);
-      tmem_st16(tR + 64 + 16 * h, pl);
+      if (RP == 3) tmem_st16(tR + 64 + 16 * h, pl);
     };
 
     for (int buf = blockIdx.x; buf < d.batch; buf += gridDim.x) {
@@ -387,10 +413,15 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
               mbar_wait(&v_full[st], (n / NS) & 1);
               tc_fence_after();
               const uint8_t* vt = smem + OFF_V + st * STAGE;
-#pragma unroll 1
+              uint32_t p[64];
+              tmem_ld32(tP, *reinterpret_cast<uint32_t(*)[32]>(&p[0]));
+              tmem_ld32(tP + 32, *reinterpret_cast<uint32_t(*)[32]>(&p[32]));
+              tmem_wait_ld();
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&p_free[wg]); // the issuer may overwrite this P buffer with step n+2 now
+#pragma unroll
               for (int h = 0; h < 2; h++) {
-                uint32_t p[32];
-                tmem_ld32(tP + 32 * h, p);
                 float v[32];
                 const uint8_t* row = vt + h * 16384 + r * 128;
 #pragma unroll
@@ -398,8 +429,7 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
                   float4 x = *reinterpret_cast<const float4*>(row + ((c4 ^ (r & 7)) << 4));
                   v[4 * c4] = x.x; v[4 * c4 + 1] = x.y; v[4 * c4 + 2] = x.z; v[4 * c4 + 3] = x.w;
                 }
-                tmem_wait_ld();
-                ratio_store(p, v, h);
+                ratio_store(&p[32 * h], v, h);
               }
               tmem_wait_st();
               tc_fence_before();
@@ -497,16 +527,20 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
                 mbar_wait(&v_full[st], (n / NS) & 1);
                 tc_fence_after();
                 const uint8_t* vt = smem + OFF_V + st * STAGE + q * 8192; // box q: bins 128m + 32q .. +31, rows = 64 frames
-#pragma unroll 1
+                uint32_t p[64];
+                tmem_ld32(tP, *reinterpret_cast<uint32_t(*)[32]>(&p[0]));
+                tmem_ld32(tP + 32, *reinterpret_cast<uint32_t(*)[32]>(&p[32]));
+                tmem_wait_ld();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&p_free[wg]);
+#pragma unroll
                 for (int h = 0; h < 2; h++) {
-                  uint32_t p[32];
-                  tmem_ld32(tP + 32 * h, p);
                   float v[32];
                   const uint8_t* vh = vt + h * 32 * 128;
 #pragma unroll
                   for (int j = 0; j < 32; j++) v[j] = *reinterpret_cast<const float*>(vh + j * 128 + voff[j & 7]);
-                  tmem_wait_ld();
-                  ratio_store(p, v, h);
+                  ratio_store(&p[32 * h], v, h);
                 }
                 tmem_wait_st();
                 tc_fence_before();

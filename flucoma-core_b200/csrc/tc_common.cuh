@@ -34,10 +34,18 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity)
 {
   uint32_t ok;
+#ifdef FB200_TRYWAIT_HINT_NS
+  // optional suspend-time hint (measured: a large hint delays wake-ups and costs far more than the spin it avoids)
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok)
+               : "r"(smem_u32(bar)), "r"(parity), "r"((uint32_t) FB200_TRYWAIT_HINT_NS)
+               : "memory");
+#else
   asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                : "=r"(ok)
                : "r"(smem_u32(bar)), "r"(parity)
                : "memory");
+#endif
   return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
