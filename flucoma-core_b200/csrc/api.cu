@@ -3,6 +3,8 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <random>
 
@@ -680,6 +682,14 @@ int32_t fb200_selftest_tcgen05(fb200_plan* p, const float* in, int64_t n_in, flo
   FB_CUDA(p, cudaMemsetAsync(p->out_a.p, 0, sizeof(float) * (size_t) n_out, p->stream));
   FB_TRY(run_tc_selftest(p, p->stage.as<float>(), p->out_a.as<float>()));
   FB_CUDA(p, cudaMemcpyAsync(out, p->out_a.p, sizeof(float) * (size_t) n_out, cudaMemcpyDeviceToHost, p->stream));
+  if (const char* e = getenv("FB200_MMA_TIMING")) { // developer aid: cycles per small tcgen05.mma, printed to stderr
+    FB_CUDA(p, p->out_b.ensure(sizeof(long long) * 32));
+    FB_TRY(run_tc_mma_timing(p, p->out_b.as<long long>(), atoi(e) > 0 ? atoi(e) : 256));
+    long long h[20];
+    FB_CUDA(p, cudaMemcpyAsync(h, p->out_b.p, sizeof(h), cudaMemcpyDeviceToHost, p->stream));
+    FB_CUDA(p, cudaStreamSynchronize(p->stream));
+    for (int v = 0; v < 10; v++) fprintf(stderr, "mma_timing variant %d: issue %.1f cyc, issue+exec %.1f cyc per MMA\n", v, h[2 * v] / 1000.0, h[2 * v + 1] / 1000.0);
+  }
   t.mark(1);
   return finish(p, t, 1);
 }

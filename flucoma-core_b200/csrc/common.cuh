@@ -165,6 +165,7 @@ void launch_ola(Plan* p, const float* y, int64_t nsig, int64_t F, int64_t n, flo
 // kernels_tc_selftest.cu ---------------------------------------------------------------------------------------
 int32_t make_v_tensor_map(Plan* p, void* tmap_out, const float* V, int64_t Bp, int64_t Fp, int64_t batch, int box_rows);
 int32_t run_tc_selftest(Plan* p, const float* in, float* out);
+int32_t run_tc_mma_timing(Plan* p, long long* d_out, int reps);
 
 // kernels_nmf_tc.cu ---------------------------------------------------------------------------------------------
 bool tc_eligible(const NmfDev& d);

@@ -35,6 +35,8 @@
 #include "tc_common.cuh"
 
 #include <cuda.h>
+#include <cstdio>
+#include <cstdlib>
 
 namespace fb200 {
 using namespace tc;
@@ -54,8 +56,9 @@ constexpr uint32_t TM_P = 0;      // + 64 g
 constexpr int RP = 2;             // parts of the ratio operand R written to TMEM (3 = exact fp32, 2 = hi + lo)
 constexpr uint32_t RCOLS = 32 * RP;
 constexpr uint32_t TM_R = 128;    // + RCOLS g : hi [0,32) mid [32,64) lo [64,96)
-constexpr uint32_t TM_ACC = 320;  // + 32 g : per-step partial of the second MMA, [0,16) leading term, [16,32) corrections
-constexpr uint32_t TM_WSUM = 384; // + 64 wg + 16 m : fp32 running sums of the W numerator, added by the epilogue (RN)
+constexpr uint32_t ACOLS = 48;    // per-step partial of the second MMA: [0,16) leading term, [16,48) corrections
+constexpr uint32_t TM_ACC = 256;  // + ACOLS g
+constexpr uint32_t TM_WSUM = 352; // + 64 wg + 16 m : fp32 running sums of the W numerator, added by the epilogue (RN)
 
 // shared memory map (bytes)
 constexpr int OFF_V = 0;
@@ -116,8 +119,13 @@ struct Sched {
 
 using namespace tcn;
 
+// developer timeline: CTA 0 records clock64() at a few points of steps [DBG_N0, DBG_N0 + 32) when a debug buffer is given
+#define DBG_N0 192
+#define DBG_MARK(slot, nn) do { if (dbg && blockIdx.x == 0 && (nn) >= DBG_N0 && (nn) < DBG_N0 + 32 && lane == 0) dbg[((nn) - DBG_N0) * 16 + (slot)] = clock64(); } while (0)
+
 __global__ void __launch_bounds__(NTHREADS, 1)
-k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_constant__ CUtensorMap tmap2, int iters, int upd_w, int upd_h)
+k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_constant__ CUtensorMap tmap2, int iters, int upd_w, int upd_h,
+         long long* dbg)
 {
   extern __shared__ __align__(1024) uint8_t smem[];
   __nv_bfloat16* wop = reinterpret_cast<__nv_bfloat16*>(smem + OFF_WOP);
@@ -200,68 +208,75 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
     }
   } else if (warp == 1) {
     // =========================================== MMA issuer =============================================
-    if (lane == 0) {
+    { // the whole warp runs the issue loop converged; the MMA / commit wrappers elect one lane
+      // The issuer is ONE thread and every step needs 22 MMAs, so its instruction count per MMA is what paces the whole
+      // pipeline (measured: with naive descriptor construction the kernel ran at the same speed with the epilogue
+      // math removed).  All descriptors are therefore pre-split into a constant high word and a low word that only
+      // needs one integer add per MMA (the 14-bit start-address field never carries into the LBO field).
       const uint32_t wop_a = smem_u32(wop), hop_a = smem_u32(hop);
       constexpr uint32_t ID_P1A = make_idesc_bf16(128, 64, 0, 1);
-      constexpr uint32_t ID_P1B32 = make_idesc_bf16(128, 32, 0, 0), ID_P1B16 = make_idesc_bf16(128, 16, 0, 0);
+      constexpr uint32_t ID_P1B48 = make_idesc_bf16(128, 48, 0, 0), ID_P1B16 = make_idesc_bf16(128, 16, 0, 0);
       constexpr uint32_t ID_P2A = make_idesc_bf16(128, 64, 1, 0);
-      constexpr uint32_t ID_P2B32 = make_idesc_bf16(128, 32, 0, 1), ID_P2B16 = make_idesc_bf16(128, 16, 0, 1);
+      constexpr uint32_t ID_P2B48 = make_idesc_bf16(128, 48, 0, 1), ID_P2B16 = make_idesc_bf16(128, 16, 0, 1);
+      constexpr uint32_t HI_A = (ROWB >> 4) | (1u << 14);  // first MMA operands: SBO = ROWB (block rows), version 1
+      constexpr uint32_t HI_B = (128u >> 4) | (1u << 14);  // second MMA B operand: SBO = 128 (parts / component blocks along N)
+      constexpr uint32_t LO_A = (128u >> 4) << 16;         // LBO = 128 (component blocks along K)
+      constexpr uint32_t LO_B = (ROWB >> 4) << 16;         // LBO = ROWB (block rows along K)
+      constexpr uint32_t RSTEP = ROWB >> 4;                // one block row, in descriptor address units
+      constexpr uint32_t PSTEP = (KB * 128) >> 4;          // one split part
+      const uint32_t wlo_a = (wop_a >> 4) | LO_A, hlo_a = (hop_a >> 4) | LO_A; // first MMA, part 0, block row 0
+      const uint32_t wlo_b = (wop_a >> 4) | LO_B, hlo_b = (hop_a >> 4) | LO_B; // second MMA B operand
       uint32_t n = 0, buf_cnt = 0, prep_cnt = 0, w_cnt = 0;
       // Second-stage MMAs are issued two steps late: A(n) [needs P buffer g free: p_free(n-2), signalled as soon as the
       // epilogue has pulled P(n-2) into registers], then B(n-2) [needs R(n-2): r_full].  So the first MMA of step n
       // runs while step n-2's ratio is still being computed, and each warpgroup finds its next P tile ready.
-      struct Pend { int phase, g, blk; uint32_t k; };
+      struct Pend { uint32_t blo, id48, id16, g, k; };
       Pend f0{}, f1{}; // oldest, newest (explicit slots: an indexed array would live in local memory)
       int npend = 0;
       auto issue_b_one = [&]() {
         const Pend pd = f0;
         f0 = f1;
         npend--;
+        DBG_MARK(3, 2 * pd.k + pd.g);
         mbar_wait(&r_full[pd.g], pd.k & 1);
         tc_fence_after();
+        DBG_MARK(4, 2 * pd.k + pd.g);
         const uint32_t rbase = tbase + TM_R + RCOLS * pd.g;
-        const bool ph1 = pd.phase == 1;
-        const uint32_t dacc = tbase + TM_ACC + 32 * pd.g;
-        const uint32_t base = ph1 ? wop_a : hop_a;
-        const uint32_t id32 = ph1 ? ID_P1B32 : ID_P2B32, id16 = ph1 ? ID_P1B16 : ID_P2B16;
+        const uint32_t dacc = tbase + TM_ACC + ACOLS * pd.g;
 #pragma unroll
         for (int j = 0; j < 4; j++) { // K-step j = 16 bins (phase 1) / 16 frames (phase 2) = block rows blk + 2j, +1
-          const uint32_t off = (uint32_t) (pd.blk + 2 * j) * ROWB;
           // The tensor core adds into the fp32 accumulator with truncation, so every accumulate costs up to one ulp of
           // the accumulator, always in the same direction.  Columns [0,16) therefore receive ONLY the leading term
           // R_hi X_hi (one add per K-step); all correction terms go to the small-magnitude columns [16,32).
-          const uint64_t b0 = make_smem_desc(base + off, ROWB, 128);                // parts hi, mid side by side along N
-          const uint64_t b1 = make_smem_desc(base + off + 1 * KB * 128, ROWB, 128); // part mid
-          const uint64_t b2 = make_smem_desc(base + off + 2 * KB * 128, ROWB, 128); // part lo
+          const uint32_t b0 = pd.blo + 2 * j * RSTEP; // parts hi, mid, lo side by side along N
           const uint32_t rh = rbase + 8 * j;
-          mma_ts(dacc, rh, b0, id32, j ? 1u : 0u);                               // R_hi  [X_hi | X_mid]
-          mma_ts(dacc + 16, rh, b2, id16, 1u);                                   // R_hi   X_lo
-          if (RP == 3) {
-            mma_ts(dacc + 16, rh + 32, b0, id16, 1u);                            // R_mid  X_hi
-            mma_ts(dacc + 16, rh + 32, b1, id16, 1u);                            // R_mid  X_mid
-            mma_ts(dacc + 16, rh + 64, b0, id16, 1u);                            // R_lo   X_hi
-          } else {
-            mma_ts(dacc + 16, rh + 32, b0, id16, 1u);                            // R_lo   X_hi
-            mma_ts(dacc + 16, rh + 32, b1, id16, 1u);                            // R_lo   X_mid
-          }
+          if (j == 0) mma_ts_lohi<0>(dacc, rh, b0, HI_B, pd.id48);               // R_hi [X_hi | X_mid | X_lo] -> cols [0,48)
+          else mma_ts_lohi<1>(dacc, rh, b0, HI_B, pd.id48);
+          mma_ts_lohi<1>(dacc + 16, rh + 32, b0, HI_B, pd.id16);                 // R_lo  X_hi              -> cols [16,32)
+          if (RP == 3) mma_ts_lohi<1>(dacc + 16, rh + 64, b0, HI_B, pd.id16);
         }
-        mma_commit(&b_full[pd.g]); // the epilogue adds this partial to its fp32 running sums
+        mma_commit_warp(&b_full[pd.g]); // the epilogue adds this partial to its fp32 running sums
+        DBG_MARK(5, 2 * pd.k + pd.g);
       };
       auto flush_b = [&]() { while (npend) issue_b_one(); };
-      // first-stage MMA: six significant terms of (A_hi + A_mid + A_lo)(B_hi + B_mid + B_lo)
-      auto issue_step = [&](int phase, int blk, uint32_t a_base, uint32_t b_base, uint32_t idesc) {
-        const int g = n & 1;
+      // first-stage MMA: six significant terms of (A_hi + A_mid + A_lo)(B_hi + B_mid + B_lo); then queue the second stage
+      auto issue_step = [&](uint32_t alo, uint32_t blo, uint32_t idesc, uint32_t b2lo, uint32_t id48, uint32_t id16) {
+        const uint32_t g = n & 1;
+        DBG_MARK(0, n);
         if (n >= 2) mbar_wait(&p_free[g], ((n - 2) >> 1) & 1); // P(n-2) is in the epilogue's registers
         tc_fence_after();
+        DBG_MARK(1, n);
         const uint32_t dP = tbase + TM_P + 64 * g;
-        constexpr int pa[6] = {0, 0, 1, 0, 2, 1}, pb[6] = {0, 1, 0, 2, 0, 1};
-#pragma unroll
-        for (int i = 0; i < 6; i++)
-          mma_ss(dP, make_smem_desc(a_base + pa[i] * KB * 128, 128, ROWB), make_smem_desc(b_base + pb[i] * KB * 128, 128, ROWB), idesc,
-                 i ? 1u : 0u);
-        mma_commit(&p_full[g]);
+        mma_ss_lohi<0>(dP, alo, HI_A, blo, HI_A, idesc);                          // hi  hi
+        mma_ss_lohi<1>(dP, alo, HI_A, blo + PSTEP, HI_A, idesc);                  // hi  mid
+        mma_ss_lohi<1>(dP, alo + PSTEP, HI_A, blo, HI_A, idesc);                  // mid hi
+        mma_ss_lohi<1>(dP, alo, HI_A, blo + 2 * PSTEP, HI_A, idesc);              // hi  lo
+        mma_ss_lohi<1>(dP, alo + 2 * PSTEP, HI_A, blo, HI_A, idesc);              // lo  hi
+        mma_ss_lohi<1>(dP, alo + PSTEP, HI_A, blo + PSTEP, HI_A, idesc);          // mid mid
+        mma_commit_warp(&p_full[g]);
+        DBG_MARK(2, n);
         if (npend == 2) issue_b_one();
-        Pend nw; nw.phase = phase; nw.g = g; nw.blk = blk; nw.k = n >> 1;
+        Pend nw; nw.blo = b2lo; nw.id48 = id48; nw.id16 = id16; nw.g = g; nw.k = n >> 1;
         if (npend == 0) f0 = nw; else f1 = nw;
         npend++;
         n++;
@@ -273,16 +288,17 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
           const bool p1 = sc.p1(pass), p2 = sc.p2(pass);
           for (int t = 0; t < T; t++) {
             if (p1) {
-              for (int c = 0; c < C1; c++)
-                issue_step(1, 8 * c, hop_a + (uint32_t) (16 * t) * ROWB, wop_a + (uint32_t) (8 * c) * ROWB, ID_P1A);
+              for (int c = 0; c < C1; c++) // A = H rows of tile t, B = W rows of chunk c; second stage: B = W rows of chunk c
+                issue_step(hlo_a + 16 * t * RSTEP, wlo_a + 8 * c * RSTEP, ID_P1A, wlo_b + 8 * c * RSTEP, ID_P1B48, ID_P1B16);
               flush_b(); // the tile's H numerator must be complete before the tile prep
             }
             mbar_wait(prep_ready, prep_cnt & 1); prep_cnt++; // tile prep done: H_op(t) updated
             tc_fence_after();
             if (p2) {
               for (int m = 0; m < MT; m++)
-                for (int s = 0; s < 2; s++)
-                  issue_step(2, 16 * t + 8 * s, wop_a + (uint32_t) (16 * m) * ROWB, hop_a + (uint32_t) (16 * t + 8 * s) * ROWB, ID_P2A);
+                for (int s = 0; s < 2; s++) // A = W rows of tile m, B = H rows of half s; second stage: B = H rows of half s
+                  issue_step(wlo_a + 16 * m * RSTEP, hlo_a + (16 * t + 8 * s) * RSTEP, ID_P2A, hlo_b + (16 * t + 8 * s) * RSTEP, ID_P2B48,
+                             ID_P2B16);
               if (!p1 || t == T - 1) flush_b();
             }
           }
@@ -306,7 +322,7 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
     const uint32_t lane_off = (uint32_t) (32 * q) << 16;
     const uint32_t tP = tbase + TM_P + 64 * wg + lane_off;
     const uint32_t tR = tbase + TM_R + RCOLS * wg + lane_off;
-    const uint32_t tAcc = tbase + TM_ACC + 32 * wg + lane_off;
+    const uint32_t tAcc = tbase + TM_ACC + ACOLS * wg + lane_off;
     const uint32_t tWsum = tbase + TM_WSUM + 64 * wg + lane_off; // + 16 m
     uint32_t n = 0;
     // The tensor core truncates when it adds into its fp32 accumulator, so long in-TMEM accumulation chains drift in
@@ -323,19 +339,20 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
       if (!out_valid) return;
       mbar_wait(&b_full[wg], out_par);
       tc_fence_after();
-      uint32_t a[32];
+      uint32_t a[32], a2[16];
       tmem_ld32(tAcc, a);
+      tmem_ld16(tAcc + 32, a2);
       if (out_phase == 1) {
         tmem_wait_ld();
 #pragma unroll
-        for (int k = 0; k < K; k++) hsum[k] += __uint_as_float(a[k]) + __uint_as_float(a[16 + k]);
+        for (int k = 0; k < K; k++) hsum[k] += __uint_as_float(a[k]) + (__uint_as_float(a[16 + k]) + __uint_as_float(a2[k]));
       } else {
         uint32_t w[16];
         if (!out_first) tmem_ld16(tWsum + 16 * out_m, w);
         tmem_wait_ld();
 #pragma unroll
         for (int k = 0; k < K; k++) {
-          float x = __uint_as_float(a[k]) + __uint_as_float(a[16 + k]);
+          float x = __uint_as_float(a[k]) + (__uint_as_float(a[16 + k]) + __uint_as_float(a2[k]));
           w[k] = __float_as_uint(out_first ? x : __uint_as_float(w[k]) + x);
         }
         tmem_st16(tWsum + 16 * out_m, w);
@@ -351,8 +368,13 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
     // ratio of 32 consecutive columns held in p[] against 32 values v[] -> 3-way split, stored to TMEM
     auto ratio_store = [&](const uint32_t* p, const float (&v)[32], int h) {
       uint32_t ph[16], pm[16], pl[16];
+      (void) pl;
 #pragma unroll
       for (int j = 0; j < 16; j++) {
+#ifdef FB200_TC_EXPERIMENT_NOMATH
+        ph[j] = p[2 * j] ^ __float_as_uint(v[2 * j]); pm[j] = p[2 * j + 1] ^ __float_as_uint(v[2 * j + 1]);
+        continue;
+#endif
         float r0 = v[2 * j] * rcp_fast(fmaxf(__uint_as_float(p[2 * j]), kEps));
         float r1 = v[2 * j + 1] * rcp_fast(fmaxf(__uint_as_float(p[2 * j + 1]), kEps));
         if (RP == 3) {
@@ -361,6 +383,13 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
           ph[j] = cvt2(r0, r1);
           pm[j] = cvt2(r0 - bf16lo_to_f(ph[j]), r1 - bf16hi_to_f(ph[j]));
         }
+      }
+      // R[g] is still being read by the second MMA of this warpgroup's previous step until b_full: only now, with the
+      // new ratios already sitting in registers, wait for it (and collect that step's partial sums)
+      if (h == 0) {
+        if (q == 0) DBG_MARK(9, n);
+        drain();
+        if (q == 0) DBG_MARK(10, n);
       }
       tmem_st16(tR + 16 * h, ph);
       tmem_st16(tR + 32 + 16 * h, pm);
@@ -395,7 +424,10 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
         hop[hop_index(0, f, k)] = hi; hop[hop_index(1, f, k)] = mi; hop[hop_index(2, f, k)] = lo;
       }
       for (int f = et; f < Fp; f += 256) VN[f] = gV[(int64_t) f * Bp + BT];
-      if (et < K) hden[et] = d.hden[(int64_t) buf * K + et];
+      if (et < K) {
+        hden[et] = d.hden[(int64_t) buf * K + et];
+        fin[48 + et] = 1.0f / fmaxf(hden[et], kEps);
+      }
       fence_proxy_async();
       epi_bar();
       if (lane == 0) mbar_arrive(buf_ready);
@@ -408,10 +440,12 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
             for (int c = 0; c < C1; c++, n++) {
               if ((int) (n & 1) != wg) continue;
               const uint32_t st = n % NS;
-              drain(); // collect the previous step's partial before its accumulator columns are reused
+              if (q == 0) DBG_MARK(6, n);
               mbar_wait(&p_full[wg], (n >> 1) & 1);
+              if (q == 0) DBG_MARK(7, n);
               mbar_wait(&v_full[st], (n / NS) & 1);
               tc_fence_after();
+              if (q == 0) DBG_MARK(8, n);
               const uint8_t* vt = smem + OFF_V + st * STAGE;
               uint32_t p[64];
               tmem_ld32(tP, *reinterpret_cast<uint32_t(*)[32]>(&p[0]));
@@ -429,12 +463,17 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
                   float4 x = *reinterpret_cast<const float4*>(row + ((c4 ^ (r & 7)) << 4));
                   v[4 * c4] = x.x; v[4 * c4 + 1] = x.y; v[4 * c4 + 2] = x.z; v[4 * c4 + 3] = x.w;
                 }
+                if (h == 1) { // last read of this V stage is issued: hand it back to the producer half a step early
+                  __syncwarp();
+                  if (lane == 0) mbar_arrive(&v_empty[st]);
+                }
                 ratio_store(&p[32 * h], v, h);
               }
               tmem_wait_st();
               tc_fence_before();
               __syncwarp();
-              if (lane == 0) { mbar_arrive(&r_full[wg]); mbar_arrive(&v_empty[st]); }
+              if (lane == 0) mbar_arrive(&r_full[wg]);
+              if (q == 0) DBG_MARK(11, n);
               out_valid = 1; out_phase = 1; out_par = (n >> 1) & 1;
             }
             drain(); // H numerator of this warpgroup's chunks complete (all MMAs reading H_op(t) have retired)
@@ -448,67 +487,77 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
           // ---------------- tile prep: H-update (if p1), W-denominator / Nyquist partials (if p2) ----------------
           {
             const int f = 128 * t + r;
-            float contrib[32];
+            const int k0 = 8 * wg; // this warpgroup splits / stores / reduces components [k0, k0 + 8) of every row
+            float h[16];
 #pragma unroll
-            for (int j = 0; j < 32; j++) contrib[j] = 0.f;
-            if ((lane & 1) == wg) { // the two warpgroups split the rows of the tile
-              float h[16];
+            for (int kb = 0; kb < KB; kb++) { // H[f][8kb..8kb+7] = hi + mid + lo, one 16-byte row per core matrix
+              float acc8[8];
 #pragma unroll
-              for (int kb = 0; kb < KB; kb++) { // H[f][8kb..8kb+7] = hi + mid + lo, one 16-byte row per core matrix
-                float acc8[8];
+              for (int j = 0; j < 8; j++) acc8[j] = 0.f;
 #pragma unroll
-                for (int j = 0; j < 8; j++) acc8[j] = 0.f;
-#pragma unroll
-                for (int pt = 2; pt >= 0; pt--) { // small parts first
-                  const uint4 u = *reinterpret_cast<const uint4*>(hop + hop_index(pt, f, 8 * kb));
-                  acc8[0] += bf16lo_to_f(u.x); acc8[1] += bf16hi_to_f(u.x); acc8[2] += bf16lo_to_f(u.y); acc8[3] += bf16hi_to_f(u.y);
-                  acc8[4] += bf16lo_to_f(u.z); acc8[5] += bf16hi_to_f(u.z); acc8[6] += bf16lo_to_f(u.w); acc8[7] += bf16hi_to_f(u.w);
-                }
-#pragma unroll
-                for (int j = 0; j < 8; j++) h[8 * kb + j] = acc8[j];
+              for (int pt = 2; pt >= 0; pt--) { // small parts first
+                const uint4 u = *reinterpret_cast<const uint4*>(hop + hop_index(pt, f, 8 * kb));
+                acc8[0] += bf16lo_to_f(u.x); acc8[1] += bf16hi_to_f(u.x); acc8[2] += bf16lo_to_f(u.y); acc8[3] += bf16hi_to_f(u.y);
+                acc8[4] += bf16lo_to_f(u.z); acc8[5] += bf16hi_to_f(u.z); acc8[6] += bf16lo_to_f(u.w); acc8[7] += bf16hi_to_f(u.w);
               }
-              const float vn = VN[f];
-              if (p1) {
-                float pn = 0.f;
 #pragma unroll
-                for (int k = 0; k < K; k++) pn = fmaf(h[k], WN[k], pn);
-                const float rn = vn / fmaxf(pn, kEps);
+              for (int j = 0; j < 8; j++) h[8 * kb + j] = acc8[j];
+            }
+            const float vn = VN[f];
+            if (p1) {
+              float pn = 0.f;
 #pragma unroll
-                for (int k = 0; k < K; k++) {
-                  float num = hs[r * 16 + k] + hs[(128 + r) * 16 + k]; // even + odd chunks
-                  num = fmaf(rn, WN[k], num);
-                  h[k] = h[k] * num / fmaxf(hden[k], kEps);      // NMF.hpp:170
-                }
+              for (int k = 0; k < K; k++) pn = fmaf(h[k], WN[k], pn);
+              const float rn = vn / fmaxf(pn, kEps);
 #pragma unroll
-                for (int kb = 0; kb < KB; kb++) {
-                  uint32_t ph[4], pm[4], pl[4];
+              for (int j4 = 0; j4 < 4; j4++) { // all 16 new values (the Nyquist term of phase 2 needs the whole new row)
+                const float4 a = *reinterpret_cast<const float4*>(hs + r * 16 + 4 * j4);         // even chunks
+                const float4 b = *reinterpret_cast<const float4*>(hs + (128 + r) * 16 + 4 * j4); // odd chunks
+                const float num[4] = {a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w};
 #pragma unroll
-                  for (int j = 0; j < 4; j++) split3(h[8 * kb + 2 * j], h[8 * kb + 2 * j + 1], ph[j], pm[j], pl[j]);
-                  *reinterpret_cast<uint4*>(hop + hop_index(0, f, 8 * kb)) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-                  *reinterpret_cast<uint4*>(hop + hop_index(1, f, 8 * kb)) = make_uint4(pm[0], pm[1], pm[2], pm[3]);
-                  *reinterpret_cast<uint4*>(hop + hop_index(2, f, 8 * kb)) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+                for (int i = 0; i < 4; i++) {
+                  const int k = 4 * j4 + i;
+                  h[k] = h[k] * fmaf(rn, WN[k], num[i]) * fin[48 + k];   // NMF.hpp:170, fin[48+k] = 1 / max(hden[k], eps)
                 }
               }
-              if (p2) {
-                float pn = 0.f;
+              uint32_t ph[4], pm[4], pl[4];
 #pragma unroll
-                for (int k = 0; k < K; k++) pn = fmaf(h[k], WN[k], pn);
-                const float rn = vn / fmaxf(pn, kEps);
-#pragma unroll
-                for (int k = 0; k < K; k++) { contrib[k] = h[k]; contrib[16 + k] = rn * h[k]; } // wden, Nyquist wnum
+              for (int j = 0; j < 4; j++) {
+                const float x0 = wg ? h[8 + 2 * j] : h[2 * j], x1 = wg ? h[9 + 2 * j] : h[2 * j + 1];
+                split3(x0, x1, ph[j], pm[j], pl[j]);
               }
+              *reinterpret_cast<uint4*>(hop + hop_index(0, f, k0)) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+              *reinterpret_cast<uint4*>(hop + hop_index(1, f, k0)) = make_uint4(pm[0], pm[1], pm[2], pm[3]);
+              *reinterpret_cast<uint4*>(hop + hop_index(2, f, k0)) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
             }
             if (p2) {
+              float pn = 0.f;
 #pragma unroll
-              for (int j = 0; j < 32; j++) {
-                float x = contrib[j];
+              for (int k = 0; k < K; k++) pn = fmaf(h[k], WN[k], pn);
+              const float rn = vn / fmaxf(pn, kEps);
+              float a[16]; // [0,8) W denominator terms, [8,16) Nyquist numerator terms of this warpgroup's components
 #pragma unroll
-                for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-                contrib[j] = x;
+              for (int j = 0; j < 8; j++) {
+                const float x = wg ? h[8 + j] : h[j];
+                a[j] = x;
+                a[8 + j] = rn * x;
               }
-              if (lane == 0) {
+              // vector butterfly: 16 values x 32 lanes reduced with 16 shuffles; lane l ends with the total of
+              // index 8*b16 + 4*b8 + 2*b4 + b2 (bX = bit X of l)
 #pragma unroll
-                for (int j = 0; j < 32; j++) part[(t * 8 + ew) * 32 + j] = contrib[j];
+              for (int o = 16, cnt = 8; o >= 2; o >>= 1, cnt >>= 1) {
+                const bool up = (lane & o) != 0;
+#pragma unroll
+                for (int i = 0; i < cnt; i++) {
+                  const float send = up ? a[i] : a[i + cnt];
+                  const float keep = up ? a[i + cnt] : a[i];
+                  a[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+                }
+              }
+              a[0] += __shfl_xor_sync(0xffffffffu, a[0], 1);
+              if ((lane & 1) == 0) {
+                const int idx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+                part[(t * 8 + ew) * 32 + (idx < 8 ? k0 + idx : 16 + k0 + idx - 8)] = a[0];
               }
             }
             fence_proxy_async();
@@ -522,7 +571,6 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
               for (int s = 0; s < 2; s++, n++) {
                 if ((int) (n & 1) != wg) continue;
                 const uint32_t st = n % NS;
-                drain();
                 mbar_wait(&p_full[wg], (n >> 1) & 1);
                 mbar_wait(&v_full[st], (n / NS) & 1);
                 tc_fence_after();
@@ -540,12 +588,16 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
                   const uint8_t* vh = vt + h * 32 * 128;
 #pragma unroll
                   for (int j = 0; j < 32; j++) v[j] = *reinterpret_cast<const float*>(vh + j * 128 + voff[j & 7]);
+                  if (h == 1) {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&v_empty[st]);
+                  }
                   ratio_store(&p[32 * h], v, h);
                 }
                 tmem_wait_st();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) { mbar_arrive(&r_full[wg]); mbar_arrive(&v_empty[st]); }
+                if (lane == 0) mbar_arrive(&r_full[wg]);
                 out_valid = 1; out_phase = 2; out_m = m; out_first = (t == 0); out_par = (n >> 1) & 1;
               }
           }
@@ -556,9 +608,11 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
           tc_fence_before();
           epi_bar(); // all partials of all tiles written, both warpgroups' running sums complete
           tc_fence_after();
-          if (et < 32) {
+          if (et < 32) { // component k = et & 15 was reduced by the 4 warps of warpgroup k >> 3
+            const int own = ((et & 15) >> 3) * 4;
             float s = 0.f;
-            for (int i = 0; i < T * 8; i++) s += part[i * 32 + et];
+            for (int tt = 0; tt < T; tt++)
+              for (int w4 = 0; w4 < 4; w4++) s += part[(tt * 8 + own + w4) * 32 + et];
             fin[et] = s; // [0,16) wden, [16,32) Nyquist wnum
           }
           epi_bar();
@@ -622,6 +676,7 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
             const float inv = norm ? (s2 > 0.f ? 1.0f / sqrtf(s2) : 0.f) : 1.0f;
             fin[32 + et] = inv;
             hden[et] = s1 * inv;                                           // sum_b W after normalisation
+            fin[48 + et] = 1.0f / fmaxf(s1 * inv, kEps);
           }
           epi_bar();
 #pragma unroll
@@ -696,7 +751,26 @@ int32_t tc_run(Plan* p, const NmfDev& d, int iters, bool upd_w, bool upd_h)
   int grid = std::min(d.batch, p->sm_count);
   while (p->kev.size() < p->kev_used + 2) { cudaEvent_t e; cudaEventCreate(&e); p->kev.push_back(e); }
   cudaEventRecord(p->kev[p->kev_used++], p->stream);
-  k_nmf_tc<<<grid, NTHREADS, SMEM_BYTES, p->stream>>>(d, tmap1, tmap2, iters, upd_w ? 1 : 0, upd_h ? 1 : 0);
+  long long* dbg = nullptr;
+  if (getenv("FB200_TC_TIMELINE")) { // developer aid: per-step timeline of CTA 0, dumped to stderr after the launch
+    FB_CUDA(p, p->out_b.ensure(sizeof(long long) * 32 * 16));
+    FB_CUDA(p, cudaMemsetAsync(p->out_b.p, 0, sizeof(long long) * 32 * 16, p->stream));
+    dbg = p->out_b.as<long long>();
+  }
+  k_nmf_tc<<<grid, NTHREADS, SMEM_BYTES, p->stream>>>(d, tmap1, tmap2, iters, upd_w ? 1 : 0, upd_h ? 1 : 0, dbg);
+  if (dbg) {
+    std::vector<long long> h(32 * 16);
+    FB_CUDA(p, cudaMemcpyAsync(h.data(), dbg, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost, p->stream));
+    FB_CUDA(p, cudaStreamSynchronize(p->stream));
+    long long t0 = 0;
+    for (auto v : h) if (v && (!t0 || v < t0)) t0 = v;
+    fprintf(stderr, "step | issuer: A_start A_pfree A_done B_start B_rfull B_done | epi: start p_full v_full half0 drained done\n");
+    for (int i = 0; i < 32; i++) {
+      fprintf(stderr, "%4d |", DBG_N0 + i);
+      for (int j = 0; j < 12; j++) fprintf(stderr, " %7lld", h[i * 16 + j] ? h[i * 16 + j] - t0 : -1);
+      fprintf(stderr, "\n");
+    }
+  }
   cudaEventRecord(p->kev[p->kev_used++], p->stream);
   p->launches++; p->launches_nmf++;
   FB_CUDA(p, cudaGetLastError());

@@ -189,4 +189,69 @@ int32_t run_tc_selftest(Plan* p, const float* in, float* out)
   return FB200_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Micro-benchmark of tcgen05.mma issue/execute cost for the small shapes the engine uses: `reps` back-to-back MMAs of
+// one form, timed with clock64 from first issue to commit completion.  out[v] = cycles per MMA (x1000) for variant v.
+__global__ void __launch_bounds__(128) k_tc_mma_timing(long long* out, int reps)
+{
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 65536);
+  uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 2);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < 65536 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u; // small bf16 values
+  if (tid == 0) { mbar_init(&bar[0], 1); mbar_fence_init(); }
+  if (warp == 0) tmem_alloc(slot, 512);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb = *slot;
+  uint32_t parity = 0;
+  const uint32_t sa = smem_u32(smem);
+  const uint32_t lo = (sa >> 4) | (8u << 16), hi = 48u | (1u << 14);
+  const uint32_t lob = (sa >> 4) | (48u << 16), hib = 8u | (1u << 14);
+  for (int v = 0; v < 10; v++) {
+    __syncthreads();
+    if (warp == 0) {
+      long long t0 = clock64();
+#define FB_LOOP(stmt) for (int i = 0; i < reps; i++) { stmt; }
+      switch (v) {
+      case 0: FB_LOOP(mma_ss_lohi<1>(tb, lo, hi, lo, hi, make_idesc_bf16(128, 64, 0, 1))) break;                 // SS N=64 same acc
+      case 1: FB_LOOP(mma_ss_lohi<1>(tb + 64 * (i & 1), lo, hi, lo, hi, make_idesc_bf16(128, 64, 0, 1))) break;  // SS N=64 two accs
+      case 2: FB_LOOP(mma_ss_lohi<1>(tb, lo, hi, lo, hi, make_idesc_bf16(128, 256, 0, 1))) break;                // SS N=256
+      case 3: FB_LOOP(mma_ts_lohi<1>(tb + 256, tb + 128, lob, hib, make_idesc_bf16(128, 16, 0, 0))) break;       // TS N=16 same acc
+      case 4: FB_LOOP(mma_ts_lohi<1>(tb + 256 + 16 * (i & 3), tb + 128, lob, hib, make_idesc_bf16(128, 16, 0, 0))) break; // TS N=16 4 accs
+      case 5: FB_LOOP(mma_ts_lohi<1>(tb + 256, tb + 128, lob, hib, make_idesc_bf16(128, 32, 0, 0))) break;       // TS N=32
+      case 6: FB_LOOP(mma_ts_lohi<1>(tb + 256, tb + 128, lob, hib, make_idesc_bf16(128, 128, 0, 0))) break;      // TS N=128
+      case 7: FB_LOOP(mma_ss_lohi<1>(tb + 256, lo, hi, lob, hib, make_idesc_bf16(128, 16, 0, 0))) break;         // SS N=16 same acc
+      case 8: FB_LOOP(mma_ts_lohi<1>(tb + 256, tb + 128 + 8 * (i & 3), lob, hib, make_idesc_bf16(128, 16, 0, 1))) break; // TS N=16 MN-major B
+      case 9: FB_LOOP(mma_ss_lohi<1>(tb + 64 * (i & 1), lo, hi, lo, hi, make_idesc_bf16(128, 64, 1, 0))) break;  // SS N=64, A MN-major
+      }
+#undef FB_LOOP
+      long long t1 = clock64();
+      mma_commit_warp(&bar[0]);
+      mbar_wait(&bar[0], parity);
+      long long t2 = clock64();
+      if (tid == 0) {
+        out[2 * v] = (t1 - t0) * 1000 / reps;      // issue cost per MMA (x1000)
+        out[2 * v + 1] = (t2 - t0) * 1000 / reps;  // issue + execute per MMA (x1000)
+      }
+    }
+    parity ^= 1;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tb, 512);
+}
+
+int32_t run_tc_mma_timing(Plan* p, long long* d_out, int reps)
+{
+  size_t smem = 65536 + 64;
+  FB_CUDA(p, cudaFuncSetAttribute(k_tc_mma_timing, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+  k_tc_mma_timing<<<1, 128, smem, p->stream>>>(d_out, reps);
+  FB_CUDA(p, cudaGetLastError());
+  return FB200_OK;
+}
+
 } // namespace fb200

@@ -151,6 +151,33 @@ __device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_
                "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
                : "memory");
 }
+// Same instructions with the 64-bit descriptors passed as (low, high) 32-bit halves and a compile-time accumulate flag:
+// the issuer then needs one integer add per MMA to step through shared memory.  These are WARP-LEVEL calls: all 32 lanes
+// must execute them converged, one elected lane issues.  (Issuing from inside an `if (lane == 0)` branch makes the
+// compiler wrap every uniform-datapath UTCHMMA in a vote/elect/branch loop: measured ~50 cycles per MMA.)
+template <int ACC>
+__device__ __forceinline__ void mma_ss_lohi(uint32_t d_tmem, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi, uint32_t idesc)
+{
+  asm volatile("{\n\t.reg .b64 da, db;\n\t.reg .pred p, pe;\n\telect.sync _|pe, 0xffffffff;\n\tmov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+               "setp.ne.b32 p, %6, 0;\n\t@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
+               "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "n"(ACC)
+               : "memory");
+}
+template <int ACC>
+__device__ __forceinline__ void mma_ts_lohi(uint32_t d_tmem, uint32_t a_tmem, uint32_t blo, uint32_t bhi, uint32_t idesc)
+{
+  asm volatile("{\n\t.reg .b64 db;\n\t.reg .pred p, pe;\n\telect.sync _|pe, 0xffffffff;\n\tmov.b64 db, {%2, %3};\n\tsetp.ne.b32 p, %5, 0;\n\t"
+               "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t}" ::"r"(d_tmem),
+               "r"(a_tmem), "r"(blo), "r"(bhi), "r"(idesc), "n"(ACC)
+               : "memory");
+}
+// warp-level commit: one elected lane arrives on `bar` when all MMAs issued so far by this warp have completed
+__device__ __forceinline__ void mma_commit_warp(uint64_t* bar)
+{
+  asm volatile("{\n\t.reg .pred pe;\n\telect.sync _|pe, 0xffffffff;\n\t"
+               "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar))
+               : "memory");
+}
 // all previously issued MMAs of this thread arrive on `bar` when complete (implies fence::before_thread_sync)
 __device__ __forceinline__ void mma_commit(uint64_t* bar)
 {
