@@ -227,46 +227,18 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
       const uint32_t wlo_a = (wop_a >> 4) | LO_A, hlo_a = (hop_a >> 4) | LO_A; // first MMA, part 0, block row 0
       const uint32_t wlo_b = (wop_a >> 4) | LO_B, hlo_b = (hop_a >> 4) | LO_B; // second MMA B operand
       uint32_t n = 0, buf_cnt = 0, prep_cnt = 0, w_cnt = 0;
-      // Second-stage MMAs are issued two steps late: A(n) [needs P buffer g free: p_free(n-2), signalled as soon as the
-      // epilogue has pulled P(n-2) into registers], then B(n-2) [needs R(n-2): r_full].  So the first MMA of step n
-      // runs while step n-2's ratio is still being computed, and each warpgroup finds its next P tile ready.
-      struct Pend { uint32_t blo, id48, id16, g, k; };
-      Pend f0{}, f1{}; // oldest, newest (explicit slots: an indexed array would live in local memory)
-      int npend = 0;
-      auto issue_b_one = [&]() {
-        const Pend pd = f0;
-        f0 = f1;
-        npend--;
-        DBG_MARK(3, 2 * pd.k + pd.g);
-        mbar_wait(&r_full[pd.g], pd.k & 1);
-        tc_fence_after();
-        DBG_MARK(4, 2 * pd.k + pd.g);
-        const uint32_t rbase = tbase + TM_R + RCOLS * pd.g;
-        const uint32_t dacc = tbase + TM_ACC + ACOLS * pd.g;
-#pragma unroll
-        for (int j = 0; j < 4; j++) { // K-step j = 16 bins (phase 1) / 16 frames (phase 2) = block rows blk + 2j, +1
-          // The tensor core adds into the fp32 accumulator with truncation, so every accumulate costs up to one ulp of
-          // the accumulator, always in the same direction.  Columns [0,16) therefore receive ONLY the leading term
-          // R_hi X_hi (one add per K-step); all correction terms go to the small-magnitude columns [16,32).
-          const uint32_t b0 = pd.blo + 2 * j * RSTEP; // parts hi, mid, lo side by side along N
-          const uint32_t rh = rbase + 8 * j;
-          if (j == 0) mma_ts_lohi<0>(dacc, rh, b0, HI_B, pd.id48);               // R_hi [X_hi | X_mid | X_lo] -> cols [0,48)
-          else mma_ts_lohi<1>(dacc, rh, b0, HI_B, pd.id48);
-          mma_ts_lohi<1>(dacc + 16, rh + 32, b0, HI_B, pd.id16);                 // R_lo  X_hi              -> cols [16,32)
-          if (RP == 3) mma_ts_lohi<1>(dacc + 16, rh + 64, b0, HI_B, pd.id16);
-        }
-        mma_commit_warp(&b_full[pd.g]); // the epilogue adds this partial to its fp32 running sums
-        DBG_MARK(5, 2 * pd.k + pd.g);
-      };
-      auto flush_b = [&]() { while (npend) issue_b_one(); };
-      // first-stage MMA: six significant terms of (A_hi + A_mid + A_lo)(B_hi + B_mid + B_lo); then queue the second stage
-      auto issue_step = [&](uint32_t alo, uint32_t blo, uint32_t idesc, uint32_t b2lo, uint32_t id48, uint32_t id16) {
+      // Two issuing warps with one in-order event stream each: this warp issues the first MMA of every step ("A(n)"), as
+      // soon as its P buffer is free [p_free(n-2): the epilogue signals it early in its step, once P(n-2) sits in
+      // registers]; warp 2 issues the second MMAs ("B(n)") as soon as the ratio is in TMEM [r_full(n), end of the step].
+      // Neither stream ever queues behind the other's barrier, so each warpgroup finds its next P tile ready.
+      auto issue_a = [&](uint32_t alo, uint32_t blo, uint32_t idesc) {
         const uint32_t g = n & 1;
         DBG_MARK(0, n);
-        if (n >= 2) mbar_wait(&p_free[g], ((n - 2) >> 1) & 1); // P(n-2) is in the epilogue's registers
+        if (n >= 2) mbar_wait(&p_free[g], ((n - 2) >> 1) & 1);
         tc_fence_after();
         DBG_MARK(1, n);
         const uint32_t dP = tbase + TM_P + 64 * g;
+        // six significant terms of (A_hi + A_mid + A_lo)(B_hi + B_mid + B_lo)
         mma_ss_lohi<0>(dP, alo, HI_A, blo, HI_A, idesc);                          // hi  hi
         mma_ss_lohi<1>(dP, alo, HI_A, blo + PSTEP, HI_A, idesc);                  // hi  mid
         mma_ss_lohi<1>(dP, alo + PSTEP, HI_A, blo, HI_A, idesc);                  // mid hi
@@ -275,10 +247,6 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
         mma_ss_lohi<1>(dP, alo + PSTEP, HI_A, blo + PSTEP, HI_A, idesc);          // mid mid
         mma_commit_warp(&p_full[g]);
         DBG_MARK(2, n);
-        if (npend == 2) issue_b_one();
-        Pend nw; nw.blo = b2lo; nw.id48 = id48; nw.id16 = id16; nw.g = g; nw.k = n >> 1;
-        if (npend == 0) f0 = nw; else f1 = nw;
-        npend++;
         n++;
       };
       for (int buf = blockIdx.x; buf < d.batch; buf += gridDim.x) {
@@ -287,28 +255,67 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
         for (int pass = 0; pass < sc.npass; pass++) {
           const bool p1 = sc.p1(pass), p2 = sc.p2(pass);
           for (int t = 0; t < T; t++) {
-            if (p1) {
-              for (int c = 0; c < C1; c++) // A = H rows of tile t, B = W rows of chunk c; second stage: B = W rows of chunk c
-                issue_step(hlo_a + 16 * t * RSTEP, wlo_a + 8 * c * RSTEP, ID_P1A, wlo_b + 8 * c * RSTEP, ID_P1B48, ID_P1B16);
-              flush_b(); // the tile's H numerator must be complete before the tile prep
-            }
+            if (p1)
+              for (int c = 0; c < C1; c++) issue_a(hlo_a + 16 * t * RSTEP, wlo_a + 8 * c * RSTEP, ID_P1A); // A = H rows of tile t, B = W rows of chunk c
             mbar_wait(prep_ready, prep_cnt & 1); prep_cnt++; // tile prep done: H_op(t) updated
             tc_fence_after();
-            if (p2) {
+            if (p2)
               for (int m = 0; m < MT; m++)
-                for (int s = 0; s < 2; s++) // A = W rows of tile m, B = H rows of half s; second stage: B = H rows of half s
-                  issue_step(wlo_a + 16 * m * RSTEP, hlo_a + (16 * t + 8 * s) * RSTEP, ID_P2A, hlo_b + (16 * t + 8 * s) * RSTEP, ID_P2B48,
-                             ID_P2B16);
-              if (!p1 || t == T - 1) flush_b();
-            }
+                for (int s = 0; s < 2; s++) issue_a(wlo_a + 16 * m * RSTEP, hlo_a + (16 * t + 8 * s) * RSTEP, ID_P2A); // A = W rows of tile m, B = H rows of half s
           }
           if (p2) {
-            flush_b();
             mbar_wait(w_ready, w_cnt & 1); w_cnt++; // W-update done: W_op rewritten
             tc_fence_after();
           }
         }
       }
+    }
+  } else if (warp == 2) {
+    // =========================================== MMA issuer, second stage ===============================
+    {
+      const uint32_t wop_a = smem_u32(wop), hop_a = smem_u32(hop);
+      constexpr uint32_t ID_P1B48 = make_idesc_bf16(128, 48, 0, 0), ID_P1B16 = make_idesc_bf16(128, 16, 0, 0);
+      constexpr uint32_t ID_P2B48 = make_idesc_bf16(128, 48, 0, 1), ID_P2B16 = make_idesc_bf16(128, 16, 0, 1);
+      constexpr uint32_t HI_B = (128u >> 4) | (1u << 14);  // B operand: SBO = 128 (parts / component blocks along N)
+      constexpr uint32_t LO_B = (ROWB >> 4) << 16;         // LBO = ROWB (block rows along K)
+      constexpr uint32_t RSTEP = ROWB >> 4;
+      const uint32_t wlo_b = (wop_a >> 4) | LO_B, hlo_b = (hop_a >> 4) | LO_B;
+      uint32_t n = 0;
+      // The operands read here are rewritten only after the epilogue has collected every partial (b_full) of the phase
+      // that used them, so this stream needs no barrier besides r_full.
+      auto issue_b = [&](uint32_t blo, uint32_t id48, uint32_t id16) {
+        const uint32_t g = n & 1;
+        mbar_wait(&r_full[g], (n >> 1) & 1);
+        tc_fence_after();
+        DBG_MARK(4, n);
+        const uint32_t rbase = tbase + TM_R + RCOLS * g;
+        const uint32_t dacc = tbase + TM_ACC + ACOLS * g;
+#pragma unroll
+        for (int j = 0; j < 4; j++) { // K-step j = 16 bins (phase 1) / 16 frames (phase 2) = block rows 2j, 2j+1 of the step
+          // The tensor core adds into the fp32 accumulator with truncation, so every accumulate costs up to one ulp of
+          // the accumulator, always in the same direction.  Columns [0,16) therefore receive ONLY the leading term
+          // R_hi X_hi (one add per K-step); all correction terms go to the small-magnitude columns [16,48).
+          const uint32_t b0 = blo + 2 * j * RSTEP; // parts hi, mid, lo side by side along N
+          const uint32_t rh = rbase + 8 * j;
+          if (j == 0) mma_ts_lohi<0>(dacc, rh, b0, HI_B, id48);                  // R_hi [X_hi | X_mid | X_lo] -> cols [0,48)
+          else mma_ts_lohi<1>(dacc, rh, b0, HI_B, id48);
+          mma_ts_lohi<1>(dacc + 16, rh + 32, b0, HI_B, id16);                    // R_lo  X_hi              -> cols [16,32)
+        }
+        mma_commit_warp(&b_full[g]); // the epilogue adds this partial to its fp32 running sums
+        DBG_MARK(5, n);
+        n++;
+      };
+      for (int buf = blockIdx.x; buf < d.batch; buf += gridDim.x)
+        for (int pass = 0; pass < sc.npass; pass++) {
+          const bool p1 = sc.p1(pass), p2 = sc.p2(pass);
+          for (int t = 0; t < T; t++) {
+            if (p1)
+              for (int c = 0; c < C1; c++) issue_b(wlo_b + 8 * c * RSTEP, ID_P1B48, ID_P1B16);           // B = W rows of chunk c
+            if (p2)
+              for (int m = 0; m < MT; m++)
+                for (int s = 0; s < 2; s++) issue_b(hlo_b + (16 * t + 8 * s) * RSTEP, ID_P2B48, ID_P2B16); // B = H rows of half s
+          }
+        }
     }
   }
   } else {
@@ -365,36 +372,65 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
 #pragma unroll
     for (int x = 0; x < 8; x++) voff[x] = (uint32_t) ((((lane >> 2) ^ x) << 4) + ((lane & 3) << 2));
 
-    // ratio of 32 consecutive columns held in p[] against 32 values v[] -> 3-way split, stored to TMEM
-    auto ratio_store = [&](const uint32_t* p, const float (&v)[32], int h) {
-      uint32_t ph[16], pm[16], pl[16];
-      (void) pl;
+    // One step of either phase for this thread's row: 64 columns of P against 64 values of V -> split ratio in TMEM.
+    // All loads are issued up front and the only mid-step synchronisation (b_full of this warpgroup's previous step,
+    // whose second MMA still reads R[g]) is taken after the ratios already sit in registers.
+    auto do_step = [&](uint32_t nn, uint32_t st, bool ph1) {
+      {
+        bool okp = mbar_try_wait(&p_full[wg], (nn >> 1) & 1), okv = mbar_try_wait(&v_full[st], (nn / NS) & 1);
+        while (!okp) okp = mbar_try_wait(&p_full[wg], (nn >> 1) & 1);
+        while (!okv) okv = mbar_try_wait(&v_full[st], (nn / NS) & 1);
+      }
+      tc_fence_after();
+      if (q == 0) DBG_MARK(8, nn);
+      uint32_t p[64];
+      tmem_ld32(tP, *reinterpret_cast<uint32_t(*)[32]>(&p[0]));
+      tmem_ld32(tP + 32, *reinterpret_cast<uint32_t(*)[32]>(&p[32]));
+      float v[64];
+      if (ph1) { // two boxes [128 frames][32 bins]: this thread's row, 16-byte chunks un-swizzled
+        const uint8_t* row = smem + OFF_V + st * STAGE + r * 128;
 #pragma unroll
-      for (int j = 0; j < 16; j++) {
+        for (int h = 0; h < 2; h++)
+#pragma unroll
+          for (int c4 = 0; c4 < 8; c4++) {
+            const float4 x = *reinterpret_cast<const float4*>(row + h * 16384 + ((c4 ^ (r & 7)) << 4));
+            v[32 * h + 4 * c4] = x.x; v[32 * h + 4 * c4 + 1] = x.y; v[32 * h + 4 * c4 + 2] = x.z; v[32 * h + 4 * c4 + 3] = x.w;
+          }
+      } else { // box q [64 frames][32 bins]: this thread's bin = lane, one value per frame
+        const uint8_t* vt = smem + OFF_V + st * STAGE + q * 8192;
+#pragma unroll
+        for (int j = 0; j < 64; j++) v[j] = *reinterpret_cast<const float*>(vt + j * 128 + voff[j & 7]);
+      }
+      tmem_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(&p_free[wg]); mbar_arrive(&v_empty[st]); } // P buffer and V stage are in registers now
+      uint32_t ph[32], pl[32];
+#pragma unroll
+      for (int j = 0; j < 32; j++) {
 #ifdef FB200_TC_EXPERIMENT_NOMATH
-        ph[j] = p[2 * j] ^ __float_as_uint(v[2 * j]); pm[j] = p[2 * j + 1] ^ __float_as_uint(v[2 * j + 1]);
+        ph[j] = p[2 * j] ^ __float_as_uint(v[2 * j]); pl[j] = p[2 * j + 1] ^ __float_as_uint(v[2 * j + 1]);
         continue;
 #endif
-        float r0 = v[2 * j] * rcp_fast(fmaxf(__uint_as_float(p[2 * j]), kEps));
-        float r1 = v[2 * j + 1] * rcp_fast(fmaxf(__uint_as_float(p[2 * j + 1]), kEps));
-        if (RP == 3) {
-          split3(r0, r1, ph[j], pm[j], pl[j]);
-        } else {
-          ph[j] = cvt2(r0, r1);
-          pm[j] = cvt2(r0 - bf16lo_to_f(ph[j]), r1 - bf16hi_to_f(ph[j]));
-        }
+        const float r0 = v[2 * j] * rcp_fast(fmaxf(__uint_as_float(p[2 * j]), kEps));
+        const float r1 = v[2 * j + 1] * rcp_fast(fmaxf(__uint_as_float(p[2 * j + 1]), kEps));
+        ph[j] = cvt2(r0, r1);
+        pl[j] = cvt2(r0 - bf16lo_to_f(ph[j]), r1 - bf16hi_to_f(ph[j]));
       }
-      // R[g] is still being read by the second MMA of this warpgroup's previous step until b_full: only now, with the
-      // new ratios already sitting in registers, wait for it (and collect that step's partial sums)
-      if (h == 0) {
-        if (q == 0) DBG_MARK(9, n);
-        drain();
-        if (q == 0) DBG_MARK(10, n);
-      }
-      tmem_st16(tR + 16 * h, ph);
-      tmem_st16(tR + 32 + 16 * h, pm);
-      if (RP == 3) tmem_st16(tR + 64 + 16 * h, pl);
+      if (q == 0) DBG_MARK(9, nn);
+      drain();
+      if (q == 0) DBG_MARK(10, nn);
+      tmem_st16(tR, *reinterpret_cast<uint32_t(*)[16]>(&ph[0]));
+      tmem_st16(tR + 16, *reinterpret_cast<uint32_t(*)[16]>(&ph[16]));
+      tmem_st16(tR + 32, *reinterpret_cast<uint32_t(*)[16]>(&pl[0]));
+      tmem_st16(tR + 48, *reinterpret_cast<uint32_t(*)[16]>(&pl[16]));
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&r_full[wg]);
+      if (q == 0) DBG_MARK(11, nn);
     };
+    static_assert(RP == 2, "the step epilogue writes a two-part ratio");
 
     for (int buf = blockIdx.x; buf < d.batch; buf += gridDim.x) {
       // ---------------- buffer prologue: state -> 3-way split operands --------------------------------------------
@@ -439,41 +475,8 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
           if (p1) {
             for (int c = 0; c < C1; c++, n++) {
               if ((int) (n & 1) != wg) continue;
-              const uint32_t st = n % NS;
               if (q == 0) DBG_MARK(6, n);
-              mbar_wait(&p_full[wg], (n >> 1) & 1);
-              if (q == 0) DBG_MARK(7, n);
-              mbar_wait(&v_full[st], (n / NS) & 1);
-              tc_fence_after();
-              if (q == 0) DBG_MARK(8, n);
-              const uint8_t* vt = smem + OFF_V + st * STAGE;
-              uint32_t p[64];
-              tmem_ld32(tP, *reinterpret_cast<uint32_t(*)[32]>(&p[0]));
-              tmem_ld32(tP + 32, *reinterpret_cast<uint32_t(*)[32]>(&p[32]));
-              tmem_wait_ld();
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(&p_free[wg]); // the issuer may overwrite this P buffer with step n+2 now
-#pragma unroll
-              for (int h = 0; h < 2; h++) {
-                float v[32];
-                const uint8_t* row = vt + h * 16384 + r * 128;
-#pragma unroll
-                for (int c4 = 0; c4 < 8; c4++) {
-                  float4 x = *reinterpret_cast<const float4*>(row + ((c4 ^ (r & 7)) << 4));
-                  v[4 * c4] = x.x; v[4 * c4 + 1] = x.y; v[4 * c4 + 2] = x.z; v[4 * c4 + 3] = x.w;
-                }
-                if (h == 1) { // last read of this V stage is issued: hand it back to the producer half a step early
-                  __syncwarp();
-                  if (lane == 0) mbar_arrive(&v_empty[st]);
-                }
-                ratio_store(&p[32 * h], v, h);
-              }
-              tmem_wait_st();
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(&r_full[wg]);
-              if (q == 0) DBG_MARK(11, n);
+              do_step(n, n % NS, true);
               out_valid = 1; out_phase = 1; out_par = (n >> 1) & 1;
             }
             drain(); // H numerator of this warpgroup's chunks complete (all MMAs reading H_op(t) have retired)
@@ -570,34 +573,7 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
             for (int m = 0; m < MT; m++)
               for (int s = 0; s < 2; s++, n++) {
                 if ((int) (n & 1) != wg) continue;
-                const uint32_t st = n % NS;
-                mbar_wait(&p_full[wg], (n >> 1) & 1);
-                mbar_wait(&v_full[st], (n / NS) & 1);
-                tc_fence_after();
-                const uint8_t* vt = smem + OFF_V + st * STAGE + q * 8192; // box q: bins 128m + 32q .. +31, rows = 64 frames
-                uint32_t p[64];
-                tmem_ld32(tP, *reinterpret_cast<uint32_t(*)[32]>(&p[0]));
-                tmem_ld32(tP + 32, *reinterpret_cast<uint32_t(*)[32]>(&p[32]));
-                tmem_wait_ld();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&p_free[wg]);
-#pragma unroll
-                for (int h = 0; h < 2; h++) {
-                  float v[32];
-                  const uint8_t* vh = vt + h * 32 * 128;
-#pragma unroll
-                  for (int j = 0; j < 32; j++) v[j] = *reinterpret_cast<const float*>(vh + j * 128 + voff[j & 7]);
-                  if (h == 1) {
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&v_empty[st]);
-                  }
-                  ratio_store(&p[32 * h], v, h);
-                }
-                tmem_wait_st();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&r_full[wg]);
+                do_step(n, n % NS, false);
                 out_valid = 1; out_phase = 2; out_m = m; out_first = (t == 0); out_par = (n >> 1) & 1;
               }
           }
