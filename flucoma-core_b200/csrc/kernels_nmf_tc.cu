@@ -110,6 +110,42 @@ __device__ __forceinline__ void split3(float x0, float x1, uint32_t& h, uint32_t
 }
 __device__ __forceinline__ float bf16_bits_to_f(unsigned short u) { return __uint_as_float((uint32_t) u << 16); }
 
+// Block schedule of one pass, shared by every warp role.
+enum BlockKind { BLK_P1 = 0, BLK_PREP = 1, BLK_P2 = 2, BLK_W = 3 };
+__device__ __forceinline__ int block_count(bool p1, bool p2, int T) { return (p1 && p2) ? 3 * T + 1 : (p1 ? 2 * T : 2 * T + 1); }
+__device__ __forceinline__ void block_at(bool p1, bool p2, int T, int i, int& kind, int& t)
+{
+  if (p1 && p2) { // [P1(t) PREP(t) P2(t)] W
+    // (Running phase 1 of tile t+1 ahead of phase 2 of tile t would take the prep's barrier round trip off the critical
+    // path, but measured 9 % slower: phase 2 then re-reads a V tile that is 512 KB "old" per CTA instead of 256 KB, and
+    // with 148 CTAs streaming that falls out of L2.)
+    if (i == 3 * T) { kind = BLK_W; t = 0; }
+    else { const int rr = i % 3; t = i / 3; kind = rr == 0 ? BLK_P1 : (rr == 1 ? BLK_PREP : BLK_P2); }
+  } else if (p1) { // [P1(t) PREP(t)]
+    kind = (i & 1) ? BLK_PREP : BLK_P1;
+    t = i >> 1;
+  } else { // [PREP(t) P2(t)] W
+    if (i == 2 * T) { kind = BLK_W; t = 0; }
+    else { kind = (i & 1) ? BLK_P2 : BLK_PREP; t = i >> 1; }
+  }
+}
+// one call site for the body (a callback invoked from several places would be inlined several times)
+// `rev`: walk the tiles in descending order.  Passes alternate direction so that the V tiles touched last in one pass
+// are the first ones needed by the next pass: with 148 CTAs streaming 157 MB of V through a 126 MB L2 a fixed cyclic
+// order never hits, a boustrophedon order re-uses whatever the L2 still holds.  (Any tile order is a valid schedule:
+// tiles only meet in the fixed-order sums of the W-update.)
+template <class F>
+__device__ __forceinline__ void for_blocks(bool p1, bool p2, int T, bool rev, F&& f)
+{
+  const int nb = block_count(p1, p2, T);
+#pragma unroll 1
+  for (int i = 0; i < nb; i++) {
+    int kind, t;
+    block_at(p1, p2, T, i, kind, t);
+    f(kind, (rev && kind != BLK_W) ? T - 1 - t : t);
+  }
+}
+
 struct Sched {
   int npass, both, upd_w, upd_h, iters;
   __device__ bool p1(int pass) const { return both ? pass > 0 : upd_h != 0; }
@@ -181,9 +217,8 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
       uint32_t n = 0;
       for (int buf = blockIdx.x; buf < d.batch; buf += gridDim.x) {
         for (int pass = 0; pass < sc.npass; pass++) {
-          const bool p1 = sc.p1(pass), p2 = sc.p2(pass);
-          for (int t = 0; t < T; t++) {
-            if (p1)
+          for_blocks(sc.p1(pass), sc.p2(pass), T, (pass & 1) != 0, [&](int kind, int t) {
+            if (kind == BLK_P1)
               for (int c = 0; c < C1; c++, n++) {
                 const uint32_t st = n % NS, k = n / NS;
                 mbar_wait(&v_empty[st], (k & 1) ^ 1);
@@ -192,7 +227,7 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
                 tma_load_3d(dst, &tmap1, 64 * c, 128 * t, buf, &v_full[st]);
                 tma_load_3d(dst + 16384, &tmap1, 64 * c + 32, 128 * t, buf, &v_full[st]);
               }
-            if (p2)
+            else if (kind == BLK_P2)
               for (int m = 0; m < MT; m++)
                 for (int s = 0; s < 2; s++, n++) {
                   const uint32_t st = n % NS, k = n / NS;
@@ -202,7 +237,7 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
 #pragma unroll
                   for (int w = 0; w < 4; w++) tma_load_3d(dst + w * 8192, &tmap2, 128 * m + 32 * w, 128 * t + 64 * s, buf, &v_full[st]);
                 }
-          }
+          });
         }
       }
     }
@@ -254,19 +289,27 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
         tc_fence_after();
         for (int pass = 0; pass < sc.npass; pass++) {
           const bool p1 = sc.p1(pass), p2 = sc.p2(pass);
-          for (int t = 0; t < T; t++) {
-            if (p1)
+          int prep_owed = 0; // tile preps whose completion this warp has not consumed yet (each must be observed
+                             // before the next one can complete: see the placement of the waits below)
+          for_blocks(p1, p2, T, (pass & 1) != 0, [&](int kind, int t) {
+            if (kind == BLK_P1) {
               for (int c = 0; c < C1; c++) issue_a(hlo_a + 16 * t * RSTEP, wlo_a + 8 * c * RSTEP, ID_P1A); // A = H rows of tile t, B = W rows of chunk c
-            mbar_wait(prep_ready, prep_cnt & 1); prep_cnt++; // tile prep done: H_op(t) updated
-            tc_fence_after();
-            if (p2)
+              if (!p2 && prep_owed) { mbar_wait(prep_ready, prep_cnt & 1); prep_cnt++; prep_owed--; }       // prep(t-1), long done
+            } else if (kind == BLK_PREP) {
+              prep_owed++;
+              if (!p1) { mbar_wait(prep_ready, prep_cnt & 1); prep_cnt++; prep_owed--; tc_fence_after(); }  // phase 2 follows directly
+            } else if (kind == BLK_P2) {
+              if (prep_owed) { mbar_wait(prep_ready, prep_cnt & 1); prep_cnt++; prep_owed--; }              // H_op(t) updated
+              tc_fence_after();
               for (int m = 0; m < MT; m++)
                 for (int s = 0; s < 2; s++) issue_a(wlo_a + 16 * m * RSTEP, hlo_a + (16 * t + 8 * s) * RSTEP, ID_P2A); // A = W rows of tile m, B = H rows of half s
-          }
-          if (p2) {
-            mbar_wait(w_ready, w_cnt & 1); w_cnt++; // W-update done: W_op rewritten
-            tc_fence_after();
-          }
+            } else {
+              mbar_wait(w_ready, w_cnt & 1); w_cnt++; // W-update done: W_op rewritten
+              tc_fence_after();
+            }
+          });
+          while (prep_owed) { mbar_wait(prep_ready, prep_cnt & 1); prep_cnt++; prep_owed--; }
+          tc_fence_after();
         }
       }
     }
@@ -306,16 +349,14 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
         n++;
       };
       for (int buf = blockIdx.x; buf < d.batch; buf += gridDim.x)
-        for (int pass = 0; pass < sc.npass; pass++) {
-          const bool p1 = sc.p1(pass), p2 = sc.p2(pass);
-          for (int t = 0; t < T; t++) {
-            if (p1)
+        for (int pass = 0; pass < sc.npass; pass++)
+          for_blocks(sc.p1(pass), sc.p2(pass), T, (pass & 1) != 0, [&](int kind, int t) {
+            if (kind == BLK_P1)
               for (int c = 0; c < C1; c++) issue_b(wlo_b + 8 * c * RSTEP, ID_P1B48, ID_P1B16);           // B = W rows of chunk c
-            if (p2)
+            else if (kind == BLK_P2)
               for (int m = 0; m < MT; m++)
                 for (int s = 0; s < 2; s++) issue_b(hlo_b + (16 * t + 8 * s) * RSTEP, ID_P2B48, ID_P2B16); // B = H rows of half s
-          }
-        }
+          });
     }
   }
   } else {
@@ -470,9 +511,9 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
 
       for (int pass = 0; pass < sc.npass; pass++) {
         const bool p1 = sc.p1(pass), p2 = sc.p2(pass);
-        for (int t = 0; t < T; t++) {
+        for_blocks(p1, p2, T, (pass & 1) != 0, [&](int kind, int t) {
           // ---------------- phase 1 steps ------------------------------------------------------------------------
-          if (p1) {
+          if (kind == BLK_P1) {
             for (int c = 0; c < C1; c++, n++) {
               if ((int) (n & 1) != wg) continue;
               if (q == 0) DBG_MARK(6, n);
@@ -485,10 +526,10 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
               *reinterpret_cast<float4*>(hs + (wg * 128 + r) * 16 + 4 * j4) = make_float4(hsum[4 * j4], hsum[4 * j4 + 1], hsum[4 * j4 + 2], hsum[4 * j4 + 3]);
 #pragma unroll
             for (int k = 0; k < K; k++) hsum[k] = 0.f;
-            epi_bar();
           }
           // ---------------- tile prep: H-update (if p1), W-denominator / Nyquist partials (if p2) ----------------
-          {
+          else if (kind == BLK_PREP) {
+            epi_bar(); // both warpgroups' H-numerator partials of tile t are in `hs`
             const int f = 128 * t + r;
             const int k0 = 8 * wg; // this warpgroup splits / stores / reduces components [k0, k0 + 8) of every row
             float h[16];
@@ -567,19 +608,19 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(prep_ready);
+            epi_bar(); // `hs` may be overwritten by the next phase-1 block only after every warp has read it
           }
           // ---------------- phase 2 steps ------------------------------------------------------------------------
-          if (p2) {
+          else if (kind == BLK_P2) {
             for (int m = 0; m < MT; m++)
               for (int s = 0; s < 2; s++, n++) {
                 if ((int) (n & 1) != wg) continue;
                 do_step(n, n % NS, false);
-                out_valid = 1; out_phase = 2; out_m = m; out_first = (t == 0); out_par = (n >> 1) & 1;
+                out_valid = 1; out_phase = 2; out_m = m; out_first = (t == ((pass & 1) ? T - 1 : 0)); out_par = (n >> 1) & 1;
               }
           }
-        }
         // ---------------- W-update (NMF.hpp:161-162) + hden refresh (:169) --------------------------------------
-        if (p2) {
+          else {
           drain(); // last outstanding W-numerator partial of this warpgroup
           tc_fence_before();
           epi_bar(); // all partials of all tiles written, both warpgroups' running sums complete
@@ -679,7 +720,8 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
           tc_fence_before();
           epi_bar();
           if (lane == 0) mbar_arrive(w_ready);
-        }
+          }
+        });
       }
       // ---------------- buffer epilogue: state back to global ----------------------------------------------------
       epi_bar();
