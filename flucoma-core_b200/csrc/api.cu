@@ -69,7 +69,7 @@ struct StageTimer {
 // STFT of `batch` buffers already on the device (float [batch][n]) -> V (padded magnitudes, may be null) and/or
 // spec_all (float2 [batch][F][B], may be null).  STFT.hpp:90-108 + :61-66.
 int32_t run_stft(Plan* p, const float* d_audio, int64_t batch, int64_t n, int64_t F, float* V, int64_t Fp, int64_t Bp,
-                 float2* spec_all, int half)
+                 float2* spec_all, int64_t half)
 {
   const int B = p->bins;
   int64_t wave = wave_size(p, F, batch, 1);
@@ -92,9 +92,12 @@ int32_t run_stft(Plan* p, const float* d_audio, int64_t batch, int64_t n, int64_
   return FB200_OK;
 }
 
-// ISTFT of nsig spectra (float2 [nsig][F][B], destroyed) -> out float [nsig][n].  STFT.hpp:178-199
-int32_t run_istft(Plan* p, float2* spec, int64_t nsig, int64_t F, int64_t n, float* out, int half)
+// ISTFT of nsig spectra (float2 [nsig][F][B], destroyed) -> out float [nsig][out_stride], n samples each.
+// STFT.hpp:178-199; stream_norm: the streaming clients' normalisation (BufferedProcess.hpp:231-237).
+int32_t run_istft(Plan* p, float2* spec, int64_t nsig, int64_t F, int64_t n, float* out, int64_t half,
+                  int64_t out_stride = -1, int stream_norm = 0)
 {
+  if (out_stride < 0) out_stride = n;
   int64_t wave = wave_size(p, F, nsig, 1);
   FB_CUDA(p, p->frames.ensure(sizeof(float) * (size_t) (wave * F * p->fft)));
   for (int64_t s0 = 0; s0 < nsig; s0 += wave) {
@@ -103,7 +106,7 @@ int32_t run_istft(Plan* p, float2* spec, int64_t nsig, int64_t F, int64_t n, flo
     FB_TRY(get_fft_plan(p, CUFFT_C2R, ns * F, &h));
     FB_CUFFT(p, cufftExecC2R(h, reinterpret_cast<cufftComplex*>(spec + s0 * F * p->bins), p->frames.as<float>()));
     p->launches++;
-    launch_ola(p, p->frames.as<float>(), ns, F, n, out + s0 * n, half);
+    launch_ola(p, p->frames.as<float>(), ns, F, n, out + s0 * out_stride, half, out_stride, stream_norm);
   }
   return FB200_OK;
 }
@@ -659,12 +662,80 @@ int32_t fb200_bufnmf(fb200_plan* p, const fb200_bufnmf_args* a)
   return FB200_OK;
 }
 
+// NMFFilter (and, with out == NULL, NMFMatch) over a mono stream that starts from reset state.
+// NMFFilterClient.hpp:98-117 / NMFMatchClient.hpp:106-118 under STFTBufferedProcess (BufferedProcess.hpp:49-93,187-241):
+// frame f (f*hop < n) sees stream[f*hop - win, f*hop); its `rank` masked resyntheses are overlap-added at [f*hop, f*hop+win).
+// Frames are independent (fixed bases, identical h0), so the stream is cut into chunks of frames sized for the cuFFT
+// scratch; a chunk re-computes the (win-1)/hop frames before its first output sample instead of carrying OLA state.
 int32_t fb200_nmf_filter(fb200_plan* p, const fb200_filter_args* a)
 {
   if (!p) return FB200_ERR_INVALID;
-  (void) a;
-  p->err = "fb200_nmf_filter: not implemented yet";
-  return FB200_ERR_UNSUPPORTED;
+  if (!a || a->struct_size != sizeof(fb200_filter_args) || !a->audio || !a->bases || a->n_samples <= 0 || a->rank <= 0 ||
+      a->iterations < 0 || (!a->out && !a->acts_out)) {
+    p->err = "fb200_nmf_filter: bad arguments";
+    return FB200_ERR_INVALID;
+  }
+  FB_CUDA(p, cudaSetDevice(p->cfg.device));
+  StageTimer t(p);
+  t.mark(0);
+  const int64_t n = a->n_samples, K = a->rank, B = p->bins, hop = p->hop, win = p->win;
+  const int64_t frames_total = (n + hop - 1) / hop;                      // BufferedProcess.hpp:57
+  const int64_t ov = a->out ? (win - 1) / hop : 0;                       // earlier frames that still reach a sample
+  int64_t chunk = (((int64_t) 1 << 27) / std::max<int64_t>(1, K * p->fft)) / 128 * 128;
+  chunk = std::max<int64_t>(chunk, (ov / 128 + 1) * 128);
+  chunk = std::min<int64_t>(chunk, (frames_total + ov + 127) / 128 * 128);
+  const int64_t fresh = chunk - ov;                                      // new frames per chunk
+  const int host = a->mem == FB200_HOST;
+
+  const void* raw;
+  FB_TRY(to_device_raw(p, a->audio, a->mem, sizeof(float) * (size_t) n, p->audio, &raw));
+  const float* d_audio = (const float*) raw;
+  FB_TRY(to_device_raw(p, a->bases, a->mem, sizeof(float) * (size_t) (K * B), p->out_a, &raw));
+  const float* d_bases = (const float*) raw;
+  int64_t seed = a->seed;
+  FB_TRY(upload_seeds(p, &seed, 1));
+  FB_CUDA(p, p->rnd.ensure(sizeof(float) * (size_t) K));
+  launch_mt_uniform(p, p->seeds.as<int64_t>(), 1, K, p->rnd.as<float>()); // NMF.hpp:55, same h0 for every frame
+  FB_CUDA(p, p->spec.ensure(sizeof(float2) * (size_t) (chunk * B)));
+  if (a->out) FB_CUDA(p, p->cspec.ensure(sizeof(float2) * (size_t) (K * chunk * B)));
+  if (host && a->out) FB_CUDA(p, p->stage.ensure(sizeof(float) * (size_t) (K * fresh * hop)));
+  if (host && a->acts_out) FB_CUDA(p, p->out_b.ensure(sizeof(float) * (size_t) (fresh * K)));
+  t.mark(1);
+  for (int64_t f_new = 0; f_new < frames_total; f_new += fresh) {
+    const int64_t f_lo = std::max<int64_t>(0, f_new - ov);
+    const int64_t f_hi = std::min(frames_total, f_new + fresh);
+    NmfDev d{};
+    d.batch = 1; d.F = (int) (f_hi - f_lo); d.B = (int) B; d.K = (int) K; d.clamp_v = 1;
+    FB_TRY(alloc_nmf(p, d));
+    FB_CUDA(p, cudaMemsetAsync(d.V, 0, sizeof(float) * (size_t) d.Fp * d.Bp, p->stream));
+    FB_TRY(run_stft(p, d_audio, 1, n, d.F, d.V, d.Fp, d.Bp, p->spec.as<float2>(), win - f_lo * hop));
+    launch_nmf_init(p, d, p->rnd.as<float>(), K, d_bases, nullptr, 1);   // NMF.hpp:55-64
+    if (a->iterations > 0) simt_launch_tile(p, d, 1, 0, a->iterations);  // NMF.hpp:72-83
+    if (a->acts_out) {
+      const int64_t rows = f_hi - f_new;
+      const float* src = d.H + (f_new - f_lo) * d.KP;
+      float* dst = host ? p->out_b.as<float>() : a->acts_out + f_new * K;
+      launch_copy3d(p, src, FB200_F32, 0, d.KP, dst, FB200_F32, 0, K, 1, rows, K, nullptr, 0);
+      if (host)
+        FB_CUDA(p, cudaMemcpyAsync(a->acts_out + f_new * K, dst, sizeof(float) * (size_t) (rows * K), cudaMemcpyDeviceToHost,
+                                   p->stream));
+    }
+    if (a->out) {
+      const int64_t t_lo = f_new * hop, t_hi = std::min(n, f_hi * hop), len = t_hi - t_lo;
+      launch_mask(p, d, p->spec.as<float2>(), 0, 1, p->cspec.as<float2>()); // NMFFilterClient.hpp:104-113
+      float* dst = host ? p->stage.as<float>() : a->out + t_lo;
+      const int64_t stride = host ? len : n;
+      FB_TRY(run_istft(p, p->cspec.as<float2>(), K, d.F, len, dst, t_lo - f_lo * hop, stride, 1));
+      if (host)
+        FB_CUDA(p, cudaMemcpy2DAsync(a->out + t_lo, sizeof(float) * (size_t) n, dst, sizeof(float) * (size_t) len,
+                                     sizeof(float) * (size_t) len, (size_t) K, cudaMemcpyDeviceToHost, p->stream));
+    }
+    if (host) FB_CUDA(p, cudaStreamSynchronize(p->stream)); // staging buffers are reused by the next chunk
+  }
+  t.mark(2);
+  FB_TRY(finish(p, t, 2));
+  p->stats.ms_h2d = t.ms(0, 1); p->stats.ms_nmf = t.ms(1, 2);
+  return FB200_OK;
 }
 
 int32_t fb200_selftest_tcgen05(fb200_plan* p, const float* in, int64_t n_in, float* out, int64_t n_out)

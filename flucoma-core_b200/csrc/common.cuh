@@ -154,13 +154,14 @@ void launch_vhat(Plan* p, const NmfDev& d, void* dst, int dst_dtype);
 
 // kernels_stft.cu -----------------------------------------------------------------------------------------------
 void launch_hann(Plan* p);
-void launch_frame_window(Plan* p, const float* audio, int64_t n, int64_t nbuf, int64_t F, float* frames, int half);
+void launch_frame_window(Plan* p, const float* audio, int64_t n, int64_t nbuf, int64_t F, float* frames, int64_t half);
 // spec [nbuf*F][B] complex -> V[nbuf][Fp][Bp] magnitudes (+ zero imag of DC/Nyquist in place, FFT.hpp:99-101)
 void launch_magnitude(Plan* p, float2* spec, int64_t nbuf, int64_t F, float* V, int64_t Fp, int64_t Bp);
 // masked component spectra for buffers [b0, b0+nb): cspec[nb][K][F][B]  (NMF.hpp:33-42 + RatioMask.hpp:33-57)
 void launch_mask(Plan* p, const NmfDev& d, const float2* spec, int64_t b0, int64_t nb, float2* cspec);
 // overlap-add + normalise + trim (STFT.hpp:178-199): y [nsig][F][fft] -> out [nsig][n]
-void launch_ola(Plan* p, const float* y, int64_t nsig, int64_t F, int64_t n, float* out, int half);
+void launch_ola(Plan* p, const float* y, int64_t nsig, int64_t F, int64_t n, float* out, int64_t half, int64_t out_stride,
+                int stream_norm);
 
 // kernels_tc_selftest.cu ---------------------------------------------------------------------------------------
 int32_t make_v_tensor_map(Plan* p, void* tmap_out, const float* V, int64_t Bp, int64_t Fp, int64_t batch, int box_rows);

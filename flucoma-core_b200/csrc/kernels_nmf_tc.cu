@@ -19,7 +19,7 @@
 //   after the last tile: W <- W * wnum / max(wden, eps), conditional column normalisation (:161-162), hden = sum_b W.
 //
 // Precision: a product of two 3-way splits keeps the six terms above 2^-24 (hh, hm, mh, hl, lh, mm), i.e. fp32-grade
-// operands with fp32 accumulation.  (A 2-way split, 16-17 mantissa bits, measured 1.3e-4 against the fp64 oracle after
+// operands with fp32 accumulation.  (A 2-way split, 16-17 mantissa bits, measured 1.3e-4 against the fp64 CPU restatement after
 // 200 iterations -- the NMF dynamics amplify the per-iteration error about 100x -- and missed the 1e-4 bar.)
 // For the second MMA the three parts of the B operand sit next to each other in shared memory, so one instruction
 // with N = 32 multiplies a ratio part by [X_hi | X_mid] at once; the accumulator is 32 columns wide and its two halves

@@ -22,7 +22,7 @@ void launch_hann(Plan* p)
 // `half` is the left padding: win/2 for STFT::process, win for the streaming clients (BufferedProcess.hpp:75-93).
 __global__ void __launch_bounds__(256) k_frame_window(const float* __restrict__ audio, int64_t n, int64_t nbuf, int64_t F,
                                                       const float* __restrict__ window, int win, int fft, int hop,
-                                                      int half, float* __restrict__ frames)
+                                                      int64_t half, float* __restrict__ frames)
 {
   int64_t total = nbuf * F * (int64_t) (fft / 4);
   for (int64_t e = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; e < total; e += (int64_t) gridDim.x * blockDim.x) {
@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(256) k_frame_window(const float* __restrict__ 
   }
 }
 
-void launch_frame_window(Plan* p, const float* audio, int64_t n, int64_t nbuf, int64_t F, float* frames, int half)
+void launch_frame_window(Plan* p, const float* audio, int64_t n, int64_t nbuf, int64_t F, float* frames, int64_t half)
 {
   int64_t total = nbuf * F * (int64_t) (p->fft / 4);
   if (total <= 0) return;
@@ -130,9 +130,11 @@ void launch_mask(Plan* p, const NmfDev& d, const float2* spec, int64_t b0, int64
 
 // ISTFT::process (STFT.hpp:178-199) as a gather: sample t of signal s sums the <= ceil(win/hop) frames covering
 // padded position t+half, each * (1/fft) * window, then / max(sum window^2, eps).  y [nsig][F][fft] (cuFFT C2R output).
+// stream_norm selects the streaming clients' rule instead (BufferedProcess.hpp:231-237): x != 0 ? x / (g > 0 ? g : 1) : x.
+// Signal s writes out[s * out_stride + t], t in [0, n).
 __global__ void __launch_bounds__(256) k_ola(const float* __restrict__ y, int64_t nsig, int64_t F, int64_t n,
-                                             const float* __restrict__ window, int win, int fft, int hop, int half,
-                                             float* __restrict__ out)
+                                             const float* __restrict__ window, int win, int fft, int hop, int64_t half,
+                                             float* __restrict__ out, int64_t out_stride, int stream_norm)
 {
   int64_t total = nsig * n;
   const float scale = 1.0f / (float) fft;
@@ -150,16 +152,19 @@ __global__ void __launch_bounds__(256) k_ola(const float* __restrict__ y, int64_
       acc = fmaf(ys[i * fft + j] * scale, w, acc);
       nrm = fmaf(w, w, nrm);
     }
-    out[e] = acc / fmaxf(nrm, kEps);
+    float r = stream_norm ? (acc != 0.f ? acc / (nrm > 0.f ? nrm : 1.f) : acc) : acc / fmaxf(nrm, kEps);
+    out[s * out_stride + t] = r;
   }
 }
 
-void launch_ola(Plan* p, const float* y, int64_t nsig, int64_t F, int64_t n, float* out, int half)
+void launch_ola(Plan* p, const float* y, int64_t nsig, int64_t F, int64_t n, float* out, int64_t half, int64_t out_stride,
+                int stream_norm)
 {
   int64_t total = nsig * n;
   if (total <= 0) return;
   int grid = (int) std::min<int64_t>((total + 255) / 256, (int64_t) p->sm_count * 32);
-  k_ola<<<grid, 256, 0, p->stream>>>(y, nsig, F, n, p->window.as<float>(), p->win, p->fft, p->hop, half, out);
+  k_ola<<<grid, 256, 0, p->stream>>>(y, nsig, F, n, p->window.as<float>(), p->win, p->fft, p->hop, half, out,
+                                           out_stride, stream_norm);
   p->launches++;
 }
 

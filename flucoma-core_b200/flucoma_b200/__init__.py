@@ -357,3 +357,22 @@ class Plan:
         st = self._L.fb200_bufnmf(self._h, C.byref(a))
         self._check(st)
         return dict(bases=None if fix_w else bases, acts=None if fix_h else acts, resynth=rs, status=st)
+
+    # -- streaming NMFFilter / NMFMatch ------------------------------------------------------------------------------
+    def nmf_filter(self, audio, bases, iterations=10, seed=-1, want_out=True, want_acts=True):
+        """Mono stream float32 [n] + bases float32 [K][bins] -> (out [K][n] | None, acts [ceil(n/hop)][K] | None).
+
+        NMFFilterClient.hpp:98-117 (and NMFMatchClient.hpp:106-118 when want_out is False) from reset state; `out`
+        carries the client's latency of `win` samples."""
+        a_in = self._contig(audio); W = self._contig(bases)
+        assert a_in.ndim == 1 and _dtype_code(a_in) == F32 and _dtype_code(W) == F32
+        n = a_in.shape[0]
+        K = W.shape[0]
+        assert W.shape[1] == self.bins
+        frames = (n + self.hop - 1) // self.hop
+        out = self._empty_like_space(a_in, (K, n), "float32") if want_out else None
+        acts = self._empty_like_space(a_in, (frames, K), "float32") if want_acts else None
+        a = FilterArgs(C.sizeof(FilterArgs), DEVICE if _is_torch(a_in) else HOST, n, K, iterations, seed, _ptr(a_in),
+                       _ptr(W), _ptr(out), _ptr(acts))
+        self._check(self._L.fb200_nmf_filter(self._h, C.byref(a)))
+        return out, acts

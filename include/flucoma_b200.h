@@ -159,8 +159,11 @@ typedef struct fb200_bufnmf_args {
 FB200_API int32_t fb200_bufnmf(fb200_plan* plan, const fb200_bufnmf_args* args);
 
 /* ---- NMFFilter over a stream  (clients/rt/NMFFilterClient.hpp:98-117 + BufferedProcess.hpp:187-241) ---------- */
-/* audio [n_samples] mono stream -> out [rank][n_samples], the `rank` masked resyntheses, as the streaming client
- * produces them but without its `win` samples of latency (frame f covers [f*hop-win, f*hop)). */
+/* audio [n_samples]: a mono stream from reset state.  Frame f (f*hop < n_samples) covers stream[f*hop - win, f*hop)
+ * (FluidSource.hpp:68-89); out [rank][n_samples] are the `rank` masked resyntheses exactly as the streaming client emits
+ * them, i.e. delayed by its latency of `win` samples (NMFFilterClient.hpp:64) -- append `win` zeros to flush the tail.
+ * out == NULL with acts_out != NULL is NMFMatch on the same stream (clients/rt/NMFMatchClient.hpp:106-118, which
+ * hard-codes 10 iterations).  Independent of the host vector size the client would have been driven with. */
 typedef struct fb200_filter_args {
   uint32_t struct_size;
   int32_t mem;

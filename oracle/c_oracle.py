@@ -71,6 +71,7 @@ def lib(path: str | None = None):
                                   C.c_int]
     L.fo_nmfmatch_frames.argtypes = [_pd, _i64, _pd, _i64, _i64, _i64, _i64, _pd, C.c_int]
     L.fo_stream_frames_mag.argtypes = [_pd, _i64, _i64, _i64, _i64, _i64, _pd, _pd]
+    L.fo_nmffilter_stream.argtypes = [_pd, _i64, _i64, _i64, _i64, _pd, _i64, _i64, _i64, _pd, _pd]
     L.fo_num_threads.restype = C.c_int
     if path is None:
         _LIB = L
@@ -251,6 +252,19 @@ def stream_frames_mag(audio, win, fft, hop, nframes, want_spec=False):
     lib().fo_stream_frames_mag(_d(a), a.size, win, fft, hop, nframes, _d(mags),
                                _d(spec.view(np.float64)) if want_spec else None)
     return (mags, spec) if want_spec else mags
+
+
+def nmffilter_stream(audio, win, fft, hop, W, n_iter, seed, want_out=True):
+    """NMFFilter over a stream from reset state: (out[K][n] or None, acts[ceil(n/hop)][K])."""
+    a = _c64(audio); W = _c64(W)
+    K, B = W.shape
+    assert B == fft // 2 + 1
+    nframes = (a.size + hop - 1) // hop
+    out = np.empty((K, a.size)) if want_out else None
+    acts = np.empty((nframes, K))
+    lib().fo_nmffilter_stream(_d(a), a.size, win, fft, hop, _d(W), K, n_iter, seed, _d(out) if want_out else None,
+                              _d(acts))
+    return out, acts
 
 
 def num_threads():

@@ -677,6 +677,68 @@ FO_EXPORT void fo_stream_frames_mag(const double* audio, int64_t n, int64_t win,
   free(frame); free(sp);
 }
 
+/* Streaming NMFFilter equivalent: clients/rt/NMFFilterClient.hpp:98-117 driven by STFTBufferedProcess<true>
+ * (clients/common/BufferedProcess.hpp:187-241) over a mono stream of n samples that starts from reset state.
+ *   frame f (f*hop < n) = stream[f*hop - win, f*hop) (FluidSource.hpp:68-89), windowed rFFT (STFT.hpp:110-118), |.|;
+ *   processFrame with the bases copied fresh from the float filter buffer (:94-95; the copy happens once per host
+ *   vector, we model host vectors <= hop), estimate v = W^T h (:104-106); mask k = h[k] W[k,:] / max(v, eps), min 1
+ *   (:107-113); ISTFT::processFrame = irfft * 1/fft * window (STFT.hpp:154-164); overlap-add at [f*hop, f*hop+win)
+ *   (FluidSink.hpp:49-68) next to window*window (BufferedProcess.hpp:219-224); output sample = x != 0 ?
+ *   x / (g > 0 ? g : 1) : x (:231-237).  Latency = win samples (NMFFilterClient.hpp:64).
+ * out[K][n] (NULL ok), acts[nframes][K] (NULL ok; what NMFMatch would emit with the same iteration count). */
+FO_EXPORT void fo_nmffilter_stream(const double* audio, int64_t n, int64_t win, int64_t fft, int64_t hop,
+                                   const double* W_in, int64_t K, int64_t n_iter, int64_t seed, double* out,
+                                   double* acts)
+{
+  int64_t B = fft / 2 + 1;
+  int64_t nframes = (n + hop - 1) / hop;
+  double scale = 1.0 / (double) fft;
+  double* w = (double*) malloc(sizeof(double) * (size_t) win);
+  fo_hann(win, w);
+  double* frame = (double*) malloc(sizeof(double) * (size_t) win);
+  double* sp = (double*) malloc(sizeof(double) * (size_t) (2 * B));
+  double* msp = (double*) malloc(sizeof(double) * (size_t) (2 * B));
+  double* mag = (double*) malloc(sizeof(double) * (size_t) B);
+  double* est = (double*) malloc(sizeof(double) * (size_t) B);
+  double* src = (double*) malloc(sizeof(double) * (size_t) B);
+  double* W = (double*) malloc(sizeof(double) * (size_t) (K * B));
+  double* h = (double*) malloc(sizeof(double) * (size_t) K);
+  double* nrm = (double*) calloc((size_t) (n + win), sizeof(double));
+  double* acc = out ? (double*) calloc((size_t) (K * (n + win)), sizeof(double)) : NULL;
+  fo_fft_plan* p = fo_fft_plan_new(fft);
+  double* scratch = (double*) malloc(sizeof(double) * (size_t) fft * 3);
+  double* y = scratch + 2 * fft;
+  for (int64_t f = 0; f < nframes; f++) {
+    for (int64_t j = 0; j < win; j++) {
+      int64_t t = f * hop - win + j;
+      frame[j] = (t >= 0 && t < n) ? audio[t] : 0.0;
+    }
+    fo_stft_frame(frame, win, fft, sp);
+    fo_magnitude(sp, B, mag);
+    memcpy(W, W_in, sizeof(double) * (size_t) (K * B));
+    fo_nmf_process_frame(mag, W, B, K, n_iter, seed, h, est);
+    if (acts) memcpy(acts + f * K, h, sizeof(double) * (size_t) K);
+    for (int64_t j = 0; j < win; j++) nrm[f * hop + j] += w[j] * w[j];
+    if (!out) continue;
+    for (int64_t k = 0; k < K; k++) {
+      fo_nmf_estimate(W, h, 1, B, K, k, src);
+      fo_ratio_mask(sp, src, est, B, msp);
+      fo_irfft_plan(p, msp, y, scratch, scratch + fft);
+      double* a = acc + k * (n + win);
+      for (int64_t j = 0; j < win; j++) a[f * hop + j] += y[j] * scale * w[j];
+    }
+  }
+  if (out)
+    for (int64_t k = 0; k < K; k++)
+      for (int64_t t = 0; t < n; t++) {
+        double x = acc[k * (n + win) + t], g = nrm[t];
+        if (x != 0) x /= (g > 0) ? g : 1;
+        out[k * n + t] = x;
+      }
+  free(scratch); fo_fft_plan_free(p); free(acc); free(nrm); free(h); free(W); free(src); free(est); free(mag);
+  free(msp); free(sp); free(frame); free(w);
+}
+
 FO_EXPORT int fo_num_threads(void)
 {
 #ifdef _OPENMP

@@ -203,3 +203,95 @@ def bufnmf_channel(audio_f32, win, fft, hop, rank, iters, seed, bases_mode=0, ba
             est = nmf_estimate(W, H, j)
             rs[j] = istft(ratio_mask(S, est, Vh), win, fft, hop, n).astype(np.float32)
     return dict(bases=bases, acts=acts, resynth=rs, W=W, H=H, V=Vh)
+
+
+# ---- streaming NMFFilter / NMFMatch: NMFFilterClient.hpp:98-117, NMFMatchClient.hpp:106-118 -----------------------
+class _Source:
+    """FluidSource.hpp:42-130: ring of size+host samples; pull(frame_time) reads `size` samples ending host-frame_time
+    samples before the write head."""
+
+    def __init__(self, size, host):
+        self.size, self.host = size, host
+        self.ring = np.zeros(size + host)
+        self.counter = 0
+
+    def push(self, block):
+        n = self.ring.size
+        idx = (self.counter + np.arange(block.size)) % n
+        self.ring[idx] = block
+        self.counter = (self.counter + block.size) % n
+
+    def pull(self, blocksize, frame_time):
+        n = self.ring.size
+        offset = self.host - frame_time
+        if offset > n:
+            return np.zeros(blocksize)
+        offset += blocksize
+        start = self.counter - offset if offset <= self.counter else self.counter + n - offset
+        return self.ring[(start + np.arange(blocksize)) % n].copy()
+
+
+class _Sink:
+    """FluidSink.hpp:40-130: accumulating ring; push adds at write head + frame_time, pull copies and clears."""
+
+    def __init__(self, size, chans, host):
+        self.ring = np.zeros((chans, size + host))
+        self.counter = 0
+
+    def push(self, x, frame_time):
+        n = self.ring.shape[1]
+        if frame_time + x.shape[1] > n:
+            return
+        idx = (self.counter + frame_time + np.arange(x.shape[1])) % n
+        self.ring[:, idx] += x
+
+    def pull(self, blocksize):
+        n = self.ring.shape[1]
+        idx = (self.counter + np.arange(blocksize)) % n
+        out = self.ring[:, idx].copy()
+        self.ring[:, idx] = 0
+        self.counter = (self.counter + blocksize) % n
+        return out
+
+
+def nmffilter_stream(audio, win, fft, hop, W_in, n_iter, seed, host_size=64, want_out=True):
+    """Drives the client exactly as a host would: `host_size` samples per call through BufferedProcess
+    (BufferedProcess.hpp:49-73, 187-241).  Returns (out[K][n], acts[frames][K]); n is cut to whole host vectors."""
+    a = np.asarray(audio, dtype=np.float64)
+    W_in = np.asarray(W_in, dtype=np.float64)
+    K = W_in.shape[0]
+    nblocks = a.size // host_size
+    n = nblocks * host_size
+    src = _Source(win, host_size)
+    snk = _Sink(win, K + 1, host_size)
+    w = hann(win)
+    frame_time = 0
+    out = np.zeros((K, n))
+    acts = []
+    for blk in range(nblocks):
+        src.push(a[blk * host_size:(blk + 1) * host_size])
+        W = W_in.copy()                                                  # NMFFilterClient.hpp:94-95, per host vector
+        while frame_time < host_size:                                    # BufferedProcess.hpp:57
+            frame = src.pull(win, frame_time)
+            S = np.fft.rfft(frame * w, n=fft)                            # STFT.hpp:110-118
+            S[0] = S[0].real; S[-1] = S[-1].real
+            h, est, W = nmf_process_frame(np.abs(S), W, n_iter, seed)    # mutates the filter copy (NMF.hpp:63-64)
+            acts.append(h)
+            frames_out = np.zeros((K + 1, win))
+            if want_out:
+                for k in range(K):
+                    msp = ratio_mask(S, h[k] * W[k, :], est)             # :107-113
+                    msp[0] = msp[0].real; msp[-1] = msp[-1].real
+                    frames_out[k] = (np.fft.irfft(msp, n=fft) * fft)[:win] * (1.0 / fft) * w  # STFT.hpp:154-164
+            frames_out[K] = w * w                                        # BufferedProcess.hpp:219-224
+            snk.push(frames_out, frame_time)
+            frame_time += hop
+        frame_time -= host_size                                          # :72
+        y = snk.pull(host_size)
+        g = y[K]
+        for k in range(K):                                               # :231-237
+            x = y[k]
+            nz = x != 0
+            x[nz] = x[nz] / np.where(g[nz] > 0, g[nz], 1.0)
+            out[k, blk * host_size:(blk + 1) * host_size] = x
+    return out, np.array(acts)

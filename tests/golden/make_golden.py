@@ -10,6 +10,9 @@ Sources of truth, in order of independence:
                            synthetic spectrogram through the C oracle, cross-checked against the numpy oracle here.
   * bufnmf_wav.npz      -- BASELINE config 1 style: Resources/AudioFiles/Tremblay-AaS-SynthTwoVoices-M.wav
                            (first 32768 samples), fft 1024 hop 256 rank 4 iters 100 seed 42, incl. resynthesis.
+  * nmffilter_stream.npz -- NMFFilter/NMFMatch over a 6000-sample stream (win 256, hop 64, the rank-5 bases of
+                           nmf_small, 10 iterations, seed 42): C oracle output, cross-checked against a numpy
+                           simulation of the client's ring buffers driven with host vectors of 64 and 100 samples.
 The reference itself cannot be executed (Eigen/HISSTools absent), so these are oracle outputs: "parity unpinned".
 """
 import json
@@ -150,8 +153,23 @@ def bufnmf_wav():
                         resynth=r["resynth"].astype(np.float16 if False else np.float32), W=r["W"], H=r["H"])
 
 
+def nmffilter_stream():
+    g = np.load(os.path.join(HERE, "nmf_small.npz"))
+    a = g["audio"]; W = g["W_wh"].astype(np.float32)
+    out, acts = co.nmffilter_stream(a.astype(np.float64), 256, 256, 64, W.astype(np.float64), 10, 42)
+    for hs in (64, 100):
+        o2, h2 = no.nmffilter_stream(a.astype(np.float64), 256, 256, 64, W.astype(np.float64), 10, 42, host_size=hs)
+        n2, f2 = o2.shape[1], h2.shape[0]
+        assert np.abs(o2 - out[:, :n2]).max() < 1e-12 and np.abs(h2 - acts[:f2]).max() < 1e-12
+    np.savez_compressed(os.path.join(HERE, "nmffilter_stream.npz"), audio=a, bases=W, out=out.astype(np.float32),
+                        acts=acts)
+
+
 if __name__ == "__main__":
     co.build()
-    rng_kat(); fft_kat(); nmf_small(); bufnmf_wav()
+    if len(sys.argv) > 1 and sys.argv[1] == "stream":
+        nmffilter_stream()
+    else:
+        rng_kat(); fft_kat(); nmf_small(); bufnmf_wav(); nmffilter_stream()
     for f in sorted(os.listdir(HERE)):
         print(f, os.path.getsize(os.path.join(HERE, f)))

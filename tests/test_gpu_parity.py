@@ -206,6 +206,80 @@ def test_process_frame_reference_test_replica(fb):
 
 
 # ------------------------------------------------------------------------------------------------ BufNMF
+# ------------------------------------------------------------------------------------------------ streaming clients
+def test_nmf_filter_stream_golden(fb, oracle, golden_dir):
+    g = np.load(os.path.join(golden_dir, "nmffilter_stream.npz"))
+    a, W = g["audio"], g["bases"]
+    with fb.Plan(win=256, hop=64) as plan:
+        out, acts = plan.nmf_filter(a, W, 10, 42)
+        _, acts_only = plan.nmf_filter(a, W, 10, 42, want_out=False)          # NMFMatch on the same stream
+        import torch
+        out_d, acts_d = plan.nmf_filter(torch.from_numpy(a).cuda(), torch.from_numpy(W).cuda(), 10, 42)
+    assert out.shape == g["out"].shape and acts.shape == g["acts"].shape
+    assert rel(out, g["out"]) < TOL and rel(acts, g["acts"]) < TOL
+    assert np.array_equal(acts, acts_only)
+    assert np.array_equal(out_d.cpu().numpy(), out) and np.array_equal(acts_d.cpu().numpy(), acts)
+    assert rel(out.sum(0)[256:], a[:-256]) < 1e-5 and np.abs(out[:, :64]).max() == 0.0
+
+
+@pytest.mark.parametrize("n,win,fft,hop,K", [(5000, 200, 256, 50, 3), (3000, 128, 128, 128, 2), (777, 64, 64, 16, 4),
+                                             (4000, 256, 512, 300, 2)])
+def test_nmf_filter_stream_shapes(fb, oracle, synth, n, win, fft, hop, K):
+    a = synth(77, n)
+    rng = np.random.default_rng(3)
+    W = (rng.random((K, fft // 2 + 1)) ** 2).astype(np.float32)
+    ref_out, ref_acts = oracle.nmffilter_stream(a.astype(np.float64), win, fft, hop, W.astype(np.float64), 7, 5)
+    with fb.Plan(win=win, hop=hop, fft=fft) as plan:
+        out, acts = plan.nmf_filter(a, W, 7, 5)
+    assert rel(out, ref_out) < TOL and rel(acts, ref_acts) < TOL
+
+
+def test_nmf_filter_stream_multi_chunk(fb, oracle, synth):
+    """A stream longer than one chunk of frames (8192 at rank 16, fft 1024): chunk seams must be invisible."""
+    hop, win, K = 256, 1024, 16
+    n = 256 * 20000 + 17
+    a = np.tile(synth(11, 1 << 18), n // (1 << 18) + 1)[:n].copy()
+    a *= np.linspace(0.2, 1.0, n, dtype=np.float32)                            # no two chunks see the same frames
+    rng = np.random.default_rng(7)
+    W = (rng.random((K, 513)) ** 3).astype(np.float32)
+    with fb.Plan(win=win, hop=hop) as plan:
+        out, acts = plan.nmf_filter(a, W, 10, 42)
+    assert acts.shape == ((n + hop - 1) // hop, K)
+    assert rel(out.sum(0)[win:], a[:-win]) < 1e-5
+    for f0 in (0, 8192 - 3 - 40, 2 * (8192 - 3) - 40, 20000 - 60):             # start, both seams, tail
+        lo = max(0, f0 * hop - win); hi = min(n, (f0 + 80) * hop)
+        seg = a[lo:hi].astype(np.float64)
+        r_out, r_acts = oracle.nmffilter_stream(seg, win, 1024, hop, W.astype(np.float64), 10, 42)
+        skip = win // hop + 4                                                   # frames that saw zeros instead of history
+        t0 = lo + skip * hop + win
+        assert rel(out[:, t0:hi], r_out[:, t0 - lo:]) < TOL
+        assert rel(acts[lo // hop + skip:(hi + hop - 1) // hop], r_acts[skip:]) < TOL
+
+
+def test_config5_million_frames(fb, oracle, synth):
+    """BASELINE config 5: 10^6 streaming frames against fixed rank-16 bases, 10 iterations, h0 from seed 42."""
+    import torch
+    win, hop, K, frames = 1024, 512, 16, 1_000_000
+    n = frames * hop
+    base = torch.from_numpy(synth(21, 1 << 20)).cuda()
+    a = base.repeat(n // base.numel() + 1)[:n].contiguous()
+    a *= torch.linspace(0.1, 1.0, n, device="cuda")
+    rng = np.random.default_rng(7)
+    W = (rng.random((K, 513)) ** 3).astype(np.float32)
+    with fb.Plan(win=win, hop=hop) as plan:
+        _, acts = plan.nmf_filter(a, torch.from_numpy(W).cuda(), 10, 42, want_out=False)
+        ms = plan.stats()["ms_total"]
+    acts = acts.cpu().numpy()
+    assert acts.shape == (frames, K) and np.all(np.isfinite(acts)) and acts.min() >= 0
+    print(f"config 5: {frames / ms * 1e3:.3e} frames/s")
+    for f0 in (0, 8190, 500_000, frames - 50):                                  # includes a chunk seam
+        lo = max(0, f0 * hop - win); hi = min(n, (f0 + 50) * hop)
+        seg = a[lo:hi].cpu().numpy().astype(np.float64)
+        _, r = oracle.nmffilter_stream(seg, win, 1024, hop, W.astype(np.float64), 10, 42, want_out=False)
+        skip = win // hop + 1
+        assert rel(acts[lo // hop + skip:(hi + hop - 1) // hop], r[skip:]) < TOL
+
+
 def test_bufnmf_golden_wav(fb, golden_dir):
     g = np.load(os.path.join(golden_dir, "bufnmf_wav.npz"))
     with fb.Plan(win=1024, hop=256, fft=1024) as plan:
