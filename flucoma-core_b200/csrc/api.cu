@@ -57,7 +57,15 @@ struct StageTimer {
     p->launches = 0; p->launches_nmf = 0; p->kev_used = 0; p->backend_used = FB200_BACKEND_SIMT;
     std::memset(&p->stats, 0, sizeof(p->stats));
   }
-  void mark(int i) { cudaEventRecord(p->ev[i], p->stream); }
+  void mark(int i)
+  {
+    cudaEventRecord(p->ev[i], p->stream);
+    static const bool dbg_sync = getenv("FB200_DEBUG_SYNC") != nullptr; // developer aid: localise an asynchronous fault
+    if (dbg_sync) {
+      cudaError_t e = cudaStreamSynchronize(p->stream);
+      if (e != cudaSuccess) fprintf(stderr, "[fb200] stage mark %d: %s\n", i, cudaGetErrorString(e));
+    }
+  }
   float ms(int a, int b)
   {
     float t = 0.f;

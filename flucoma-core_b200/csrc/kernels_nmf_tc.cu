@@ -56,9 +56,12 @@ constexpr uint32_t TM_P = 0;      // + 64 g
 constexpr int RP = 2;             // parts of the ratio operand R written to TMEM (3 = exact fp32, 2 = hi + lo)
 constexpr uint32_t RCOLS = 32 * RP;
 constexpr uint32_t TM_R = 128;    // + RCOLS g : hi [0,32) mid [32,64) lo [64,96)
-constexpr uint32_t ACOLS = 48;    // per-step partial of the second MMA: [0,16) leading term, [16,48) corrections
+// per-step partial of the second MMA: [0,16) leading term R_hi X_hi, [16,48) corrections R_hi [X_mid | X_lo], [48,64) R_lo X_hi.
+// Every accumulation chain owns its columns: only MMAs of the same shape on the same accumulator address are
+// pipelined in issue order; chains of different shape must not touch each other's destination columns.
+constexpr uint32_t ACOLS = 64;
 constexpr uint32_t TM_ACC = 256;  // + ACOLS g
-constexpr uint32_t TM_WSUM = 352; // + 64 wg + 16 m : fp32 running sums of the W numerator, added by the epilogue (RN)
+constexpr uint32_t TM_WSUM = 384; // + 64 wg + 16 m : fp32 running sums of the W numerator, added by the epilogue (RN)
 
 // shared memory map (bytes)
 constexpr int OFF_V = 0;
@@ -81,6 +84,8 @@ __device__ __forceinline__ int wop_index(int part, int k, int b) { return ((((b 
 __device__ __forceinline__ int hop_index(int part, int f, int k) { return ((((f >> 3) * 3 + part) * KB + (k >> 3)) << 6) + ((f & 7) << 3) + (k & 7); }
 
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+// warp q of epilogue warpgroup 0 with warp q of warpgroup 1 (named barriers 2..5, 64 threads)
+__device__ __forceinline__ void pair_bar(int q) { asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory"); }
 // register re-distribution between the control warpgroup and the epilogue warpgroups (whole warpgroup executes it)
 __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 88;" ::: "memory"); }
 __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 208;" ::: "memory"); }
@@ -241,6 +246,7 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
         }
       }
     }
+    __syncwarp(); // lanes 1..31 wait here, not inside the CTA-wide barrier at the end of the kernel
   } else if (warp == 1) {
     // =========================================== MMA issuer =============================================
     { // the whole warp runs the issue loop converged; the MMA / commit wrappers elect one lane
@@ -333,16 +339,19 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
         DBG_MARK(4, n);
         const uint32_t rbase = tbase + TM_R + RCOLS * g;
         const uint32_t dacc = tbase + TM_ACC + ACOLS * g;
+        // The tensor core adds into the fp32 accumulator with truncation, so every accumulate costs up to one ulp of
+        // the accumulator, always in the same direction.  Columns [0,16) therefore receive ONLY the leading term
+        // R_hi X_hi (one add per K-step); all correction terms go to the small-magnitude columns [16,64).
+        // The two accumulation chains own disjoint columns: MMAs of different shape / accumulator address are not
+        // ordered against each other by the tensor pipe, only same-shape same-accumulator chains are.
 #pragma unroll
         for (int j = 0; j < 4; j++) { // K-step j = 16 bins (phase 1) / 16 frames (phase 2) = block rows 2j, 2j+1 of the step
-          // The tensor core adds into the fp32 accumulator with truncation, so every accumulate costs up to one ulp of
-          // the accumulator, always in the same direction.  Columns [0,16) therefore receive ONLY the leading term
-          // R_hi X_hi (one add per K-step); all correction terms go to the small-magnitude columns [16,48).
           const uint32_t b0 = blo + 2 * j * RSTEP; // parts hi, mid, lo side by side along N
           const uint32_t rh = rbase + 8 * j;
           if (j == 0) mma_ts_lohi<0>(dacc, rh, b0, HI_B, id48);                  // R_hi [X_hi | X_mid | X_lo] -> cols [0,48)
           else mma_ts_lohi<1>(dacc, rh, b0, HI_B, id48);
-          mma_ts_lohi<1>(dacc + 16, rh + 32, b0, HI_B, id16);                    // R_lo  X_hi              -> cols [16,32)
+          if (j == 0) mma_ts_lohi<0>(dacc + 48, rh + 32, b0, HI_B, id16);        // R_lo  X_hi              -> cols [48,64)
+          else mma_ts_lohi<1>(dacc + 48, rh + 32, b0, HI_B, id16);
         }
         mma_commit_warp(&b_full[g]); // the epilogue adds this partial to its fp32 running sums
         DBG_MARK(5, n);
@@ -387,20 +396,21 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
       if (!out_valid) return;
       mbar_wait(&b_full[wg], out_par);
       tc_fence_after();
-      uint32_t a[32], a2[16];
+      uint32_t a[32], a2[32];
       tmem_ld32(tAcc, a);
-      tmem_ld16(tAcc + 32, a2);
+      tmem_ld32(tAcc + 32, a2);
       if (out_phase == 1) {
         tmem_wait_ld();
 #pragma unroll
-        for (int k = 0; k < K; k++) hsum[k] += __uint_as_float(a[k]) + (__uint_as_float(a[16 + k]) + __uint_as_float(a2[k]));
+        for (int k = 0; k < K; k++)
+          hsum[k] += __uint_as_float(a[k]) + ((__uint_as_float(a[16 + k]) + __uint_as_float(a2[k])) + __uint_as_float(a2[16 + k]));
       } else {
         uint32_t w[16];
         if (!out_first) tmem_ld16(tWsum + 16 * out_m, w);
         tmem_wait_ld();
 #pragma unroll
         for (int k = 0; k < K; k++) {
-          float x = __uint_as_float(a[k]) + (__uint_as_float(a[16 + k]) + __uint_as_float(a2[k]));
+          float x = __uint_as_float(a[k]) + ((__uint_as_float(a[16 + k]) + __uint_as_float(a2[k])) + __uint_as_float(a2[16 + k]));
           w[k] = __float_as_uint(out_first ? x : __uint_as_float(w[k]) + x);
         }
         tmem_st16(tWsum + 16 * out_m, w);
@@ -417,11 +427,15 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
     // All loads are issued up front and the only mid-step synchronisation (b_full of this warpgroup's previous step,
     // whose second MMA still reads R[g]) is taken after the ratios already sit in registers.
     auto do_step = [&](uint32_t nn, uint32_t st, bool ph1) {
-      {
-        bool okp = mbar_try_wait(&p_full[wg], (nn >> 1) & 1), okv = mbar_try_wait(&v_full[st], (nn / NS) & 1);
-        while (!okp) okp = mbar_try_wait(&p_full[wg], (nn >> 1) & 1);
-        while (!okv) okv = mbar_try_wait(&v_full[st], (nn / NS) & 1);
-      }
+      // p_full FIRST, v_full only afterwards.  A parity wait is only unambiguous if the waiter cannot be a whole phase
+      // ahead of the barrier.  v_full[st] is the one barrier whose consecutive phases are waited for by DIFFERENT
+      // warpgroups (stage = n % 3, warpgroup = n % 2): use k-1 of this stage belonged to the other warpgroup, so this
+      // warpgroup has no wait of its own that orders it behind phase k-1.  p_full(n) does: the issuer releases A(n-1), and
+      // hence A(n), only after the other warpgroup has loaded P(n-3), which it does after ITS v_full wait on this stage.
+      // (Sampling v_full before p_full was confirmed let a parity test pass on the still incomplete previous phase when
+      // TMA was slow - cold start: stale V for the boxes not yet landed, a second expect_tx arrive inside one phase.)
+      mbar_wait(&p_full[wg], (nn >> 1) & 1);
+      mbar_wait(&v_full[st], (nn / NS) & 1);
       tc_fence_after();
       if (q == 0) DBG_MARK(8, nn);
       uint32_t p[64];
@@ -548,6 +562,9 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
               for (int j = 0; j < 8; j++) h[8 * kb + j] = acc8[j];
             }
             const float vn = VN[f];
+            // The warp with the same q in the other warpgroup works on the SAME 128 rows (it owns the other 8 components)
+            // and also needs all 16 old values: nobody may store before both have loaded.
+            if (p1) pair_bar(q);
             if (p1) {
               float pn = 0.f;
 #pragma unroll

@@ -1,0 +1,17 @@
+#!/bin/bash
+# Developer aid: link a variant of libflucoma_b200.so whose tcgen05 engine comes from another source file / extra defines.
+# usage: scratch/build_variant.sh <out.so> <kernels_nmf_tc source> [extra nvcc flags...]
+set -e
+ROOT=$(cd "$(dirname "$0")/.." && pwd)
+OUT=$1; SRC=$2; shift 2
+python $ROOT/flucoma-core_b200/build.py > /dev/null
+B=$ROOT/flucoma-core_b200/build
+TMP=$(mktemp -d)
+cp "$SRC" $ROOT/flucoma-core_b200/csrc/.variant_tc.cu
+/usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-fvisibility=hidden -ccbin /usr/bin/g++ \
+  --expt-relaxed-constexpr "$@" -c $ROOT/flucoma-core_b200/csrc/.variant_tc.cu -o $TMP/tc.o
+rm -f $ROOT/flucoma-core_b200/csrc/.variant_tc.cu
+OBJS=$(ls $B/*.o | grep -v kernels_nmf_tc.o)
+/usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -shared -ccbin /usr/bin/g++ -o "$OUT" $OBJS $TMP/tc.o -lcufft -Xlinker -rpath,/usr/local/cuda/lib64
+rm -rf $TMP
+echo "$OUT"

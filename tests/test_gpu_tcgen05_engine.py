@@ -68,3 +68,26 @@ def test_tc_engine_rejects_unqualified_shapes(fb):
     with fb.Plan(win=64, backend=fb.BACKEND_TCGEN05) as plan:
         with pytest.raises(fb.FlucomaB200Error):
             plan.nmf_process(X, 16, 3, True, True, seeds=1)
+
+
+@pytest.mark.parametrize("iters,uw,uh,launches", [(1, True, False, 150), (1, True, True, 100), (3, True, True, 60)])
+def test_tc_engine_identical_buffers_stay_identical_under_stress(fb, iters, uw, uh, launches):
+    """Regression for two synchronisation races found on the B200 (a parity wait on the V ring that could pass one phase
+    early when TMA was slow; the two warps sharing a tile row in the H-update storing before the other had loaded).
+    Every CTA factorises copies of ONE spectrogram with ONE seed, several buffers per CTA, many launches: all buffers of
+    all launches must be bit-identical (the reference's seed tests require repeatability, TestNMF.cpp:31-45), and no
+    launch may fault."""
+    torch = pytest.importorskip("torch")
+    rng = np.random.default_rng(11)
+    X1 = lowrank(rng, 1, 512, 513).astype(np.float32)
+    copies = 7 * 148
+    X = torch.from_numpy(X1).cuda().expand(copies, -1, -1).contiguous()
+    seeds = np.full(copies, 7, dtype=np.int64)
+    ref = None
+    with fb.Plan(win=64, backend=fb.BACKEND_TCGEN05) as plan:
+        for _ in range(launches):
+            W, H, _, _ = plan.nmf_process(X, 16, iters, uw, uh, seeds=seeds, want_v=False)
+            if ref is None:
+                ref = (W[0].clone(), H[0].clone())
+                assert bool(torch.isfinite(ref[0]).all()) and bool(torch.isfinite(ref[1]).all())
+            assert bool((W == ref[0]).all()) and bool((H == ref[1]).all())
