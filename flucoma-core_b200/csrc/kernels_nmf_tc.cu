@@ -73,7 +73,7 @@ constexpr int OFF_HDEN = OFF_WN + K * 4;                    // float [K]
 constexpr int OFF_PART = OFF_HDEN + K * 4;                  // float [4 tiles][8 warps][32]
 constexpr int OFF_RED = OFF_PART + 4 * 8 * 32 * 4;          // float [8 warps][36]
 constexpr int OFF_FIN = OFF_RED + 8 * 36 * 4;               // float [64]
-constexpr int OFF_HS = OFF_FIN + 64 * 4;                    // float [2 wg][128][16] per-warpgroup partial H numerators
+constexpr int OFF_HS = OFF_FIN + 64 * 4;                    // float [4 j4][2 wg][128 rows][4] per-warpgroup partial H numerators (16-byte lane stride)
 constexpr int OFF_BAR = OFF_HS + 2 * 128 * 16 * 4;          // mbarriers
 constexpr int NBAR = 2 * NS + 2 + 2 + 2 + 2 + 3;
 constexpr int OFF_SLOT = OFF_BAR + NBAR * 8;
@@ -97,6 +97,31 @@ __device__ __forceinline__ uint32_t cvt2(float a, float b)
   uint32_t r;
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
   return r;
+}
+// packed fp32 pairs (FMUL2 / FADD2: one issue slot for two IEEE-rounded operations, results identical to the scalar forms)
+__device__ __forceinline__ void mul2(float& o0, float& o1, float a0, float a1, float b0, float b1)
+{
+  uint64_t a, b, c;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(b0), "f"(b1));
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(c) : "l"(a), "l"(b));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(o0), "=f"(o1) : "l"(c));
+}
+__device__ __forceinline__ void add2(float& o0, float& o1, float a0, float a1, float b0, float b1)
+{
+  uint64_t a, b, c;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(b0), "f"(b1));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(c) : "l"(a), "l"(b));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(o0), "=f"(o1) : "l"(c));
+}
+__device__ __forceinline__ void sub2(float& o0, float& o1, float a0, float a1, float b0, float b1)
+{
+  uint64_t a, b, c;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(b0), "f"(b1));
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(c) : "l"(a), "l"(b));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(o0), "=f"(o1) : "l"(c));
 }
 __device__ __forceinline__ float rcp_fast(float x)
 {
@@ -402,16 +427,25 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
       if (out_phase == 1) {
         tmem_wait_ld();
 #pragma unroll
-        for (int k = 0; k < K; k++)
-          hsum[k] += __uint_as_float(a[k]) + ((__uint_as_float(a[16 + k]) + __uint_as_float(a2[k])) + __uint_as_float(a2[16 + k]));
+        for (int k = 0; k < K; k += 2) { // hsum += a[k] + ((a[16+k] + a2[k]) + a2[16+k]), two components per instruction
+          float x0, x1;
+          add2(x0, x1, __uint_as_float(a[16 + k]), __uint_as_float(a[17 + k]), __uint_as_float(a2[k]), __uint_as_float(a2[k + 1]));
+          add2(x0, x1, x0, x1, __uint_as_float(a2[16 + k]), __uint_as_float(a2[17 + k]));
+          add2(x0, x1, __uint_as_float(a[k]), __uint_as_float(a[k + 1]), x0, x1);
+          add2(hsum[k], hsum[k + 1], hsum[k], hsum[k + 1], x0, x1);
+        }
       } else {
         uint32_t w[16];
         if (!out_first) tmem_ld16(tWsum + 16 * out_m, w);
         tmem_wait_ld();
 #pragma unroll
-        for (int k = 0; k < K; k++) {
-          float x = __uint_as_float(a[k]) + ((__uint_as_float(a[16 + k]) + __uint_as_float(a2[k])) + __uint_as_float(a2[16 + k]));
-          w[k] = __float_as_uint(out_first ? x : __uint_as_float(w[k]) + x);
+        for (int k = 0; k < K; k += 2) {
+          float x0, x1;
+          add2(x0, x1, __uint_as_float(a[16 + k]), __uint_as_float(a[17 + k]), __uint_as_float(a2[k]), __uint_as_float(a2[k + 1]));
+          add2(x0, x1, x0, x1, __uint_as_float(a2[16 + k]), __uint_as_float(a2[17 + k]));
+          add2(x0, x1, __uint_as_float(a[k]), __uint_as_float(a[k + 1]), x0, x1);
+          if (!out_first) add2(x0, x1, __uint_as_float(w[k]), __uint_as_float(w[k + 1]), x0, x1);
+          w[k] = __float_as_uint(x0); w[k + 1] = __float_as_uint(x1);
         }
         tmem_st16(tWsum + 16 * out_m, w);
         tmem_wait_st();
@@ -467,10 +501,12 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
         ph[j] = p[2 * j] ^ __float_as_uint(v[2 * j]); pl[j] = p[2 * j + 1] ^ __float_as_uint(v[2 * j + 1]);
         continue;
 #endif
-        const float r0 = v[2 * j] * rcp_fast(fmaxf(__uint_as_float(p[2 * j]), kEps));
-        const float r1 = v[2 * j + 1] * rcp_fast(fmaxf(__uint_as_float(p[2 * j + 1]), kEps));
+        float r0, r1, l0, l1;
+        mul2(r0, r1, v[2 * j], v[2 * j + 1], rcp_fast(fmaxf(__uint_as_float(p[2 * j]), kEps)),
+             rcp_fast(fmaxf(__uint_as_float(p[2 * j + 1]), kEps)));
         ph[j] = cvt2(r0, r1);
-        pl[j] = cvt2(r0 - bf16lo_to_f(ph[j]), r1 - bf16hi_to_f(ph[j]));
+        sub2(l0, l1, r0, r1, bf16lo_to_f(ph[j]), bf16hi_to_f(ph[j]));
+        pl[j] = cvt2(l0, l1);
       }
       if (q == 0) DBG_MARK(9, nn);
       drain();
@@ -537,7 +573,7 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
             drain(); // H numerator of this warpgroup's chunks complete (all MMAs reading H_op(t) have retired)
 #pragma unroll
             for (int j4 = 0; j4 < 4; j4++)
-              *reinterpret_cast<float4*>(hs + (wg * 128 + r) * 16 + 4 * j4) = make_float4(hsum[4 * j4], hsum[4 * j4 + 1], hsum[4 * j4 + 2], hsum[4 * j4 + 3]);
+              *reinterpret_cast<float4*>(hs + ((j4 * 2 + wg) * 128 + r) * 4) = make_float4(hsum[4 * j4], hsum[4 * j4 + 1], hsum[4 * j4 + 2], hsum[4 * j4 + 3]);
 #pragma unroll
             for (int k = 0; k < K; k++) hsum[k] = 0.f;
           }
@@ -572,8 +608,8 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
               const float rn = vn / fmaxf(pn, kEps);
 #pragma unroll
               for (int j4 = 0; j4 < 4; j4++) { // all 16 new values (the Nyquist term of phase 2 needs the whole new row)
-                const float4 a = *reinterpret_cast<const float4*>(hs + r * 16 + 4 * j4);         // even chunks
-                const float4 b = *reinterpret_cast<const float4*>(hs + (128 + r) * 16 + 4 * j4); // odd chunks
+                const float4 a = *reinterpret_cast<const float4*>(hs + ((j4 * 2) * 128 + r) * 4);     // even chunks
+                const float4 b = *reinterpret_cast<const float4*>(hs + ((j4 * 2 + 1) * 128 + r) * 4); // odd chunks
                 const float num[4] = {a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w};
 #pragma unroll
                 for (int i = 0; i < 4; i++) {

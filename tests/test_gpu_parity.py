@@ -360,3 +360,26 @@ def test_config2_full_size_properties(fb, oracle, synth):
         o = oracle.bufnmf_channel(a[b], 1024, 1024, 256, K, iters, b, resynth=True)
         assert rel(bases[b], o["bases"]) < TOL and rel(acts[b], o["acts"]) < TOL
         assert rel(rs[b], o["resynth"]) < TOL
+
+
+# ------------------------------------------------------------------------- configs 3 and 4 (full shapes, reduced batch)
+@pytest.mark.parametrize("name,win,hop,K,iters", [("config3", 1024, 256, 32, 40), ("config4", 4096, 1024, 64, 12)])
+def test_config3_config4_shapes(fb, oracle, synth, name, win, hop, K, iters):
+    """BASELINE configs 3 (rank 32) and 4 (fft 4096, rank 64) at their real frame/bin/rank shapes (F = 512), a few buffers
+    and a reduced iteration count so that the fp64 CPU check stays in seconds; plus the size-independent properties."""
+    import torch
+    F = 512
+    n = (F - 1) * hop
+    batch = 3
+    a = np.stack([synth(3000 + b, n) for b in range(batch)])
+    with fb.Plan(win=win, hop=hop, fft=win) as plan:
+        r = plan.bufnmf(torch.from_numpy(a).cuda(), K, iters, seeds=np.arange(batch))
+        st = plan.stats()
+    bases = r["bases"].cpu().numpy(); acts = r["acts"].cpu().numpy()
+    assert bases.shape == (batch, K, win // 2 + 1) and acts.shape == (batch, F, K)
+    assert np.isfinite(bases).all() and np.isfinite(acts).all() and (bases >= 0).all() and (acts >= 0).all()
+    assert np.allclose(np.linalg.norm(bases.astype(np.float64), axis=2), 1.0, atol=1e-4)
+    assert np.allclose(acts.reshape(batch, -1).max(1), 1.0, atol=1e-6)
+    o = oracle.bufnmf_channel(a[1], win, win, hop, K, iters, 1)
+    assert rel(bases[1], o["bases"]) < TOL and rel(acts[1], o["acts"]) < TOL
+    print(f"{name}: {batch * F / st['ms_nmf'] * 1e3 * iters:.3e} frame-iterations/s on {batch} buffers")
