@@ -344,9 +344,14 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
         }
       }
     }
-  } else if (warp == 2) {
-    // =========================================== MMA issuer, second stage ===============================
+  } else {
+    // =========================================== MMA issuers, second stage ==============================
+    // One issuing warp PER epilogue warpgroup (warp 2: even steps, warp 3: odd steps).  With a single in-order stream
+    // the second MMA of step n queued behind that of step n-1, which belongs to the other warpgroup: whenever the two
+    // warpgroups were out of phase, B(n) was issued ~1000 cycles after its ratio was ready and the owner stalled in
+    // its next step collecting it (developer timeline).
     {
+      const uint32_t myg = warp - 2;
       const uint32_t wop_a = smem_u32(wop), hop_a = smem_u32(hop);
       constexpr uint32_t ID_P1B48 = make_idesc_bf16(128, 48, 0, 0), ID_P1B16 = make_idesc_bf16(128, 16, 0, 0);
       constexpr uint32_t ID_P2B48 = make_idesc_bf16(128, 48, 0, 1), ID_P2B16 = make_idesc_bf16(128, 16, 0, 1);
@@ -359,6 +364,7 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
       // that used them, so this stream needs no barrier besides r_full.
       auto issue_b = [&](uint32_t blo, uint32_t id48, uint32_t id16) {
         const uint32_t g = n & 1;
+        if (g != myg) { n++; return; }
         mbar_wait(&r_full[g], (n >> 1) & 1);
         tc_fence_after();
         DBG_MARK(4, n);
@@ -410,11 +416,9 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
     // The tensor core truncates when it adds into its fp32 accumulator, so long in-TMEM accumulation chains drift in
     // one direction; the NMF problem has nearly flat directions (almost identical components) along which such a
     // persistent bias piles up over the iterations.  Each step's second MMA therefore starts a fresh partial (4
-    // K-steps), and the partials are summed here with round-to-nearest fp32 adds: hsum in registers for phase 1,
+    // K-steps), and the partials are summed here with round-to-nearest fp32 adds: into this thread's row of `hs` (shared
+    // memory, conflict-free 16-byte lane stride; registers are the scarce resource of these warps) for phase 1, into the
     // TM_WSUM columns for phase 2.
-    float hsum[16];
-#pragma unroll
-    for (int k = 0; k < K; k++) hsum[k] = 0.f;
     int out_valid = 0, out_phase = 0, out_m = 0, out_first = 0; // this warpgroup's step whose partial is not yet collected
     uint32_t out_par = 0;
     auto drain = [&]() {
@@ -426,13 +430,23 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
       tmem_ld32(tAcc + 32, a2);
       if (out_phase == 1) {
         tmem_wait_ld();
+        float4* hp = reinterpret_cast<float4*>(hs) + (wg * 128 + r); // [j4][wg][row]
 #pragma unroll
-        for (int k = 0; k < K; k += 2) { // hsum += a[k] + ((a[16+k] + a2[k]) + a2[16+k]), two components per instruction
-          float x0, x1;
-          add2(x0, x1, __uint_as_float(a[16 + k]), __uint_as_float(a[17 + k]), __uint_as_float(a2[k]), __uint_as_float(a2[k + 1]));
-          add2(x0, x1, x0, x1, __uint_as_float(a2[16 + k]), __uint_as_float(a2[17 + k]));
-          add2(x0, x1, __uint_as_float(a[k]), __uint_as_float(a[k + 1]), x0, x1);
-          add2(hsum[k], hsum[k + 1], hsum[k], hsum[k + 1], x0, x1);
+        for (int j4 = 0; j4 < 4; j4++) { // hs += a[k] + ((a[16+k] + a2[k]) + a2[16+k]), two components per instruction
+          float x[4];
+#pragma unroll
+          for (int i = 0; i < 4; i += 2) {
+            const int k = 4 * j4 + i;
+            add2(x[i], x[i + 1], __uint_as_float(a[16 + k]), __uint_as_float(a[17 + k]), __uint_as_float(a2[k]), __uint_as_float(a2[k + 1]));
+            add2(x[i], x[i + 1], x[i], x[i + 1], __uint_as_float(a2[16 + k]), __uint_as_float(a2[17 + k]));
+            add2(x[i], x[i + 1], __uint_as_float(a[k]), __uint_as_float(a[k + 1]), x[i], x[i + 1]);
+          }
+          if (!out_first) {
+            const float4 h = hp[j4 * 256];
+            add2(x[0], x[1], h.x, h.y, x[0], x[1]);
+            add2(x[2], x[3], h.z, h.w, x[2], x[3]);
+          }
+          hp[j4 * 256] = make_float4(x[0], x[1], x[2], x[3]);
         }
       } else {
         uint32_t w[16];
@@ -568,14 +582,9 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
               if ((int) (n & 1) != wg) continue;
               if (q == 0) DBG_MARK(6, n);
               do_step(n, n % NS, true);
-              out_valid = 1; out_phase = 1; out_par = (n >> 1) & 1;
+              out_valid = 1; out_phase = 1; out_first = (c == wg); out_par = (n >> 1) & 1;
             }
-            drain(); // H numerator of this warpgroup's chunks complete (all MMAs reading H_op(t) have retired)
-#pragma unroll
-            for (int j4 = 0; j4 < 4; j4++)
-              *reinterpret_cast<float4*>(hs + ((j4 * 2 + wg) * 128 + r) * 4) = make_float4(hsum[4 * j4], hsum[4 * j4 + 1], hsum[4 * j4 + 2], hsum[4 * j4 + 3]);
-#pragma unroll
-            for (int k = 0; k < K; k++) hsum[k] = 0.f;
+            drain(); // H numerator of this warpgroup's chunks complete in `hs` (all MMAs reading H_op(t) have retired)
           }
           // ---------------- tile prep: H-update (if p1), W-denominator / Nyquist partials (if p2) ----------------
           else if (kind == BLK_PREP) {
