@@ -483,6 +483,7 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
       // (Sampling v_full before p_full was confirmed let a parity test pass on the still incomplete previous phase when
       // TMA was slow - cold start: stale V for the boxes not yet landed, a second expect_tx arrive inside one phase.)
       mbar_wait(&p_full[wg], (nn >> 1) & 1);
+      if (q == 0) DBG_MARK(7, nn);
       mbar_wait(&v_full[st], (nn / NS) & 1);
       tc_fence_after();
       if (q == 0) DBG_MARK(8, nn);
