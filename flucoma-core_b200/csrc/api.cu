@@ -76,19 +76,38 @@ struct StageTimer {
 
 // STFT of `batch` buffers already on the device (float [batch][n]) -> V (padded magnitudes, may be null) and/or
 // spec_all (float2 [batch][F][B], may be null).  STFT.hpp:90-108 + :61-66.
+// h_audio != nullptr: the audio still sits in (pinned) host memory; every wave is uploaded into d_audio on the plan's
+// copy stream while the previous waves run their kernels, so that only the first upload is exposed.
 int32_t run_stft(Plan* p, const float* d_audio, int64_t batch, int64_t n, int64_t F, float* V, int64_t Fp, int64_t Bp,
-                 float2* spec_all, int64_t half)
+                 float2* spec_all, int64_t half, const float* h_audio = nullptr)
 {
   const int B = p->bins;
   int64_t wave = wave_size(p, F, batch, 1);
+  if (h_audio) {
+    wave = std::min<int64_t>(wave, std::max<int64_t>(1, (batch + 7) / 8)); // at least ~8 waves to overlap
+    size_t nw = (size_t) ((batch + wave - 1) / wave);
+    while (p->cev.size() < nw + 1) { cudaEvent_t e; FB_CUDA(p, cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); p->cev.push_back(e); }
+    // the copy stream must not overwrite the staging buffer before everything queued so far has finished with it
+    FB_CUDA(p, cudaEventRecord(p->cev[nw], p->stream));
+    FB_CUDA(p, cudaStreamWaitEvent(p->copy_stream, p->cev[nw], 0));
+    size_t i = 0;
+    for (int64_t b0 = 0; b0 < batch; b0 += wave, i++) {
+      int64_t nb = std::min(wave, batch - b0);
+      FB_CUDA(p, cudaMemcpyAsync(const_cast<float*>(d_audio) + b0 * n, h_audio + b0 * n, sizeof(float) * (size_t) (nb * n),
+                                 cudaMemcpyHostToDevice, p->copy_stream));
+      FB_CUDA(p, cudaEventRecord(p->cev[i], p->copy_stream));
+    }
+  }
   FB_CUDA(p, p->frames.ensure(sizeof(float) * (size_t) (wave * F * p->fft)));
   float2* spec_wave = nullptr;
   if (!spec_all) {
     FB_CUDA(p, p->spec.ensure(sizeof(float2) * (size_t) (wave * F * B)));
     spec_wave = p->spec.as<float2>();
   }
-  for (int64_t b0 = 0; b0 < batch; b0 += wave) {
+  size_t wi = 0;
+  for (int64_t b0 = 0; b0 < batch; b0 += wave, wi++) {
     int64_t nb = std::min(wave, batch - b0);
+    if (h_audio) FB_CUDA(p, cudaStreamWaitEvent(p->stream, p->cev[wi], 0));
     launch_frame_window(p, d_audio + b0 * n, n, nb, F, p->frames.as<float>(), half);
     cufftHandle h;
     FB_TRY(get_fft_plan(p, CUFFT_R2C, nb * F, &h));
@@ -295,6 +314,7 @@ int32_t fb200_plan_create(const fb200_config* cfg, fb200_plan** out)
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, cfg->device) == cudaSuccess) p->sm_count = prop.multiProcessorCount;
   bool ok = cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking) == cudaSuccess;
+  ok = ok && cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
   for (auto& e : p->ev) ok = ok && cudaEventCreate(&e) == cudaSuccess;
   ok = ok && p->window.ensure(sizeof(float) * (size_t) p->win) == cudaSuccess;
   if (!ok) {
@@ -324,6 +344,8 @@ void fb200_plan_destroy(fb200_plan* p)
   p->pin_a.release(); p->pin_b.release();
   for (auto& e : p->ev) if (e) cudaEventDestroy(e);
   for (auto& e : p->kev) cudaEventDestroy(e);
+  for (auto& e : p->cev) cudaEventDestroy(e);
+  if (p->copy_stream) { cudaStreamSynchronize(p->copy_stream); cudaStreamDestroy(p->copy_stream); }
   if (p->stream) cudaStreamDestroy(p->stream);
   delete p;
 }
@@ -585,8 +607,11 @@ int32_t fb200_bufnmf(fb200_plan* p, const fb200_bufnmf_args* a)
   const int host = a->mem == FB200_HOST;
 
   // audio in (float32, NMFClient.hpp:240)
-  const void* d_audio;
-  FB_TRY(to_device_raw(p, a->audio, a->mem, sizeof(float) * (size_t) (batch * n), p->audio, &d_audio));
+  const void* d_audio = a->audio;
+  if (host) { // uploaded wave by wave inside run_stft, overlapped with the STFT kernels
+    FB_CUDA(p, p->audio.ensure(sizeof(float) * (size_t) (batch * n)));
+    d_audio = p->audio.p;
+  }
   const float* dW0 = nullptr; const float* dH0 = nullptr; const float* U = nullptr;
   if (a->bases_mode > 0) {                                               // :248-252
     const void* raw;
@@ -611,7 +636,8 @@ int32_t fb200_bufnmf(fb200_plan* p, const fb200_bufnmf_args* a)
     FB_CUDA(p, p->spec.ensure(sizeof(float2) * (size_t) (batch * F * B)));
     spec_all = p->spec.as<float2>();
   }
-  FB_TRY(run_stft(p, (const float*) d_audio, batch, n, F, d.V, d.Fp, d.Bp, spec_all, p->win / 2));
+  FB_TRY(run_stft(p, (const float*) d_audio, batch, n, F, d.V, d.Fp, d.Bp, spec_all, p->win / 2,
+                  host ? (const float*) a->audio : nullptr));
   t.mark(2);
   if (!dW0 || !dH0) {
     launch_mt_uniform(p, p->seeds.as<int64_t>(), batch, u_stride, p->rnd.as<float>());

@@ -83,6 +83,8 @@ struct Plan {
   fb200_config cfg{};
   int win = 0, hop = 0, fft = 0, bins = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr; // host -> device uploads that overlap with kernels on `stream`
+  std::vector<cudaEvent_t> cev;       // one event per upload wave (+ one fence)
   cudaEvent_t ev[10]{};
   std::string err;
   fb200_stats stats{};
