@@ -42,44 +42,67 @@ void launch_copy3d(Plan* p, const void* src, int src_dtype, int64_t s_b, int64_t
 
 // ------------------------------------------------------------------------------------------------------------
 // mt19937_64 + libstdc++ uniform_real_distribution<double>(0,1): value = double(raw) / 2^64, 1.0 -> nextafter(1,0).
-// algorithms/util/EigenRandom.hpp:73-110.  One thread per seed (sequential generator); the twist of the 312-word
-// state lives in local memory.  Cheap next to the update loop (B*K draws per buffer).
+// algorithms/util/EigenRandom.hpp:73-110.  One WARP per seed, the 312-word state in shared memory.  The twist of a
+// state block is two data-parallel halves: words 0..155 depend on old words only, words 156..311 on old words and on
+// the new first half (word 311 also on the new word 0), exactly as the sequential recurrence sees them.  Each half
+// reads everything it needs before it writes (the sequential loop reads mt[i+1] before overwriting it).
 // ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32) k_mt_uniform(const int64_t* __restrict__ seeds, int64_t batch, int64_t count,
-                                                   float* __restrict__ U)
+__global__ void __launch_bounds__(128) k_mt_uniform(const int64_t* __restrict__ seeds, int64_t batch, int64_t count,
+                                                    float* __restrict__ U)
 {
-  int64_t b = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
+  __shared__ unsigned long long state[4][312];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t b = (int64_t) blockIdx.x * 4 + w;
   if (b >= batch) return;
-  unsigned long long mt[312];
-  mt[0] = (unsigned long long) seeds[b];
-  for (int i = 1; i < 312; i++) mt[i] = 6364136223846793005ULL * (mt[i - 1] ^ (mt[i - 1] >> 62)) + (unsigned long long) i;
-  int idx = 312;
-  float* out = U + b * count;
-  for (int64_t n = 0; n < count; n++) {
-    if (idx >= 312) {
-      for (int i = 0; i < 312; i++) {
-        int i1 = i + 1 == 312 ? 0 : i + 1;
-        int im = i + 156 >= 312 ? i + 156 - 312 : i + 156;
-        unsigned long long x = (mt[i] & 0xFFFFFFFF80000000ULL) | (mt[i1] & 0x7FFFFFFFULL);
-        mt[i] = mt[im] ^ (x >> 1) ^ ((x & 1ULL) ? 0xB5026F5AA96619E9ULL : 0ULL);
-      }
-      idx = 0;
+  unsigned long long* mt = state[w];
+  if (lane == 0) {
+    unsigned long long x = (unsigned long long) seeds[b];
+    mt[0] = x;
+    for (int i = 1; i < 312; i++) {
+      x = 6364136223846793005ULL * (x ^ (x >> 62)) + (unsigned long long) i;
+      mt[i] = x;
     }
-    unsigned long long x = mt[idx++];
-    x ^= (x >> 29) & 0x5555555555555555ULL;
-    x ^= (x << 17) & 0x71D67FFFEDA60000ULL;
-    x ^= (x << 37) & 0xFFF7EEE000000000ULL;
-    x ^= (x >> 43);
-    double r = __ull2double_rn(x) * 5.42101086242752217e-20; // 2^-64
-    if (r >= 1.0) r = 0.99999999999999989;
-    out[n] = (float) r;
+  }
+  __syncwarp();
+  float* out = U + b * count;
+  for (int64_t base = 0; base < count; base += 312) {
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+      unsigned long long nv[5];
+#pragma unroll
+      for (int j = 0; j < 5; j++) {
+        const int i = half * 156 + lane + 32 * j;
+        if (lane + 32 * j < 156) {
+          const int i1 = i + 1 == 312 ? 0 : i + 1;
+          const int im = i + 156 >= 312 ? i - 156 : i + 156;
+          const unsigned long long x = (mt[i] & 0xFFFFFFFF80000000ULL) | (mt[i1] & 0x7FFFFFFFULL);
+          nv[j] = mt[im] ^ (x >> 1) ^ ((x & 1ULL) ? 0xB5026F5AA96619E9ULL : 0ULL);
+        }
+      }
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 5; j++)
+        if (lane + 32 * j < 156) mt[half * 156 + lane + 32 * j] = nv[j];
+      __syncwarp();
+    }
+    for (int i = lane; i < 312 && base + i < count; i += 32) {
+      unsigned long long x = mt[i];
+      x ^= (x >> 29) & 0x5555555555555555ULL;
+      x ^= (x << 17) & 0x71D67FFFEDA60000ULL;
+      x ^= (x << 37) & 0xFFF7EEE000000000ULL;
+      x ^= (x >> 43);
+      double r = __ull2double_rn(x) * 5.42101086242752217e-20; // 2^-64
+      if (r >= 1.0) r = 0.99999999999999989;
+      out[base + i] = (float) r;
+    }
+    __syncwarp();
   }
 }
 
 void launch_mt_uniform(Plan* p, const int64_t* d_seeds, int64_t batch, int64_t count, float* U)
 {
   if (batch <= 0 || count <= 0) return;
-  k_mt_uniform<<<(unsigned) ((batch + 31) / 32), 32, 0, p->stream>>>(d_seeds, batch, count, U);
+  k_mt_uniform<<<(unsigned) ((batch + 3) / 4), 128, 0, p->stream>>>(d_seeds, batch, count, U);
   p->launches++;
 }
 
