@@ -187,7 +187,12 @@ using namespace tcn;
 
 // developer timeline: CTA 0 records clock64() at a few points of steps [DBG_N0, DBG_N0 + 32) when a debug buffer is given
 #define DBG_N0 192
+// (compiled in only with -DFB200_TC_DEBUG_TIMELINE: the marks cost issue slots and registers in the per-step path)
+#ifdef FB200_TC_DEBUG_TIMELINE
 #define DBG_MARK(slot, nn) do { if (dbg && blockIdx.x == 0 && (nn) >= DBG_N0 && (nn) < DBG_N0 + 32 && lane == 0) dbg[((nn) - DBG_N0) * 16 + (slot)] = clock64(); } while (0)
+#else
+#define DBG_MARK(slot, nn) do { (void) dbg; } while (0)
+#endif
 
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_constant__ CUtensorMap tmap2, int iters, int upd_w, int upd_h,
@@ -833,11 +838,13 @@ int32_t tc_run(Plan* p, const NmfDev& d, int iters, bool upd_w, bool upd_h)
   while (p->kev.size() < p->kev_used + 2) { cudaEvent_t e; cudaEventCreate(&e); p->kev.push_back(e); }
   cudaEventRecord(p->kev[p->kev_used++], p->stream);
   long long* dbg = nullptr;
+#ifdef FB200_TC_DEBUG_TIMELINE
   if (getenv("FB200_TC_TIMELINE")) { // developer aid: per-step timeline of CTA 0, dumped to stderr after the launch
     FB_CUDA(p, p->out_b.ensure(sizeof(long long) * 32 * 16));
     FB_CUDA(p, cudaMemsetAsync(p->out_b.p, 0, sizeof(long long) * 32 * 16, p->stream));
     dbg = p->out_b.as<long long>();
   }
+#endif
   k_nmf_tc<<<grid, NTHREADS, SMEM_BYTES, p->stream>>>(d, tmap1, tmap2, iters, upd_w ? 1 : 0, upd_h ? 1 : 0, dbg);
   if (dbg) {
     std::vector<long long> h(32 * 16);
