@@ -772,6 +772,99 @@ int32_t fb200_nmf_filter(fb200_plan* p, const fb200_filter_args* a)
   return FB200_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+int32_t fb200_bufstft_sizes(int32_t win, int32_t hop, int32_t padding_mode, int32_t invert, int64_t count, int64_t* padding,
+                            int64_t* out)
+{
+  if (win <= 0 || padding_mode < 0 || padding_mode > 2 || count < 0) return FB200_ERR_INVALID;
+  if (hop <= 0) hop = win >> 1;
+  if (hop <= 0) return FB200_ERR_INVALID;
+  const int64_t pad = padding_mode == 0 ? 0 : (padding_mode == 1 ? (win >> 1) : win - hop); // ParameterTypes.hpp:315-323
+  if (padding) *padding = pad;
+  if (!invert) {
+    int64_t padded = count + 2 * pad;                                    // BufSTFTClient.hpp:121-124
+    if (padding_mode == 2) padded = (padded + hop - 1) / hop * hop;      // :126-128
+    if (padded < win) return FB200_ERR_INVALID;
+    if (out) *out = 1 + (padded - win) / hop;                            // :130-131
+  } else {
+    if (count < 1) return FB200_ERR_INVALID;
+    const int64_t len = (count - 1) * hop + win - pad;                   // :241-242
+    if (len <= 0) return FB200_ERR_INVALID;
+    if (out) *out = len;
+  }
+  return FB200_OK;
+}
+
+int32_t fb200_bufstft(fb200_plan* p, const fb200_bufstft_args* a)
+{
+  if (!p) return FB200_ERR_INVALID;
+  if (!a || a->struct_size != sizeof(fb200_bufstft_args) || a->batch <= 0 || a->frames <= 0) {
+    p->err = "fb200_bufstft: bad arguments";
+    return FB200_ERR_INVALID;
+  }
+  const int64_t batch = a->batch, F = a->frames, B = p->bins;
+  const int host = a->mem == FB200_HOST;
+  int64_t pad = 0, derived = 0;
+  FB_CUDA(p, cudaSetDevice(p->cfg.device));
+  StageTimer t(p);
+  t.mark(0);
+  const size_t fb_bytes = sizeof(float) * (size_t) (batch * F * B);
+  if (!a->invert) {
+    // ---- processFwd (:82-190)
+    if (!a->audio) { p->err = "No input buffer supplied"; return FB200_ERR_INVALID; }                    // :86
+    if (!a->mag && !a->phase) { p->err = "Neither magnitude nor phase buffer supplied"; return FB200_ERR_INVALID; } // :94-96
+    if (fb200_bufstft_sizes(p->win, p->hop, a->padding_mode, 0, a->n_samples, &pad, &derived) != FB200_OK || derived != F) {
+      p->err = "fb200_bufstft: frames does not match fb200_bufstft_sizes for this input length";
+      return FB200_ERR_INVALID;
+    }
+    const int64_t n = a->n_samples;
+    const void* raw;
+    FB_TRY(to_device_raw(p, a->audio, a->mem, sizeof(float) * (size_t) (batch * n), p->audio, &raw));
+    t.mark(1);
+    FB_CUDA(p, p->spec.ensure(sizeof(float2) * (size_t) (batch * F * B)));
+    float* d_mag = nullptr;
+    if (a->mag) {
+      d_mag = a->mag;
+      if (host) { FB_CUDA(p, p->out_a.ensure(fb_bytes)); d_mag = p->out_a.as<float>(); }
+    }
+    // frame i = padded[i*hop, i*hop + win) with the audio at offset `pad` (:148-160); dense magnitudes [F][B]
+    FB_TRY(run_stft(p, (const float*) raw, batch, n, F, d_mag, F, B, p->spec.as<float2>(), pad));
+    if (a->phase) {
+      float* d_ph = a->phase;
+      if (host) { FB_CUDA(p, p->out_b.ensure(fb_bytes)); d_ph = p->out_b.as<float>(); }
+      launch_phase(p, p->spec.as<float2>(), batch * F * B, d_ph);
+      if (host) FB_CUDA(p, cudaMemcpyAsync(a->phase, d_ph, fb_bytes, cudaMemcpyDeviceToHost, p->stream));
+    }
+    if (a->mag && host) FB_CUDA(p, cudaMemcpyAsync(a->mag, d_mag, fb_bytes, cudaMemcpyDeviceToHost, p->stream));
+    t.mark(2);
+    FB_TRY(finish(p, t, 2));
+    p->stats.ms_h2d = t.ms(0, 1); p->stats.ms_stft = t.ms(1, 2);
+    return FB200_OK;
+  }
+  // ---- processInverse (:192-279)
+  if (!a->mag || !a->phase) { p->err = "Need both magnutude and phase buffers for inverse transform"; return FB200_ERR_INVALID; } // :201-203
+  if (!a->resynth) { p->err = "No resynthesis buffer supplied"; return FB200_ERR_INVALID; }              // :207
+  if (fb200_bufstft_sizes(p->win, p->hop, a->padding_mode, 1, F, &pad, &derived) != FB200_OK) {
+    p->err = "fb200_bufstft: bad frame count";
+    return FB200_ERR_INVALID;
+  }
+  const int64_t n_out = derived;
+  const void* raw_m; const void* raw_p;
+  FB_TRY(to_device_raw(p, a->mag, a->mem, fb_bytes, p->out_a, &raw_m));
+  FB_TRY(to_device_raw(p, a->phase, a->mem, fb_bytes, p->out_b, &raw_p));
+  t.mark(1);
+  FB_CUDA(p, p->cspec.ensure(sizeof(float2) * (size_t) (batch * F * B)));
+  launch_polar(p, (const float*) raw_m, (const float*) raw_p, batch * F, p->cspec.as<float2>());
+  float* d_out = a->resynth;
+  if (host) { FB_CUDA(p, p->audio.ensure(sizeof(float) * (size_t) (batch * n_out))); d_out = p->audio.as<float>(); }
+  FB_TRY(run_istft(p, p->cspec.as<float2>(), batch, F, n_out, d_out, pad));                               // :254-275
+  if (host) FB_CUDA(p, cudaMemcpyAsync(a->resynth, d_out, sizeof(float) * (size_t) (batch * n_out), cudaMemcpyDeviceToHost, p->stream));
+  t.mark(2);
+  FB_TRY(finish(p, t, 2));
+  p->stats.ms_h2d = t.ms(0, 1); p->stats.ms_resynth = t.ms(1, 2);
+  return FB200_OK;
+}
+
 int32_t fb200_selftest_tcgen05(fb200_plan* p, const float* in, int64_t n_in, float* out, int64_t n_out)
 {
   if (!p) return FB200_ERR_INVALID;
@@ -804,7 +897,7 @@ const fb200_api* fb200_get_api(uint32_t abi_version)
   static const fb200_api api = {FB200_ABI_VERSION, (uint32_t) sizeof(fb200_api), fb200_device_count, fb200_plan_create,
                                 fb200_plan_destroy, fb200_last_error, fb200_num_frames, fb200_resolve_fft,
                                 fb200_shard_range, fb200_stft, fb200_istft, fb200_nmf_process, fb200_nmf_process_frames,
-                                fb200_bufnmf, fb200_nmf_filter, fb200_get_stats};
+                                fb200_bufnmf, fb200_nmf_filter, fb200_get_stats, fb200_bufstft_sizes, fb200_bufstft};
   return abi_version == FB200_ABI_VERSION ? &api : nullptr;
 }
 

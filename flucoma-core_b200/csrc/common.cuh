@@ -159,6 +159,9 @@ void launch_hann(Plan* p);
 void launch_frame_window(Plan* p, const float* audio, int64_t n, int64_t nbuf, int64_t F, float* frames, int64_t half);
 // spec [nbuf*F][B] complex -> V[nbuf][Fp][Bp] magnitudes (+ zero imag of DC/Nyquist in place, FFT.hpp:99-101)
 void launch_magnitude(Plan* p, float2* spec, int64_t nbuf, int64_t F, float* V, int64_t Fp, int64_t Bp);
+// phase[e] = arg(spec[e]) (STFT.hpp:75-87); spec = polar(mag, phase) (BufSTFTClient.hpp:236-239)
+void launch_phase(Plan* p, const float2* spec, int64_t count, float* phase);
+void launch_polar(Plan* p, const float* mag, const float* phase, int64_t rows, float2* spec);
 // masked component spectra for buffers [b0, b0+nb): cspec[nb][K][F][B]  (NMF.hpp:33-42 + RatioMask.hpp:33-57)
 void launch_mask(Plan* p, const NmfDev& d, const float2* spec, int64_t b0, int64_t nb, float2* cspec);
 // overlap-add + normalise + trim (STFT.hpp:178-199): y [nsig][F][fft] -> out [nsig][n]

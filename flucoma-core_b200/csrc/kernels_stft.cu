@@ -77,6 +77,46 @@ void launch_magnitude(Plan* p, float2* spec, int64_t nbuf, int64_t F, float* V, 
   p->launches++;
 }
 
+// STFT::phase (STFT.hpp:75-87): arg of every bin, dense [count].  Im(DC) = Im(Nyquist) = 0 was applied by k_magnitude.
+__global__ void __launch_bounds__(256) k_phase(const float2* __restrict__ spec, int64_t count, float* __restrict__ phase)
+{
+  for (int64_t e = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; e < count; e += (int64_t) gridDim.x * blockDim.x) {
+    const float2 x = spec[e];
+    phase[e] = atan2f(x.y, x.x);
+  }
+}
+
+void launch_phase(Plan* p, const float2* spec, int64_t count, float* phase)
+{
+  if (count <= 0) return;
+  int grid = (int) std::min<int64_t>((count + 255) / 256, (int64_t) p->sm_count * 32);
+  k_phase<<<grid, 256, 0, p->stream>>>(spec, count, phase);
+  p->launches++;
+}
+
+// std::polar(m, p) per bin (BufSTFTClient.hpp:236-239) -> spec [rows][B]; the imaginary parts of DC and Nyquist are
+// dropped, as IFFT::process does when it packs the spectrum (FFT.hpp:151-158).
+__global__ void __launch_bounds__(256) k_polar(const float* __restrict__ mag, const float* __restrict__ phase, int64_t rows, int B,
+                                               float2* __restrict__ spec)
+{
+  const int64_t count = rows * B;
+  for (int64_t e = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; e < count; e += (int64_t) gridDim.x * blockDim.x) {
+    const int bin = (int) (e % B);
+    float sn, cs;
+    sincosf(phase[e], &sn, &cs);
+    const float m = mag[e];
+    spec[e] = make_float2(m * cs, (bin == 0 || bin == B - 1) ? 0.f : m * sn);
+  }
+}
+
+void launch_polar(Plan* p, const float* mag, const float* phase, int64_t rows, float2* spec)
+{
+  if (rows <= 0) return;
+  int grid = (int) std::min<int64_t>((rows * p->bins + 255) / 256, (int64_t) p->sm_count * 32);
+  k_polar<<<grid, 256, 0, p->stream>>>(mag, phase, rows, p->bins, spec);
+  p->launches++;
+}
+
 // NMF::estimate (NMF.hpp:33-42) + RatioMask::init/process with exponent 1 (RatioMask.hpp:33-57), all components at once:
 //   out_k[f][b] = S[f][b] * min(1, H[f][k] W[k][b] * (1 / max(sum_j H[f][j] W[j][b], eps)))
 // spec holds buffers [0, batch); this launch handles [b0, b0+nb) and writes cspec[nb][K][F][B].

@@ -65,6 +65,12 @@ class FilterArgs(C.Structure):
                 ("out", C.c_void_p), ("acts_out", C.c_void_p)]
 
 
+class BufStftArgs(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("mem", C.c_int32), ("invert", C.c_int32), ("padding_mode", C.c_int32),
+                ("batch", C.c_int64), ("n_samples", C.c_int64), ("frames", C.c_int64), ("audio", C.c_void_p),
+                ("mag", C.c_void_p), ("phase", C.c_void_p), ("resynth", C.c_void_p)]
+
+
 class Stats(C.Structure):
     _fields_ = [(n, C.c_float) for n in ("ms_h2d", "ms_stft", "ms_init", "ms_nmf", "ms_post", "ms_resynth", "ms_d2h",
                                          "ms_total")] + [("launches_total", C.c_int64), ("launches_nmf", C.c_int64),
@@ -76,7 +82,7 @@ class Stats(C.Structure):
 SYMBOLS = ["fb200_abi_version", "fb200_device_count", "fb200_plan_create", "fb200_plan_destroy", "fb200_last_error",
            "fb200_num_frames", "fb200_resolve_fft", "fb200_shard_range", "fb200_stft", "fb200_istft",
            "fb200_nmf_process", "fb200_nmf_process_frames", "fb200_bufnmf", "fb200_nmf_filter", "fb200_get_stats",
-           "fb200_get_api", "fb200_selftest_tcgen05"]
+           "fb200_get_api", "fb200_selftest_tcgen05", "fb200_bufstft_sizes", "fb200_bufstft"]
 
 _lib = None
 
@@ -116,12 +122,15 @@ def load(path: str | None = None):
     L.fb200_istft.restype = C.c_int32
     L.fb200_istft.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_int32]
     for name, T in (("fb200_nmf_process", NmfArgs), ("fb200_nmf_process_frames", FramesArgs),
-                    ("fb200_bufnmf", BufNmfArgs), ("fb200_nmf_filter", FilterArgs)):
+                    ("fb200_bufnmf", BufNmfArgs), ("fb200_nmf_filter", FilterArgs), ("fb200_bufstft", BufStftArgs)):
         fn = getattr(L, name)
         fn.restype = C.c_int32
         fn.argtypes = [C.c_void_p, C.POINTER(T)]
     L.fb200_get_stats.restype = C.c_int32
     L.fb200_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
+    L.fb200_bufstft_sizes.restype = C.c_int32
+    L.fb200_bufstft_sizes.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.POINTER(C.c_int64),
+                                      C.POINTER(C.c_int64)]
     L.fb200_selftest_tcgen05.restype = C.c_int32
     L.fb200_selftest_tcgen05.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]
     L.fb200_get_api.restype = C.c_void_p
@@ -147,6 +156,15 @@ def shard_range(total: int, world: int, rank: int):
     b, c = C.c_int64(), C.c_int64()
     load().fb200_shard_range(total, world, rank, C.byref(b), C.byref(c))
     return int(b.value), int(c.value)
+
+
+def bufstft_sizes(win: int, hop: int, padding_mode: int, invert: bool, count: int):
+    """BufSTFT size rules (BufSTFTClient.hpp:121-131, 241-242): (padding, numHops) forward / (padding, samples) inverse."""
+    pad, out = C.c_int64(), C.c_int64()
+    st = load().fb200_bufstft_sizes(win, hop, padding_mode, int(bool(invert)), count, C.byref(pad), C.byref(out))
+    if st != 0:
+        raise FlucomaB200Error(st, "bufstft_sizes: input shorter than one window or bad arguments")
+    return int(pad.value), int(out.value)
 
 
 def device_count() -> int:
@@ -260,6 +278,41 @@ class Plan:
         self._check(self._L.fb200_istft(self._h, _ptr(s), batch, F, _ptr(out), n_samples, code,
                                         DEVICE if _is_torch(s) else HOST))
         return out
+
+    # -- BufSTFT (clients/nrt/BufSTFTClient.hpp:82-190, 192-279) -----------------------------------------------------
+    def bufstft(self, audio, padding_mode=1, want_mag=True, want_phase=True):
+        """audio [batch][n] (or [n]) float32 -> (mag, phase) [batch][numHops][bins] float32 (None where not wanted)."""
+        a = self._contig(audio)
+        squeeze = a.ndim == 1
+        if squeeze:
+            a = a[None, :]
+        assert _dtype_code(a) == F32
+        batch, n = a.shape
+        _, hops = bufstft_sizes(self.win, self.hop, padding_mode, False, n)
+        mag = self._empty_like_space(a, (batch, hops, self.bins), "float32") if want_mag else None
+        ph = self._empty_like_space(a, (batch, hops, self.bins), "float32") if want_phase else None
+        args = BufStftArgs(C.sizeof(BufStftArgs), DEVICE if _is_torch(a) else HOST, 0, padding_mode, batch, n, hops, _ptr(a),
+                           _ptr(mag), _ptr(ph), None)
+        self._check(self._L.fb200_bufstft(self._h, C.byref(args)))
+        if squeeze:
+            mag = None if mag is None else mag[0]
+            ph = None if ph is None else ph[0]
+        return mag, ph
+
+    def bufstft_inverse(self, mag, phase, padding_mode=1):
+        """(mag, phase) [batch][frames][bins] (or [frames][bins]) float32 -> resynth [batch][(frames-1)*hop + win - padding]."""
+        m = self._contig(mag); p = self._contig(phase)
+        squeeze = m.ndim == 2
+        if squeeze:
+            m = m[None]; p = p[None]
+        assert _dtype_code(m) == F32 and _dtype_code(p) == F32 and tuple(m.shape) == tuple(p.shape) and m.shape[2] == self.bins
+        batch, frames, _ = m.shape
+        _, n_out = bufstft_sizes(self.win, self.hop, padding_mode, True, frames)
+        out = self._empty_like_space(m, (batch, n_out), "float32")
+        args = BufStftArgs(C.sizeof(BufStftArgs), DEVICE if _is_torch(m) else HOST, 1, padding_mode, batch, 0, frames, None,
+                           _ptr(m), _ptr(p), _ptr(out))
+        self._check(self._L.fb200_bufstft(self._h, C.byref(args)))
+        return out[0] if squeeze else out
 
     # -- NMF::process ----------------------------------------------------------------------------------------------
     def nmf_process(self, X, rank, iterations, update_w=True, update_h=True, seeds=None, W0=None, H0=None,

@@ -177,6 +177,29 @@ typedef struct fb200_filter_args {
 } fb200_filter_args;
 FB200_API int32_t fb200_nmf_filter(fb200_plan* plan, const fb200_filter_args* args);
 
+/* ---- BufSTFT: BufferSTFTClient::processFwd / processInverse  (clients/nrt/BufSTFTClient.hpp:82-190, 192-279) ----- */
+/* Size rules of the client.  padding = FFTParams::padding (clients/common/ParameterTypes.hpp:315-323): mode 0 -> 0,
+ * 1 -> win/2, 2 -> win-hop.  Forward (invert = 0, count = samples): padded = count + 2*padding, rounded up to a multiple of
+ * hop in mode 2 (:126-128); *out = numHops = 1 + (padded - win)/hop (:130-131).  Inverse (invert = 1, count = frames):
+ * *out = (count-1)*hop + win - padding (:241-242).  Returns FB200_ERR_INVALID when the padded input is shorter than
+ * one window (the reference would read past its buffer). */
+FB200_API int32_t fb200_bufstft_sizes(int32_t win, int32_t hop, int32_t padding_mode, int32_t invert, int64_t count,
+                                      int64_t* padding, int64_t* out);
+typedef struct fb200_bufstft_args {
+  uint32_t struct_size;
+  int32_t mem;                  /* float32 buffers, like BufferAdaptor */
+  int32_t invert;               /* 0 forward: audio -> mag and/or phase; 1 inverse: mag + phase -> resynth */
+  int32_t padding_mode;         /* 0 / 1 / 2 as above (the client's default is 1) */
+  int64_t batch;                /* independent mono buffers per call (the client does one) */
+  int64_t n_samples;            /* forward: samples per buffer */
+  int64_t frames;               /* frames per buffer in mag / phase: forward = numHops, inverse = given */
+  const float* audio;           /* forward in  [batch][n_samples] */
+  float* mag;                   /* forward out (may be NULL) / inverse in: [batch][frames][bins]  (:171-175 / :236-239) */
+  float* phase;                 /* forward out (may be NULL) / inverse in: [batch][frames][bins], radians (:177-181) */
+  float* resynth;               /* inverse out [batch][(frames-1)*hop + win - padding] (:243-275) */
+} fb200_bufstft_args;
+FB200_API int32_t fb200_bufstft(fb200_plan* plan, const fb200_bufstft_args* args);
+
 /* ---- instrumentation (bench.py roofline) ------------------------------------------------------------------- */
 typedef struct fb200_stats {
   float ms_h2d, ms_stft, ms_init, ms_nmf, ms_post, ms_resynth, ms_d2h, ms_total; /* CUDA-event times of the last call */
@@ -212,6 +235,8 @@ typedef struct fb200_api {
   int32_t (*bufnmf)(fb200_plan*, const fb200_bufnmf_args*);
   int32_t (*nmf_filter)(fb200_plan*, const fb200_filter_args*);
   int32_t (*get_stats)(const fb200_plan*, fb200_stats*);
+  int32_t (*bufstft_sizes)(int32_t, int32_t, int32_t, int32_t, int64_t, int64_t*, int64_t*);
+  int32_t (*bufstft)(fb200_plan*, const fb200_bufstft_args*);
 } fb200_api;
 /* returns NULL when abi_version is not supported */
 FB200_API const fb200_api* fb200_get_api(uint32_t abi_version);

@@ -73,6 +73,12 @@ def lib(path: str | None = None):
     L.fo_stream_frames_mag.argtypes = [_pd, _i64, _i64, _i64, _i64, _i64, _pd, _pd]
     L.fo_nmffilter_stream.argtypes = [_pd, _i64, _i64, _i64, _i64, _pd, _i64, _i64, _i64, _pd, _pd]
     L.fo_num_threads.restype = C.c_int
+    L.fo_bufstft_sizes.restype = C.c_int
+    L.fo_bufstft_sizes.argtypes = [_i64, _i64, _i64, C.c_int, _i64, _pi64, _pi64]
+    L.fo_bufstft_fwd.restype = C.c_int
+    L.fo_bufstft_fwd.argtypes = [_pf, _i64, _i64, _i64, _i64, _i64, _pf, _pf]
+    L.fo_bufstft_inv.restype = C.c_int
+    L.fo_bufstft_inv.argtypes = [_pf, _pf, _i64, _i64, _i64, _i64, _i64, _pf]
     if path is None:
         _LIB = L
     return L
@@ -265,6 +271,34 @@ def nmffilter_stream(audio, win, fft, hop, W, n_iter, seed, want_out=True):
     lib().fo_nmffilter_stream(_d(a), a.size, win, fft, hop, _d(W), K, n_iter, seed, _d(out) if want_out else None,
                               _d(acts))
     return out, acts
+
+
+def bufstft_sizes(win, hop, mode, invert, count):
+    """(padding, numHops) for the forward transform of `count` samples, (padding, samples) for the inverse of `count` frames."""
+    pad, out = _i64(), _i64()
+    if lib().fo_bufstft_sizes(win, hop, mode, int(invert), count, C.byref(pad), C.byref(out)) != 0:
+        raise ValueError("bufstft_sizes: input shorter than one window or bad arguments")
+    return pad.value, out.value
+
+
+def bufstft_fwd(audio, win, fft, hop, mode=1):
+    """BufSTFT processFwd of one mono float32 buffer -> (mag [hops][bins], phase [hops][bins]) float32."""
+    a = np.ascontiguousarray(audio, dtype=np.float32)
+    _, hops = bufstft_sizes(win, hop, mode, False, a.size)
+    bins = fft // 2 + 1
+    mag = np.empty((hops, bins), np.float32); ph = np.empty((hops, bins), np.float32)
+    assert lib().fo_bufstft_fwd(_f(a), a.size, win, fft, hop, mode, _f(mag), _f(ph)) == 0
+    return mag, ph
+
+
+def bufstft_inv(mag, phase, win, fft, hop, mode=1):
+    """BufSTFT processInverse: (mag, phase) [frames][bins] float32 -> float32 audio."""
+    m = np.ascontiguousarray(mag, dtype=np.float32); p = np.ascontiguousarray(phase, dtype=np.float32)
+    frames = m.shape[0]
+    _, n_out = bufstft_sizes(win, hop, mode, True, frames)
+    out = np.empty(n_out, np.float32)
+    assert lib().fo_bufstft_inv(_f(m), _f(p), frames, win, fft, hop, mode, _f(out)) == 0
+    return out
 
 
 def num_threads():

@@ -239,6 +239,95 @@ FO_EXPORT void fo_istft(const double* spec, int64_t nframes, int64_t win, int64_
 }
 
 /* ------------------------------------------------------------------------------------------------
+ * BufSTFT  clients/nrt/BufSTFTClient.hpp:82-190 (processFwd) and :192-279 (processInverse), one mono channel.
+ * Size rules: FFTParams::padding (clients/common/ParameterTypes.hpp:315-323); paddedLength and numHops (:121-131);
+ * inverse output length (:241-242).  float32 buffers in and out (BufferAdaptor), fp64 arithmetic in between.
+ * ---------------------------------------------------------------------------------------------- */
+FO_EXPORT int fo_bufstft_sizes(int64_t win, int64_t hop, int64_t mode, int invert, int64_t count, int64_t* padding,
+                               int64_t* out)
+{
+  if (win <= 0 || mode < 0 || mode > 2 || count < 0) return -1;
+  if (hop <= 0) hop = win >> 1;
+  if (hop <= 0) return -1;
+  int64_t pad = mode == 0 ? 0 : (mode == 1 ? (win >> 1) : win - hop);   /* ParameterTypes.hpp:319-321 */
+  if (padding) *padding = pad;
+  if (!invert) {
+    int64_t padded = count + 2 * pad;                                  /* :121-124 */
+    if (mode == 2) padded = (padded + hop - 1) / hop * hop;            /* :126-128 ceil to a hop multiple */
+    if (padded < win) return -1;                                       /* the reference would read out of bounds */
+    if (out) *out = 1 + (padded - win) / hop;                          /* :130-131 */
+  } else {
+    if (count < 1) return -1;
+    if (out) *out = (count - 1) * hop + win - pad;                     /* :241-242 */
+  }
+  return 0;
+}
+
+/* mag / phase: [numHops][bins] float32 (either may be NULL) */
+FO_EXPORT int fo_bufstft_fwd(const float* audio, int64_t n, int64_t win, int64_t fft, int64_t hop, int64_t mode, float* mag,
+                             float* phase)
+{
+  int64_t pad, hops;
+  if (fo_bufstft_sizes(win, hop, mode, 0, n, &pad, &hops)) return -1;
+  int64_t bins = fft / 2 + 1;
+  int64_t padded_len = (hops - 1) * hop + win;                         /* the part of paddedInput the frames touch */
+  double* padded = (double*) calloc((size_t) padded_len, sizeof(double));   /* :150 */
+  for (int64_t i = 0; i < n && pad + i < padded_len; i++) padded[pad + i] = (double) audio[i]; /* :152-153 */
+  double* w = (double*) malloc(sizeof(double) * (size_t) win);
+  fo_hann(win, w);
+  fo_fft_plan* p = fo_fft_plan_new(fft);
+  double* scratch = (double*) malloc(sizeof(double) * (size_t) (2 * fft + win + 2 * bins));
+  double* frame = scratch + 2 * fft;
+  double* spec = frame + win;
+  for (int64_t i = 0; i < hops; i++) {                                 /* :162-164 STFT::processFrame */
+    for (int64_t j = 0; j < win; j++) frame[j] = padded[i * hop + j] * w[j];
+    fo_rfft_plan(p, frame, win, spec, scratch, scratch + fft);
+    for (int64_t b = 0; b < bins; b++) {
+      if (mag) mag[i * bins + b] = (float) hypot(spec[2 * b], spec[2 * b + 1]);    /* :166-170 */
+      if (phase) phase[i * bins + b] = (float) atan2(spec[2 * b + 1], spec[2 * b]); /* :172-176, STFT.hpp:75-87 */
+    }
+  }
+  free(scratch); fo_fft_plan_free(p); free(w); free(padded);
+  return 0;
+}
+
+/* mag, phase [frames][bins] float32 -> out [(frames-1)*hop + win - padding] float32 */
+FO_EXPORT int fo_bufstft_inv(const float* mag, const float* phase, int64_t frames, int64_t win, int64_t fft, int64_t hop,
+                             int64_t mode, float* out)
+{
+  int64_t pad, n_out;
+  if (fo_bufstft_sizes(win, hop, mode, 1, frames, &pad, &n_out)) return -1;
+  int64_t bins = fft / 2 + 1;
+  int64_t plen = (frames - 1) * hop + win;                             /* :241 */
+  double scale = 1.0 / (double) fft;                                   /* ISTFT ctor, STFT.hpp:157 */
+  double* acc = (double*) calloc((size_t) plen, sizeof(double));
+  double* nrm = (double*) calloc((size_t) plen, sizeof(double));
+  double* w = (double*) malloc(sizeof(double) * (size_t) win);
+  fo_hann(win, w);
+  fo_fft_plan* p = fo_fft_plan_new(fft);
+  double* scratch = (double*) malloc(sizeof(double) * (size_t) (3 * fft + 2 * bins));
+  double* y = scratch + 2 * fft;
+  double* spec = y + fft;
+  for (int64_t i = 0; i < frames; i++) {                               /* :262-268 */
+    for (int64_t b = 0; b < bins; b++) {                               /* std::polar, :236-239 */
+      double m = (double) mag[i * bins + b], ph = (double) phase[i * bins + b];
+      spec[2 * b] = m * cos(ph); spec[2 * b + 1] = m * sin(ph);
+    }
+    fo_irfft_plan(p, spec, y, scratch, scratch + fft);                  /* ISTFT::processFrame STFT.hpp:201-214 */
+    for (int64_t j = 0; j < win; j++) {
+      acc[i * hop + j] += y[j] * scale * w[j];
+      nrm[i * hop + j] += w[j] * w[j];
+    }
+  }
+  for (int64_t t = 0; t < n_out; t++) {                                /* :270-277 */
+    double d = nrm[pad + t] > FO_EPS ? nrm[pad + t] : FO_EPS;
+    out[t] = (float) (acc[pad + t] / d);
+  }
+  free(scratch); fo_fft_plan_free(p); free(w); free(nrm); free(acc);
+  return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------
  * EigenRandom.  algorithms/util/EigenRandom.hpp:73-110 on libstdc++:
  *   std::mt19937_64 g{seed}; std::uniform_real_distribution<double>{0,1}(g) == generate_canonical<double,53>
  *   == double(raw u64) / 2^64 (one draw; a result of exactly 1.0 is replaced by nextafter(1,0)).

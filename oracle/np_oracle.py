@@ -295,3 +295,47 @@ def nmffilter_stream(audio, win, fft, hop, W_in, n_iter, seed, host_size=64, wan
             x[nz] = x[nz] / np.where(g[nz] > 0, g[nz], 1.0)
             out[k, blk * host_size:(blk + 1) * host_size] = x
     return out, np.array(acts)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# BufSTFT (clients/nrt/BufSTFTClient.hpp:82-190, 192-279), independent numpy restatement
+def bufstft_sizes(win, hop, mode, invert, count):
+    hop = hop if hop > 0 else win >> 1
+    pad = (0, win >> 1, win - hop)[mode]                                  # ParameterTypes.hpp:315-323
+    if not invert:
+        padded = count + 2 * pad                                          # :121-124
+        if mode == 2:
+            padded = -(-padded // hop) * hop                              # :126-128
+        if padded < win:
+            raise ValueError("input shorter than one window")
+        return pad, 1 + (padded - win) // hop                             # :130-131
+    return pad, (count - 1) * hop + win - pad                             # :241-242
+
+
+def bufstft_fwd(audio_f32, win, fft, hop, mode=1):
+    a = np.asarray(audio_f32, np.float32).astype(np.float64)
+    pad, hops = bufstft_sizes(win, hop, mode, False, a.size)
+    padded = np.zeros(max((hops - 1) * hop + win, pad + a.size))
+    padded[pad:pad + a.size] = a
+    w = hann(win)
+    frames = np.stack([padded[i * hop:i * hop + win] * w for i in range(hops)])
+    S = np.fft.rfft(frames, n=fft, axis=1)
+    S[:, 0] = S[:, 0].real; S[:, -1] = S[:, -1].real                      # FFT.hpp:99-101
+    return np.abs(S).astype(np.float32), np.angle(S).astype(np.float32)
+
+
+def bufstft_inv(mag_f32, phase_f32, win, fft, hop, mode=1):
+    m = np.asarray(mag_f32, np.float32).astype(np.float64); ph = np.asarray(phase_f32, np.float32).astype(np.float64)
+    frames = m.shape[0]
+    pad, n_out = bufstft_sizes(win, hop, mode, True, frames)
+    S = m * np.exp(1j * ph)
+    S[:, 0] = S[:, 0].real; S[:, -1] = S[:, -1].real                      # FFT.hpp:151-158 packs real DC / Nyquist
+    y = np.fft.irfft(S, n=fft, axis=1)[:, :win]                            # = rifft * (1/fft)
+    w = hann(win)
+    plen = (frames - 1) * hop + win
+    acc = np.zeros(plen); nrm = np.zeros(plen)
+    for i in range(frames):
+        acc[i * hop:i * hop + win] += y[i] * w
+        nrm[i * hop:i * hop + win] += w * w
+    out = acc / np.maximum(nrm, EPS)
+    return out[pad:pad + n_out].astype(np.float32)

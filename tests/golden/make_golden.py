@@ -13,6 +13,8 @@ Sources of truth, in order of independence:
   * nmffilter_stream.npz -- NMFFilter/NMFMatch over a 6000-sample stream (win 256, hop 64, the rank-5 bases of
                            nmf_small, 10 iterations, seed 42): C oracle output, cross-checked against a numpy
                            simulation of the client's ring buffers driven with host vectors of 64 and 100 samples.
+  * bufstft.npz         -- BufSTFT forward (mag, phase) and inverse of a 4000-sample synthetic buffer for the three
+                           padding modes (win 200, fft 256, hop 50): C oracle output, cross-checked against numpy.
 The reference itself cannot be executed (Eigen/HISSTools absent), so these are oracle outputs: "parity unpinned".
 """
 import json
@@ -165,11 +167,27 @@ def nmffilter_stream():
                         acts=acts)
 
 
+def bufstft():
+    a = synth_audio(77, 4000)
+    out = {"audio": a}
+    for mode in (0, 1, 2):
+        m, p = co.bufstft_fwd(a, 200, 256, 50, mode)
+        m2, p2 = no.bufstft_fwd(a, 200, 256, 50, mode)
+        z, z2 = m.astype(np.float64) * np.exp(1j * p.astype(np.float64)), m2.astype(np.float64) * np.exp(1j * p2.astype(np.float64))
+        assert np.abs(z - z2).max() <= 1e-6 * np.abs(z2).max()
+        r = co.bufstft_inv(m, p, 200, 256, 50, mode)
+        assert np.abs(r - no.bufstft_inv(m, p, 200, 256, 50, mode)).max() < 1e-6
+        out[f"mag{mode}"] = m; out[f"phase{mode}"] = p; out[f"inv{mode}"] = r
+    np.savez_compressed(os.path.join(HERE, "bufstft.npz"), **out)
+
+
 if __name__ == "__main__":
     co.build()
     if len(sys.argv) > 1 and sys.argv[1] == "stream":
         nmffilter_stream()
+    elif len(sys.argv) > 1 and sys.argv[1] == "bufstft":
+        bufstft()
     else:
-        rng_kat(); fft_kat(); nmf_small(); bufnmf_wav(); nmffilter_stream()
+        rng_kat(); fft_kat(); nmf_small(); bufnmf_wav(); nmffilter_stream(); bufstft()
     for f in sorted(os.listdir(HERE)):
         print(f, os.path.getsize(os.path.join(HERE, f)))

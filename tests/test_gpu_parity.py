@@ -383,3 +383,48 @@ def test_config3_config4_shapes(fb, oracle, synth, name, win, hop, K, iters):
     o = oracle.bufnmf_channel(a[1], win, win, hop, K, iters, 1)
     assert rel(bases[1], o["bases"]) < TOL and rel(acts[1], o["acts"]) < TOL
     print(f"{name}: {batch * F / st['ms_nmf'] * 1e3 * iters:.3e} frame-iterations/s on {batch} buffers")
+
+
+# ------------------------------------------------------------------------------------------------ BufSTFT
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_bufstft_golden_and_parity(fb, oracle, golden_dir, mode):
+    """BufSTFTClient processFwd / processInverse through fb200_bufstft against the committed oracle vectors; phases of
+    noise-floor bins are ill-conditioned, so the forward result is compared as the complex spectrum mag*exp(i*phase)."""
+    g = np.load(os.path.join(golden_dir, "bufstft.npz"))
+    a = g["audio"]
+    with fb.Plan(win=200, hop=50, fft=256) as plan:
+        m, p = plan.bufstft(a, padding_mode=mode)
+        r = plan.bufstft_inverse(g[f"mag{mode}"], g[f"phase{mode}"], padding_mode=mode)
+        m_only, none = plan.bufstft(a, padding_mode=mode, want_phase=False)
+    assert m.shape == g[f"mag{mode}"].shape and none is None and np.array_equal(m_only, m)
+    z = m.astype(np.float64) * np.exp(1j * p.astype(np.float64))
+    zg = g[f"mag{mode}"].astype(np.float64) * np.exp(1j * g[f"phase{mode}"].astype(np.float64))
+    assert rel(m, g[f"mag{mode}"]) < 2e-6 and rel(z, zg) < 2e-6
+    # The window^2 normaliser tends to zero at an unpadded edge (Hann), where acc/nrm amplifies the fp32 error of the
+    # irFFT by 1/w: the first/last `win` samples are held to 1e-4, everything else to the STFT-stage bar of 2e-6.
+    gi = g[f"inv{mode}"]
+    assert rel(r[200:-200], gi[200:-200]) < 2e-6 and rel(r, gi) < 1e-4
+    assert np.all(np.abs(p) <= np.float32(np.pi) + 1e-6)
+
+
+@pytest.mark.parametrize("n,win,fft,hop,mode", [(3000, 256, 256, 64, 1), (5000, 1024, 1024, 256, 2), (777, 128, 512, 128, 0),
+                                               (64, 64, 64, 16, 0)])
+def test_bufstft_batch_device_roundtrip(fb, oracle, synth, n, win, fft, hop, mode):
+    import torch
+    a = np.stack([synth(500 + b, n) for b in range(3)])
+    with fb.Plan(win=win, hop=hop, fft=fft) as plan:
+        md, pd = plan.bufstft(torch.from_numpy(a).cuda(), padding_mode=mode)
+        rd = plan.bufstft_inverse(md, pd, padding_mode=mode)
+        mh, ph = plan.bufstft(a, padding_mode=mode)
+    assert np.array_equal(md.cpu().numpy(), mh) and np.array_equal(pd.cpu().numpy(), ph)   # device and host paths agree
+    rd = rd.cpu().numpy()
+    for b in range(3):
+        mo, po = oracle.bufstft_fwd(a[b], win, fft, hop, mode)
+        assert rel(mh[b], mo) < 2e-6
+        ro = oracle.bufstft_inv(mo, po, win, fft, hop, mode)
+        assert rel(rd[b], ro) < 1e-4
+        if ro.size > 3 * win and 2 * hop <= win:   # without overlap every frame edge divides by a vanishing window^2
+            assert rel(rd[b][win:-win], ro[win:-win]) < 5e-6
+    with fb.Plan(win=win, hop=hop, fft=fft) as plan:
+        with pytest.raises(fb.FlucomaB200Error):
+            plan.bufstft(a[:, :max(1, win // 4)], padding_mode=0)                            # shorter than one window
