@@ -22,6 +22,17 @@ public:
   intptr_t fftRaw() const noexcept { return mFFTSize; }
   intptr_t hopRaw() const noexcept { return mHopSize; }
 
+  // zero padding either side of the analysed segment (reference :315-323): 0 none, 1 half a window, 2 window - hop
+  static index padding(const FFTParams& settings, index option)
+  {
+    switch (option)
+    {
+    case 1: return settings.winSize() >> 1;
+    case 2: return settings.winSize() - settings.hopSize();
+    default: return 0;
+    }
+  }
+
   static index nextPow2(uint32_t x, bool up)
   {
     if (!x) return static_cast<index>(x);

@@ -63,3 +63,29 @@ def test_shims_gpu_vs_oracle(oracle):
             assert np.linalg.norm(bases[:, ch] - o["bases"][j]) / np.linalg.norm(o["bases"][j]) < 1e-4
             assert np.linalg.norm(acts[:, ch] - o["acts"][:, j]) / np.linalg.norm(o["acts"][:, j]) < 1e-4
             assert np.linalg.norm(res[:, ch] - o["resynth"][j]) / max(np.linalg.norm(o["resynth"][j]), 1e-12) < 1e-4
+
+
+def test_bufstft_client_compiles_and_fails_loudly_without_gpu():
+    import torch
+    with tempfile.TemporaryDirectory() as t:
+        exe = compile_cpp("test_bufstft_gpu.cpp", os.path.join(t, "a"))
+        if torch.cuda.is_available():
+            pytest.skip("GPU present: covered by the gpu test")
+        r = subprocess.run([exe], capture_output=True, text=True, env=dict(os.environ, FLUCOMA_B200_LIB=LIB))
+        assert r.returncode != 0 and "no such CUDA device" in (r.stdout + r.stderr)  # no CPU fallback
+
+
+@pytest.mark.gpu
+def test_bufstft_client_gpu_vs_oracle(oracle):
+    with tempfile.TemporaryDirectory() as t:
+        exe = compile_cpp("test_bufstft_gpu.cpp", os.path.join(t, "a"))
+        dump = os.path.join(t, "dump.bin")
+        r = subprocess.run([exe, dump], capture_output=True, text=True, env=dict(os.environ, FLUCOMA_B200_LIB=LIB))
+        assert r.returncode == 0 and "bufstft client ok" in r.stdout, r.stdout + r.stderr
+        src, mag, phase, res = _read_dump(dump)
+    mo, po = oracle.bufstft_fwd(np.ascontiguousarray(src[:, 1]), 256, 256, 64, 1)
+    z = mag.astype(np.float64) * np.exp(1j * phase.astype(np.float64))
+    zo = mo.astype(np.float64) * np.exp(1j * po.astype(np.float64))
+    assert mag.shape == mo.shape and np.linalg.norm(z - zo) / np.linalg.norm(zo) < 2e-6
+    ro = oracle.bufstft_inv(mo, po, 256, 256, 64, 1)
+    assert res.shape == (ro.size, 1) and np.linalg.norm(res[:, 0] - ro) / np.linalg.norm(ro) < 1e-4
