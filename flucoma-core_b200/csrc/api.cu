@@ -715,7 +715,9 @@ int32_t fb200_nmf_filter(fb200_plan* p, const fb200_filter_args* a)
   const int64_t n = a->n_samples, K = a->rank, B = p->bins, hop = p->hop, win = p->win;
   const int64_t frames_total = (n + hop - 1) / hop;                      // BufferedProcess.hpp:57
   const int64_t ov = a->out ? (win - 1) / hop : 0;                       // earlier frames that still reach a sample
-  int64_t chunk = (((int64_t) 1 << 27) / std::max<int64_t>(1, K * p->fft)) / 128 * 128;
+  // frames per chunk: bounded by the cuFFT scratch of the K masked resyntheses, or, for activations only (NMFMatch),
+  // by that of the forward transform alone (K times larger chunks: fewer, better filled launches)
+  int64_t chunk = (((int64_t) 1 << 27) / std::max<int64_t>(1, (a->out ? K : 1) * p->fft)) / 128 * 128;
   chunk = std::max<int64_t>(chunk, (ov / 128 + 1) * 128);
   chunk = std::min<int64_t>(chunk, (frames_total + ov + 127) / 128 * 128);
   const int64_t fresh = chunk - ov;                                      // new frames per chunk

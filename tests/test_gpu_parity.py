@@ -272,7 +272,7 @@ def test_config5_million_frames(fb, oracle, synth):
     acts = acts.cpu().numpy()
     assert acts.shape == (frames, K) and np.all(np.isfinite(acts)) and acts.min() >= 0
     print(f"config 5: {frames / ms * 1e3:.3e} frames/s")
-    for f0 in (0, 8190, 500_000, frames - 50):                                  # includes a chunk seam
+    for f0 in (0, 8190, 131_070, 500_000, frames - 50):                         # includes a chunk seam (131072 frames per chunk)
         lo = max(0, f0 * hop - win); hi = min(n, (f0 + 50) * hop)
         seg = a[lo:hi].cpu().numpy().astype(np.float64)
         _, r = oracle.nmffilter_stream(seg, win, 1024, hop, W.astype(np.float64), 10, 42, want_out=False)
