@@ -51,30 +51,77 @@ void launch_frame_window(Plan* p, const float* audio, int64_t n, int64_t nbuf, i
 }
 
 // STFT.hpp:61-66 |X|, with Im(DC) = Im(Nyquist) = 0 as FFT.hpp:99-101 leaves them.  spec [nbuf*F][B] -> V [nbuf][Fp][Bp]
-__global__ void __launch_bounds__(256) k_magnitude(float2* __restrict__ spec, int64_t nbuf, int64_t F, int B,
-                                                   float* __restrict__ V, int64_t Fp, int64_t Bp)
+// HBM-bound (8 B in, 4 B out per bin): flat, fully coalesced indexing; the bin count is a template parameter for the
+// usual FFT sizes so that the per-element index split is a multiply-shift instead of 64-bit divisions (BT = 0: generic).
+template <int BT>
+__global__ void __launch_bounds__(256) k_magnitude(float2* __restrict__ spec, uint32_t total, uint32_t F, int Brt,
+                                                   float* __restrict__ V, uint32_t Fp, uint32_t Bp)
 {
-  int64_t total = nbuf * F * B;
-  for (int64_t e = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; e < total; e += (int64_t) gridDim.x * blockDim.x) {
-    int bin = (int) (e % B);
-    int64_t fr = e / B;
-    int64_t f = fr % F, b = fr / F;
-    float2 x = spec[e];
+  const uint32_t B = BT ? (uint32_t) BT : (uint32_t) Brt;
+  auto one = [&](uint32_t e, float2 x) {
+    const uint32_t fr = e / B, bin = e - fr * B;
     if (bin == 0 || bin == B - 1) {
       x.y = 0.f;
       spec[e] = x;
     }
-    if (V) V[(b * Fp + f) * Bp + bin] = hypotf(x.x, x.y);
+    if (V) {
+      const uint32_t b = fr / F, f = fr - b * F;
+      V[((size_t) b * Fp + f) * Bp + bin] = hypotf(x.x, x.y);
+    }
+  };
+  // two bins (16 bytes) per load and two loads in flight per thread: the kernel is latency bound otherwise
+  const uint32_t head = (reinterpret_cast<uintptr_t>(spec) & 8) ? 1u : 0u; // a wave may start on an odd bin: 8-byte aligned only
+  const uint32_t pairs = (total - head) >> 1, stride = gridDim.x * blockDim.x;
+  const float4* __restrict__ s4 = reinterpret_cast<const float4*>(spec + head);
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + stride < pairs; i += 2 * stride) {
+    const float4 a = s4[i], c = s4[i + stride];
+    one(head + 2 * i, make_float2(a.x, a.y)); one(head + 2 * i + 1, make_float2(a.z, a.w));
+    one(head + 2 * (i + stride), make_float2(c.x, c.y)); one(head + 2 * (i + stride) + 1, make_float2(c.z, c.w));
   }
+  if (i < pairs) {
+    const float4 a = s4[i];
+    one(head + 2 * i, make_float2(a.x, a.y)); one(head + 2 * i + 1, make_float2(a.z, a.w));
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (head) one(0, spec[0]);
+    if ((total - head) & 1) one(total - 1, spec[total - 1]);
+  }
+}
+
+static void launch_magnitude_rows(Plan* p, float2* sp, uint32_t total, uint32_t F, float* v, uint32_t Fp, uint32_t Bp)
+{
+  const int grid = (int) std::min<int64_t>(((int64_t) total / 2 + 255) / 256 + 1, (int64_t) p->sm_count * 16);
+  switch (p->bins) {
+  case 129: k_magnitude<129><<<grid, 256, 0, p->stream>>>(sp, total, F, p->bins, v, Fp, Bp); break;
+  case 257: k_magnitude<257><<<grid, 256, 0, p->stream>>>(sp, total, F, p->bins, v, Fp, Bp); break;
+  case 513: k_magnitude<513><<<grid, 256, 0, p->stream>>>(sp, total, F, p->bins, v, Fp, Bp); break;
+  case 1025: k_magnitude<1025><<<grid, 256, 0, p->stream>>>(sp, total, F, p->bins, v, Fp, Bp); break;
+  case 2049: k_magnitude<2049><<<grid, 256, 0, p->stream>>>(sp, total, F, p->bins, v, Fp, Bp); break;
+  default: k_magnitude<0><<<grid, 256, 0, p->stream>>>(sp, total, F, p->bins, v, Fp, Bp); break;
+  }
+  p->launches++;
 }
 
 void launch_magnitude(Plan* p, float2* spec, int64_t nbuf, int64_t F, float* V, int64_t Fp, int64_t Bp)
 {
-  int64_t total = nbuf * F * p->bins;
-  if (total <= 0) return;
-  int grid = (int) std::min<int64_t>((total + 255) / 256, (int64_t) p->sm_count * 32);
-  k_magnitude<<<grid, 256, 0, p->stream>>>(spec, nbuf, F, p->bins, V, Fp, Bp);
-  p->launches++;
+  if (nbuf <= 0 || F <= 0) return;
+  const int64_t max_rows = std::max<int64_t>(1, (((int64_t) 1 << 31) - 1) / p->bins); // 32-bit flat index per launch
+  if (F <= max_rows) { // whole buffers per launch
+    const int64_t per = std::max<int64_t>(1, max_rows / F);
+    for (int64_t b0 = 0; b0 < nbuf; b0 += per) {
+      const int64_t nb = std::min(per, nbuf - b0);
+      launch_magnitude_rows(p, spec + b0 * F * p->bins, (uint32_t) (nb * F * p->bins), (uint32_t) F, V ? V + b0 * Fp * Bp : nullptr,
+                            (uint32_t) Fp, (uint32_t) Bp);
+    }
+  } else { // a single buffer longer than 2^31 bins: row ranges of one buffer at a time
+    for (int64_t b = 0; b < nbuf; b++)
+      for (int64_t f0 = 0; f0 < F; f0 += max_rows) {
+        const int64_t nr = std::min(max_rows, F - f0);
+        launch_magnitude_rows(p, spec + (b * F + f0) * p->bins, (uint32_t) (nr * p->bins), (uint32_t) nr,
+                              V ? V + (b * Fp + f0) * Bp : nullptr, (uint32_t) nr, (uint32_t) Bp);
+      }
+  }
 }
 
 // STFT::phase (STFT.hpp:75-87): arg of every bin, dense [count].  Im(DC) = Im(Nyquist) = 0 was applied by k_magnitude.
