@@ -9,28 +9,30 @@
 //
 //   phase 1 (H-update of a 128-frame tile t, NMF.hpp:165-170), per 64-bin chunk c:
 //       P[f][b]    = H_t W_c           tcgen05.mma SS   A = H blocks (K-major)   B = W blocks (MN-major)   M128 N64 K16
-//       R[f][b]    = V / max(P, eps)   epilogue: tcgen05.ld, swizzled LDS of the TMA tile, rcp, 3-way split, tcgen05.st
-//       hnum[f][k] += R W_c^T          tcgen05.mma TS   A = R (TMEM)             B = W blocks (K-major)    M128 N32/16 K64
-//     then H <- H * hnum / max(hden, eps) for the tile.
+//       R[f][b]    = V / max(P, eps)   epilogue: tcgen05.ld, swizzled LDS of the TMA tile, rcp, 2-way split, tcgen05.st
+//       hnum[f][k] += R W_c^T          tcgen05.mma TS   A = R (TMEM)             B = W blocks (K-major)    M128 N48+N16 K64
+//     then H <- H * hnum / max(hden, eps) for the tile ("tile prep").
 //   phase 2 (this tile's share of the next W-update, NMF.hpp:158-160), per 128-bin tile m and 64-frame half s:
 //       P[b][f]    = W_m^T H_ts^T      SS   A = W blocks (MN-major)  B = H blocks (K-major)    M128 N64 K16
 //       R[b][f]    = V / max(P, eps)
-//       wnum[b][k] += R H_ts           TS   A = R (TMEM)             B = H blocks (MN-major)   M128 N32/16 K64
+//       wnum[b][k] += R H_ts           TS   A = R (TMEM)             B = H blocks (MN-major)   M128 N48+N16 K64
 //   after the last tile: W <- W * wnum / max(wden, eps), conditional column normalisation (:161-162), hden = sum_b W.
 //
 // Precision: a product of two 3-way splits keeps the six terms above 2^-24 (hh, hm, mh, hl, lh, mm), i.e. fp32-grade
 // operands with fp32 accumulation.  (A 2-way split, 16-17 mantissa bits, measured 1.3e-4 against the fp64 CPU restatement after
 // 200 iterations -- the NMF dynamics amplify the per-iteration error about 100x -- and missed the 1e-4 bar.)
 // For the second MMA the three parts of the B operand sit next to each other in shared memory, so one instruction
-// with N = 32 multiplies a ratio part by [X_hi | X_mid] at once; the accumulator is 32 columns wide and its two halves
-// are added by the epilogue.
+// with N = 48 multiplies the leading ratio part by [X_hi | X_mid | X_lo] at once and a second one (N = 16, its own
+// accumulator columns) adds R_lo X_hi; the epilogue sums the four 16-column groups of every step's FRESH accumulator
+// with round-to-nearest adds (the tensor core's accumulate truncates, which would drift over 200 iterations).
 //
 // The Nyquist bin (B = 2^m + 1) does not fit the 128-wide tiles; its column is carried on the SIMT side of the epilogue
 // (a 16-term dot product per frame), so the tensor tiles cover bins 0 .. B-2 exactly.
 //
-// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM owner), warps 2-9 = two epilogue
-// warpgroups that alternate steps (ping-pong on two P/R TMEM buffers).  All reductions are fixed-order: results are
-// bitwise repeatable.
+// Warp roles (384 threads): warp 0 = TMA producer, warp 1 = first-stage MMA issuer (+ TMEM owner), warps 2/3 = second-
+// stage MMA issuers (one per epilogue warpgroup), warps 4-11 = two epilogue warpgroups that alternate steps (ping-pong on
+// two P/R/accumulator TMEM buffers).  All reductions are fixed-order: results are bitwise repeatable.  The rules the
+// mbarrier protocol relies on are listed in DESIGN.md ("Synchronisation rules"); each has a regression test.
 #include "common.cuh"
 #include "tc_common.cuh"
 
