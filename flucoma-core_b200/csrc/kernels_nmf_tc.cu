@@ -3,7 +3,7 @@
 // One persistent CTA owns one buffer for ALL iterations.  W and H live in shared memory as exact three-way bf16
 // splits (x = hi + mid + lo reproduces the fp32 value), stored directly in UMMA core-matrix layout, so the operand
 // copies ARE the state.  V = |X| is streamed by TMA (128B swizzle) once per phase, WH is accumulated in TMEM, the ratio
-// V / max(WH, eps) is computed by the epilogue warps straight out of TMEM and written back to TMEM (again as a 3-way
+// V / max(WH, eps) is computed by the epilogue warps straight out of TMEM and written back to TMEM (as a 2-way bf16
 // split) as the A operand of the second MMA -- neither WH nor the ratio ever touch shared or global memory, and there
 // is no inter-CTA communication.
 //
