@@ -176,7 +176,21 @@ def run_ours(args):
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # NCCL prints its version banner (and, with NCCL_DEBUG set, its log) on stdout when the communicator is created;
+        # stdout must carry exactly one JSON line, so communicator creation runs with fd 1 pointed at stderr.
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            warm = torch.zeros(1, device="cuda")
+            dist.all_reduce(warm)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
 
     w = WORKLOAD
     batch, n, K, iters = w["batch"], w["n"], w["rank"], w["iters"]
