@@ -629,8 +629,8 @@ int32_t fb200_bufnmf(fb200_plan* p, const fb200_bufnmf_args* a)
     FB_CUDA(p, p->rnd.ensure(sizeof(float) * (size_t) (batch * u_stride)));
   }
   t.mark(1);
-  // STFT + |X|  (:241-242)
-  FB_CUDA(p, cudaMemsetAsync(d.V, 0, sizeof(float) * (size_t) d.batch * d.Fp * d.Bp, p->stream));
+  // STFT + |X|  (:241-242); k_magnitude writes every interior element, only the pads need zeros
+  launch_zero_pads(p, d.V, d.batch, d.F, d.Fp, d.B, d.Bp);
   float2* spec_all = nullptr;
   if (resynth) {
     FB_CUDA(p, p->spec.ensure(sizeof(float2) * (size_t) (batch * F * B)));

@@ -157,6 +157,8 @@ void launch_vhat(Plan* p, const NmfDev& d, void* dst, int dst_dtype);
 // kernels_stft.cu -----------------------------------------------------------------------------------------------
 void launch_hann(Plan* p);
 void launch_frame_window(Plan* p, const float* audio, int64_t n, int64_t nbuf, int64_t F, float* frames, int64_t half);
+// exact zeros in the pads of V[batch][Fp][Bp] (bins >= B, frames >= F) when the interior is about to be overwritten
+void launch_zero_pads(Plan* p, float* V, int64_t batch, int64_t F, int64_t Fp, int64_t B, int64_t Bp);
 // spec [nbuf*F][B] complex -> V[nbuf][Fp][Bp] magnitudes (+ zero imag of DC/Nyquist in place, FFT.hpp:99-101)
 void launch_magnitude(Plan* p, float2* spec, int64_t nbuf, int64_t F, float* V, int64_t Fp, int64_t Bp);
 // phase[e] = arg(spec[e]) (STFT.hpp:75-87); spec = polar(mag, phase) (BufSTFTClient.hpp:236-239)

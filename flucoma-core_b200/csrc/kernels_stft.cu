@@ -20,24 +20,38 @@ void launch_hann(Plan* p)
 // STFT.hpp:92-105: frame i of buffer b = padded[i*hop : i*hop+win] * window, padded = [win/2 zeros | audio | zeros];
 // written zero-extended to `fft` samples (FFT.hpp:97: htl::rfft zero-pads a short input).
 // `half` is the left padding: win/2 for STFT::process, win for the streaming clients (BufferedProcess.hpp:75-93).
+// VEC: hop, half, n and win are multiples of 4 and the audio is 16-byte aligned, so a frame quad inside the signal is
+// one 16-byte load (the window quad always is); the 64-bit index split is done once per quad.
+template <bool VEC>
 __global__ void __launch_bounds__(256) k_frame_window(const float* __restrict__ audio, int64_t n, int64_t nbuf, int64_t F,
                                                       const float* __restrict__ window, int win, int fft, int hop,
                                                       int64_t half, float* __restrict__ frames)
 {
-  int64_t total = nbuf * F * (int64_t) (fft / 4);
+  const int q4 = fft / 4;
+  const int64_t total = nbuf * F * (int64_t) q4;
   for (int64_t e = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; e < total; e += (int64_t) gridDim.x * blockDim.x) {
-    int j4 = (int) (e % (fft / 4));
-    int64_t fr = e / (fft / 4);
-    int64_t i = fr % F, b = fr / F;
+    const int j4 = (int) (e % q4);
+    const int64_t fr = e / q4;
+    const int64_t i = fr % F, b = fr / F;
     const float* a = audio + b * n;
-    float o[4];
+    const int j0 = 4 * j4;
+    const int64_t t0 = i * hop + j0 - half;
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (VEC && j0 + 3 < win && t0 >= 0 && t0 + 3 < n) {
+      const float4 x = *reinterpret_cast<const float4*>(a + t0);
+      const float4 w = *reinterpret_cast<const float4*>(window + j0);
+      o = make_float4(x.x * w.x, x.y * w.y, x.z * w.z, x.w * w.w);
+    } else if (j0 < win) {
+      float v[4];
 #pragma unroll
-    for (int q = 0; q < 4; q++) {
-      int j = 4 * j4 + q;
-      int64_t t = i * hop + j - half;
-      o[q] = (j < win && t >= 0 && t < n) ? a[t] * window[j] : 0.f;
+      for (int q = 0; q < 4; q++) {
+        const int j = j0 + q;
+        const int64_t t = t0 + q;
+        v[q] = (j < win && t >= 0 && t < n) ? a[t] * window[j] : 0.f;
+      }
+      o = make_float4(v[0], v[1], v[2], v[3]);
     }
-    *reinterpret_cast<float4*>(frames + fr * fft + 4 * j4) = make_float4(o[0], o[1], o[2], o[3]);
+    *reinterpret_cast<float4*>(frames + fr * fft + j0) = o;
   }
 }
 
@@ -46,7 +60,42 @@ void launch_frame_window(Plan* p, const float* audio, int64_t n, int64_t nbuf, i
   int64_t total = nbuf * F * (int64_t) (p->fft / 4);
   if (total <= 0) return;
   int grid = (int) std::min<int64_t>((total + 255) / 256, (int64_t) p->sm_count * 32);
-  k_frame_window<<<grid, 256, 0, p->stream>>>(audio, n, nbuf, F, p->window.as<float>(), p->win, p->fft, p->hop, half, frames);
+  const bool vec = (p->hop % 4 == 0) && (half % 4 == 0) && (n % 4 == 0) && (p->win % 4 == 0) &&
+                   (reinterpret_cast<uintptr_t>(audio) % 16 == 0);
+  if (vec)
+    k_frame_window<true><<<grid, 256, 0, p->stream>>>(audio, n, nbuf, F, p->window.as<float>(), p->win, p->fft, p->hop, half, frames);
+  else
+    k_frame_window<false><<<grid, 256, 0, p->stream>>>(audio, n, nbuf, F, p->window.as<float>(), p->win, p->fft, p->hop, half, frames);
+  p->launches++;
+}
+
+// |X| buffers are padded to [Fp][Bp]; the update kernels rely on exact zeros in the pads (bins >= B, frames >= F).
+// Zeroing only the pads replaces a memset of the whole array (1.1 GB at config 2) by a few MB of stores.
+__global__ void __launch_bounds__(256) k_zero_pads(float* __restrict__ V, int64_t rows_total, int F, int Fp, int B, int Bp)
+{
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = (int64_t) gridDim.x * (blockDim.x >> 5);
+  for (int64_t row = (int64_t) blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows_total; row += warps) {
+    const int f = (int) (row % Fp);
+    float* r = V + row * Bp;
+    if (f < F) {
+      if (lane < Bp - B) r[B + lane] = 0.f;
+    } else {
+      for (int j = lane; j < Bp; j += 32) r[j] = 0.f;
+    }
+  }
+}
+
+void launch_zero_pads(Plan* p, float* V, int64_t batch, int64_t F, int64_t Fp, int64_t B, int64_t Bp)
+{
+  const int64_t rows = batch * Fp;
+  if (rows <= 0 || (Bp == B && Fp == F)) return;
+  if (Bp - B > 32) { // not a layout this library produces; keep it simple and correct
+    cudaMemsetAsync(V, 0, sizeof(float) * (size_t) (rows * Bp), p->stream);
+    return;
+  }
+  int grid = (int) std::min<int64_t>((rows + 7) / 8, (int64_t) p->sm_count * 32);
+  k_zero_pads<<<grid, 256, 0, p->stream>>>(V, rows, (int) F, (int) Fp, (int) B, (int) Bp);
   p->launches++;
 }
 
