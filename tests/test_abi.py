@@ -93,3 +93,25 @@ def test_product_package_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
                 src = open(os.path.join(dp, f), errors="ignore").read()
                 assert "oracle" not in src.lower() or f == "README.md", f"{f} mentions the oracle"
+
+
+def test_bufstft_size_rules_match_the_oracle(fb):
+    """fb200_bufstft_sizes is host-only: BufSTFTClient.hpp:121-131 / 241-242 against the CPU restatement, all padding modes."""
+    from oracle import c_oracle
+    c_oracle.build()
+    for win, hop in ((1024, 256), (200, 50), (128, 128), (64, 16), (4096, 1024)):
+        for mode in (0, 1, 2):
+            for n in (win, win + 1, 3 * win - 7, 10 * win + hop // 2, 130816):
+                try:
+                    want = c_oracle.bufstft_sizes(win, hop, mode, False, n)
+                except ValueError:
+                    with pytest.raises(fb.FlucomaB200Error):
+                        fb.bufstft_sizes(win, hop, mode, False, n)
+                    continue
+                assert fb.bufstft_sizes(win, hop, mode, False, n) == want
+                frames = want[1]
+                assert fb.bufstft_sizes(win, hop, mode, True, frames) == c_oracle.bufstft_sizes(win, hop, mode, True, frames)
+    with pytest.raises(fb.FlucomaB200Error):
+        fb.bufstft_sizes(1024, 256, 0, False, 100)        # shorter than one window
+    with pytest.raises(fb.FlucomaB200Error):
+        fb.bufstft_sizes(1024, 256, 3, False, 4096)       # no such padding mode
