@@ -6,7 +6,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
 #include <random>
+#include <thread>
 
 using namespace fb200;
 
@@ -174,8 +176,67 @@ int32_t upload_seeds(Plan* p, const int64_t* seeds, int64_t batch)
   return FB200_OK;
 }
 
+// n fused iterations on the SIMT engine; leaves W,H exactly as after n reference iterations (NMF.hpp:154-172)
+void simt_run_iters(Plan* p, NmfDev& d, int n, bool upd_w, bool upd_h)
+{
+  if (upd_w && upd_h) {
+    simt_launch_tile(p, d, 0, 1, 1); // W-numerator of the first iteration
+    simt_launch_w_finalize(p, d);
+    for (int it = 1; it < n; it++) {
+      simt_launch_tile(p, d, 1, 1, 1); // H-update of iteration `it` fused with the W-numerator of `it+1`
+      simt_launch_w_finalize(p, d);
+    }
+    simt_launch_tile(p, d, 1, 0, 1); // H-update of the last iteration
+  } else if (upd_w) {
+    for (int it = 0; it < n; it++) { simt_launch_tile(p, d, 0, 1, 1); simt_launch_w_finalize(p, d); }
+  } else {
+    for (int it = 0; it < n; it++) simt_launch_tile(p, d, 1, 0, 1);
+  }
+}
+
+// Asynchronous progress on the persistent tensor-core engine: ONE launch runs all iterations; the calling thread polls
+// the per-CTA pass counters in host-mapped memory, reports iterations 1..n (each exactly once, in order) as the batch
+// advances, and raises the cancel word when a callback returns 0.  See `Ctl` in kernels_nmf_tc.cu.
+int32_t run_tc_async(Plan* p, NmfDev& d, int iters, bool upd_w, bool upd_h, fb200_progress_fn progress, void* user)
+{
+  const int grid = tc_grid(p, d);
+  if (!p->ctrl.p) FB_CUDA(p, cudaHostAlloc(&p->ctrl.p, sizeof(unsigned int) * 1025, cudaHostAllocMapped));
+  volatile unsigned int* ctrl = reinterpret_cast<volatile unsigned int*>(p->ctrl.p);
+  for (int i = 0; i <= grid; i++) ctrl[i] = 0u;
+  unsigned int* ctrl_dev = nullptr;
+  FB_CUDA(p, cudaHostGetDevicePointer(reinterpret_cast<void**>(&ctrl_dev), p->ctrl.p, 0));
+  if (!p->ev_async) FB_CUDA(p, cudaEventCreateWithFlags(&p->ev_async, cudaEventDisableTiming));
+  FB_TRY(tc_run(p, d, iters, upd_w, upd_h, ctrl_dev));
+  FB_CUDA(p, cudaEventRecord(p->ev_async, p->stream));
+  const int64_t npass = (upd_w && upd_h) ? iters + 1 : iters;
+  const int64_t total = (int64_t) d.batch * npass;
+  int64_t reported = 0;
+  bool cancelled = false;
+  auto report_up_to = [&](int64_t it) {
+    while (!cancelled && reported < it) {
+      if (!progress(user, ++reported)) { cancelled = true; ctrl[0] = 1u; }
+    }
+  };
+  for (;;) {
+    cudaError_t q = cudaEventQuery(p->ev_async);
+    if (q == cudaSuccess) break;
+    if (q != cudaErrorNotReady) { p->err = std::string("CUDA error: ") + cudaGetErrorString(q); return FB200_ERR_CUDA; }
+    int64_t done = 0;
+    for (int i = 0; i < grid; i++) done += ctrl[1 + i];
+    // iteration `it` is reported once the batch as a whole has done the work of `it` iterations; the last one only at the end
+    report_up_to(std::min<int64_t>(iters - 1, done * iters / std::max<int64_t>(1, total)));
+    std::this_thread::sleep_for(std::chrono::microseconds(100));
+  }
+  report_up_to(iters);
+  return cancelled ? FB200_CANCELLED : FB200_OK;
+}
+
 // The multiplicative-update loop (NMF.hpp:154-181) on the device state in `d`.  Returns FB200_CANCELLED when the
-// progress callback asked to stop; W/H then hold the state after the last completed iteration, as in the reference.
+// progress callback asked to stop.
+//   stride >= 1 (0 -> 1): exact mode.  The engine runs `stride` iterations per launch group, then the callbacks of those
+//     iterations are replayed in order; a cancel leaves W,H as after the LAST iteration of the group (== the reference
+//     at stride 1; cancellation granularity is `stride`).
+//   stride == FB200_PROGRESS_ASYNC: the loop is never interrupted (see run_tc_async; on the SIMT engine: groups of 8).
 int32_t run_nmf_loop(Plan* p, NmfDev& d, int iters, bool upd_w, bool upd_h, fb200_progress_fn progress, void* user,
                      int stride)
 {
@@ -185,42 +246,29 @@ int32_t run_nmf_loop(Plan* p, NmfDev& d, int iters, bool upd_w, bool upd_h, fb20
       if (!progress(user, it)) return FB200_CANCELLED;
     return FB200_OK;
   }
-  // tensor-core engine: whole loop in one persistent launch (no per-iteration host polling, hence no callbacks)
-  if (!progress && p->cfg.backend != FB200_BACKEND_SIMT && tc_eligible(d)) {
-    p->backend_used = FB200_BACKEND_TCGEN05;
-    return tc_run(p, d, iters, upd_w, upd_h);
-  }
-  if (p->cfg.backend == FB200_BACKEND_TCGEN05) {
-    p->err = "FB200_BACKEND_TCGEN05 requested but the shape does not qualify (rank 16, bins = 128k+1 <= 513, frames <= 512, no callback)";
+  const bool use_tc = p->cfg.backend != FB200_BACKEND_SIMT && tc_eligible(d);
+  if (!use_tc && p->cfg.backend == FB200_BACKEND_TCGEN05) {
+    p->err = "FB200_BACKEND_TCGEN05 requested but the shape does not qualify (rank 16, bins = 128k+1 <= 513, frames <= 512)";
     return FB200_ERR_UNSUPPORTED;
   }
-  if (upd_w) FB_TRY(alloc_partials(p, d));
-  if (progress) {
-    // exact per-iteration state so that a cancel leaves W,H as the reference would: no cross-iteration fusion
-    if (stride <= 0) stride = 1;
-    for (int it = 1; it <= iters; it++) {
-      if (upd_w) { simt_launch_tile(p, d, 0, 1, 1); simt_launch_w_finalize(p, d); }
-      if (upd_h) simt_launch_tile(p, d, 1, 0, 1);
-      if (it % stride == 0 || it == iters) {
-        FB_CUDA(p, cudaStreamSynchronize(p->stream));
-        for (int j = it - ((it - 1) % stride); j <= it; j++)
-          if (!progress(user, j)) return FB200_CANCELLED;
-      }
-    }
+  p->backend_used = use_tc ? FB200_BACKEND_TCGEN05 : FB200_BACKEND_SIMT;
+  if (!use_tc && upd_w) FB_TRY(alloc_partials(p, d));
+  // one launch group = n complete iterations: the tensor-core engine runs them in one persistent launch (its state
+  // round-trips exactly through the fp32 W/H arrays), the SIMT engine as 2n+1 fused launches
+  auto run_group = [&](int n) -> int32_t {
+    if (use_tc) return tc_run(p, d, n, upd_w, upd_h);
+    simt_run_iters(p, d, n, upd_w, upd_h);
     return FB200_OK;
-  }
-  if (upd_w && upd_h) {
-    simt_launch_tile(p, d, 0, 1, 1); // W-numerator of iteration 1
-    simt_launch_w_finalize(p, d);
-    for (int it = 1; it < iters; it++) {
-      simt_launch_tile(p, d, 1, 1, 1); // H-update of iteration `it` fused with the W-numerator of `it+1`
-      simt_launch_w_finalize(p, d);
-    }
-    simt_launch_tile(p, d, 1, 0, 1); // H-update of the last iteration
-  } else if (upd_w) {
-    for (int it = 0; it < iters; it++) { simt_launch_tile(p, d, 0, 1, 1); simt_launch_w_finalize(p, d); }
-  } else {
-    for (int it = 0; it < iters; it++) simt_launch_tile(p, d, 1, 0, 1);
+  };
+  if (!progress) return run_group(iters);
+  if (stride == FB200_PROGRESS_ASYNC && use_tc) return run_tc_async(p, d, iters, upd_w, upd_h, progress, user);
+  const int s = stride == FB200_PROGRESS_ASYNC ? 8 : std::max(1, stride);
+  for (int it0 = 0; it0 < iters; it0 += s) {
+    const int n = std::min(s, iters - it0);
+    FB_TRY(run_group(n));
+    FB_CUDA(p, cudaStreamSynchronize(p->stream));
+    for (int j = it0 + 1; j <= it0 + n; j++)
+      if (!progress(user, j)) return FB200_CANCELLED;
   }
   return FB200_OK;
 }
@@ -341,7 +389,8 @@ void fb200_plan_destroy(fb200_plan* p)
   DevBuf* bufs[] = {&p->window, &p->audio, &p->stage, &p->frames, &p->spec, &p->cspec, &p->V, &p->W, &p->H, &p->hden,
                     &p->wnum_part, &p->wden_part, &p->rnd, &p->seeds, &p->scale, &p->out_a, &p->out_b};
   for (auto* b : bufs) b->release();
-  p->pin_a.release(); p->pin_b.release();
+  p->pin_a.release(); p->pin_b.release(); p->ctrl.release();
+  if (p->ev_async) cudaEventDestroy(p->ev_async);
   for (auto& e : p->ev) if (e) cudaEventDestroy(e);
   for (auto& e : p->kev) cudaEventDestroy(e);
   for (auto& e : p->cev) cudaEventDestroy(e);

@@ -86,6 +86,7 @@ struct Plan {
   cudaStream_t copy_stream = nullptr; // host -> device uploads that overlap with kernels on `stream`
   std::vector<cudaEvent_t> cev;       // one event per upload wave (+ one fence)
   cudaEvent_t ev[10]{};
+  cudaEvent_t ev_async = nullptr;     // completion of the persistent launch the asynchronous progress mode polls
   std::string err;
   fb200_stats stats{};
   int64_t launches = 0, launches_nmf = 0;
@@ -103,6 +104,7 @@ struct Plan {
   DevBuf cspec;    // float2 [wave][K][F][B] masked component spectra
   DevBuf V, W, H, hden, wnum_part, wden_part, rnd, seeds, scale, out_a, out_b;
   HostBuf pin_a, pin_b;
+  HostBuf ctrl;    // host-mapped progress / cancel words of the asynchronous progress mode
   std::map<std::pair<int, int64_t>, cufftHandle> fft_plans; // (type, batch) -> handle
 
   bool fail(int code, const std::string& msg) { err = msg; last_code = code; return false; }
@@ -177,6 +179,8 @@ int32_t run_tc_mma_timing(Plan* p, long long* d_out, int reps);
 
 // kernels_nmf_tc.cu ---------------------------------------------------------------------------------------------
 bool tc_eligible(const NmfDev& d);
-int32_t tc_run(Plan* p, const NmfDev& d, int iters, bool upd_w, bool upd_h);
+// ctrl != nullptr: host-mapped control words (ctrl[0] cancel request, ctrl[1 + cta] finished passes), see Ctl in the .cu
+int32_t tc_run(Plan* p, const NmfDev& d, int iters, bool upd_w, bool upd_h, unsigned int* ctrl = nullptr);
+int tc_grid(const Plan* p, const NmfDev& d);
 
 } // namespace fb200

@@ -183,6 +183,29 @@ struct Sched {
   __device__ bool p1(int pass) const { return both ? pass > 0 : upd_h != 0; }
   __device__ bool p2(int pass) const { return both ? pass < iters : upd_w != 0; }
 };
+
+// Asynchronous progress / cancel (fb200_nmf_args.progress_stride == FB200_PROGRESS_ASYNC; NMFClient.hpp:261-274 polls a
+// FluidTask every iteration).  `ctrl` is host-mapped pinned memory: ctrl[0] is written by the host to request a cancel,
+// ctrl[1 + cta] counts the (buffer, pass) units this CTA has finished.  The TMA producer is the role that runs furthest
+// ahead, so it samples the cancel word once per pass (the load is issued one pass early: no PCIe round trip on its
+// critical path) and publishes the first cancelled global pass index in shared memory; every role evaluates the same
+// pure function of (pass, global pass index, published index), so all of them leave the loops at the same point.
+// A cancelled buffer finishes the iteration it is in (fused schedule: W is one update ahead of H between passes, so one
+// H-only pass follows); buffers not yet started keep their initial state.
+enum PassMode { PASS_RUN = 0, PASS_FINAL = 1, PASS_STOP = 2 };
+struct Ctl {
+  volatile uint32_t* cs; // shared: cs[1] = number of passes decided, cs[2] = first cancelled global pass index
+  bool on;
+  __device__ __forceinline__ int mode(const Sched& sc, int pass, uint32_t gp) const
+  {
+    if (!on) return PASS_RUN;
+    while (cs[1] <= gp) {}
+    __threadfence_block();
+    const uint32_t sg = cs[2];
+    if (gp < sg) return PASS_RUN;
+    return (sc.both && pass > 0 && gp == sg) ? PASS_FINAL : PASS_STOP;
+  }
+};
 } // namespace tcn
 
 using namespace tcn;
@@ -198,7 +221,7 @@ using namespace tcn;
 
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_constant__ CUtensorMap tmap2, int iters, int upd_w, int upd_h,
-         long long* dbg)
+         long long* dbg, unsigned int* ctrl)
 {
   extern __shared__ __align__(1024) uint8_t smem[];
   __nv_bfloat16* wop = reinterpret_cast<__nv_bfloat16*>(smem + OFF_WOP);
@@ -230,7 +253,10 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
   sc.both = upd_w && upd_h; sc.upd_w = upd_w; sc.upd_h = upd_h; sc.iters = iters;
   sc.npass = sc.both ? iters + 1 : iters;
 
+  Ctl ctl;
+  ctl.cs = slot; ctl.on = ctrl != nullptr;
   if (tid == 0) {
+    slot[1] = 0u; slot[2] = 0xFFFFFFFFu;
     for (int i = 0; i < NS; i++) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 4); }
     for (int i = 0; i < 2; i++) { mbar_init(&p_full[i], 1); mbar_init(&r_full[i], 4); mbar_init(&b_full[i], 1); mbar_init(&p_free[i], 4); }
     mbar_init(buf_ready, 8);
@@ -251,10 +277,19 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
   if (warp == 0) {
     // =========================================== TMA producer ===========================================
     if (lane == 0) {
-      uint32_t n = 0;
-      for (int buf = blockIdx.x; buf < d.batch; buf += gridDim.x) {
-        for (int pass = 0; pass < sc.npass; pass++) {
-          for_blocks(sc.p1(pass), sc.p2(pass), T, (pass & 1) != 0, [&](int kind, int t) {
+      uint32_t n = 0, gp = 0, cancel_pre = 0;
+      bool stop = false;
+      for (int buf = blockIdx.x; buf < d.batch && !stop; buf += gridDim.x) {
+        for (int pass = 0; pass < sc.npass; pass++, gp++) {
+          if (ctl.on) { // decide this pass with the cancel word sampled one pass ago, publish, sample for the next
+            if (cancel_pre && slot[2] == 0xFFFFFFFFu) slot[2] = gp;
+            __threadfence_block();
+            slot[1] = gp + 1;
+            cancel_pre = *reinterpret_cast<volatile unsigned int*>(ctrl);
+          }
+          const int mode = ctl.mode(sc, pass, gp);
+          if (mode == PASS_STOP) { stop = true; break; }
+          for_blocks(sc.p1(pass), sc.p2(pass) && mode == PASS_RUN, T, (pass & 1) != 0, [&](int kind, int t) {
             if (kind == BLK_P1)
               for (int c = 0; c < C1; c++, n++) {
                 const uint32_t st = n % NS, k = n / NS;
@@ -275,6 +310,7 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
                   for (int w = 0; w < 4; w++) tma_load_3d(dst + w * 8192, &tmap2, 128 * m + 32 * w, 128 * t + 64 * s, buf, &v_full[st]);
                 }
           });
+          if (mode == PASS_FINAL) { gp++; break; }
         }
       }
     }
@@ -322,11 +358,16 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
         DBG_MARK(2, n);
         n++;
       };
-      for (int buf = blockIdx.x; buf < d.batch; buf += gridDim.x) {
+      uint32_t gp = 0;
+      bool stop = false;
+      for (int buf = blockIdx.x; buf < d.batch && !stop; buf += gridDim.x) {
+        if (ctl.mode(sc, 0, gp) == PASS_STOP) break; // cancelled before this buffer started: it keeps its initial state
         mbar_wait(buf_ready, buf_cnt & 1); buf_cnt++; // operands of this buffer are in shared memory
         tc_fence_after();
-        for (int pass = 0; pass < sc.npass; pass++) {
-          const bool p1 = sc.p1(pass), p2 = sc.p2(pass);
+        for (int pass = 0; pass < sc.npass; pass++, gp++) {
+          const int mode = ctl.mode(sc, pass, gp);
+          if (mode == PASS_STOP) { stop = true; break; }
+          const bool p1 = sc.p1(pass), p2 = sc.p2(pass) && mode == PASS_RUN;
           int prep_owed = 0; // tile preps whose completion this warp has not consumed yet (each must be observed
                              // before the next one can complete: see the placement of the waits below)
           for_blocks(p1, p2, T, (pass & 1) != 0, [&](int kind, int t) {
@@ -348,6 +389,7 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
           });
           while (prep_owed) { mbar_wait(prep_ready, prep_cnt & 1); prep_cnt++; prep_owed--; }
           tc_fence_after();
+          if (mode == PASS_FINAL) { gp++; break; }
         }
       }
     }
@@ -395,15 +437,21 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
         DBG_MARK(5, n);
         n++;
       };
-      for (int buf = blockIdx.x; buf < d.batch; buf += gridDim.x)
-        for (int pass = 0; pass < sc.npass; pass++)
-          for_blocks(sc.p1(pass), sc.p2(pass), T, (pass & 1) != 0, [&](int kind, int t) {
+      uint32_t gp = 0;
+      bool stop = false;
+      for (int buf = blockIdx.x; buf < d.batch && !stop; buf += gridDim.x)
+        for (int pass = 0; pass < sc.npass; pass++, gp++) {
+          const int mode = ctl.mode(sc, pass, gp);
+          if (mode == PASS_STOP) { stop = true; break; }
+          for_blocks(sc.p1(pass), sc.p2(pass) && mode == PASS_RUN, T, (pass & 1) != 0, [&](int kind, int t) {
             if (kind == BLK_P1)
               for (int c = 0; c < C1; c++) issue_b(wlo_b + 8 * c * RSTEP, ID_P1B48, ID_P1B16);           // B = W rows of chunk c
             else if (kind == BLK_P2)
               for (int m = 0; m < MT; m++)
                 for (int s = 0; s < 2; s++) issue_b(hlo_b + (16 * t + 8 * s) * RSTEP, ID_P2B48, ID_P2B16); // B = H rows of half s
           });
+          if (mode == PASS_FINAL) { gp++; break; }
+        }
     }
   }
   } else {
@@ -524,8 +572,17 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
         continue;
 #endif
         float r0, r1, l0, l1;
+#ifdef FB200_TC_RCP_PAIR
+        // one MUFU.RCP per PAIR: 1/a = b * (1/(ab)), 1/b = a * (1/(ab)).  a, b >= eps = 2.2e-16, so ab >= 4.9e-32 stays a
+        // normal fp32 number; the quarter-rate XU pipe sees half the work, the FMA pipe (13 % busy) takes two multiplies.
+        const float pa = fmaxf(__uint_as_float(p[2 * j]), kEps), pb = fmaxf(__uint_as_float(p[2 * j + 1]), kEps);
+        const float t = rcp_fast(pa * pb);
+        mul2(r0, r1, v[2 * j], v[2 * j + 1], pb, pa);
+        mul2(r0, r1, r0, r1, t, t);
+#else
         mul2(r0, r1, v[2 * j], v[2 * j + 1], rcp_fast(fmaxf(__uint_as_float(p[2 * j]), kEps)),
              rcp_fast(fmaxf(__uint_as_float(p[2 * j + 1]), kEps)));
+#endif
         ph[j] = cvt2(r0, r1);
         sub2(l0, l1, r0, r1, bf16lo_to_f(ph[j]), bf16hi_to_f(ph[j]));
         pl[j] = cvt2(l0, l1);
@@ -545,7 +602,10 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
     };
     static_assert(RP == 2, "the step epilogue writes a two-part ratio");
 
-    for (int buf = blockIdx.x; buf < d.batch; buf += gridDim.x) {
+    uint32_t gp = 0, units_done = 0;
+    bool stop = false;
+    for (int buf = blockIdx.x; buf < d.batch && !stop; buf += gridDim.x) {
+      if (ctl.mode(sc, 0, gp) == PASS_STOP) break; // cancelled before this buffer started: it keeps its initial state
       // ---------------- buffer prologue: state -> 3-way split operands --------------------------------------------
       const float* gW = d.W + (int64_t) buf * K * Bp;
       const float* gH = d.H + (int64_t) buf * Fp * K;
@@ -581,8 +641,10 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
       epi_bar();
       if (lane == 0) mbar_arrive(buf_ready);
 
-      for (int pass = 0; pass < sc.npass; pass++) {
-        const bool p1 = sc.p1(pass), p2 = sc.p2(pass);
+      for (int pass = 0; pass < sc.npass; pass++, gp++) {
+        const int mode = ctl.mode(sc, pass, gp);
+        if (mode == PASS_STOP) { stop = true; break; }
+        const bool p1 = sc.p1(pass), p2 = sc.p2(pass) && mode == PASS_RUN;
         for_blocks(p1, p2, T, (pass & 1) != 0, [&](int kind, int t) {
           // ---------------- phase 1 steps ------------------------------------------------------------------------
           if (kind == BLK_P1) {
@@ -792,6 +854,8 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
           if (lane == 0) mbar_arrive(w_ready);
           }
         });
+        if (ctl.on && et == 0) *reinterpret_cast<volatile unsigned int*>(ctrl + 1 + blockIdx.x) = ++units_done;
+        if (mode == PASS_FINAL) { gp++; break; }
       }
       // ---------------- buffer epilogue: state back to global ----------------------------------------------------
       epi_bar();
@@ -810,6 +874,7 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
         int f = e >> 4, k = e & 15;
         oH[e] = bf16_bits_to_f(hp[hop_index(2, f, k)]) + bf16_bits_to_f(hp[hop_index(1, f, k)]) + bf16_bits_to_f(hp[hop_index(0, f, k)]);
       }
+      if (et < K) d.hden[(int64_t) buf * K + et] = hden[et]; // sum_b W of the W just written: a later launch resumes from it
       epi_bar(); // operands are overwritten by the next buffer's prologue
     }
   }
@@ -827,7 +892,9 @@ bool tc_eligible(const NmfDev& d)
          d.Bp == d.B + 3 && !d.clamp_v && !d.shared_w;
 }
 
-int32_t tc_run(Plan* p, const NmfDev& d, int iters, bool upd_w, bool upd_h)
+int tc_grid(const Plan* p, const NmfDev& d) { return std::min(d.batch, p->sm_count); }
+
+int32_t tc_run(Plan* p, const NmfDev& d, int iters, bool upd_w, bool upd_h, unsigned int* ctrl)
 {
   alignas(64) CUtensorMap tmap1, tmap2;
   FB_TRY(make_v_tensor_map(p, &tmap1, d.V, d.Bp, d.Fp, d.batch, 128));
@@ -836,8 +903,8 @@ int32_t tc_run(Plan* p, const NmfDev& d, int iters, bool upd_w, bool upd_h)
     FB_CUDA(p, cudaFuncSetAttribute(k_nmf_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     p->attr_mask |= 0x10000u;
   }
-  int grid = std::min(d.batch, p->sm_count);
-  while (p->kev.size() < p->kev_used + 2) { cudaEvent_t e; cudaEventCreate(&e); p->kev.push_back(e); }
+  const int grid = tc_grid(p, d);
+  while (p->kev.size() < p->kev_used + 2) { cudaEvent_t e; FB_CUDA(p, cudaEventCreate(&e)); p->kev.push_back(e); }
   cudaEventRecord(p->kev[p->kev_used++], p->stream);
   long long* dbg = nullptr;
 #ifdef FB200_TC_DEBUG_TIMELINE
@@ -847,7 +914,7 @@ int32_t tc_run(Plan* p, const NmfDev& d, int iters, bool upd_w, bool upd_h)
     dbg = p->out_b.as<long long>();
   }
 #endif
-  k_nmf_tc<<<grid, NTHREADS, SMEM_BYTES, p->stream>>>(d, tmap1, tmap2, iters, upd_w ? 1 : 0, upd_h ? 1 : 0, dbg);
+  k_nmf_tc<<<grid, NTHREADS, SMEM_BYTES, p->stream>>>(d, tmap1, tmap2, iters, upd_w ? 1 : 0, upd_h ? 1 : 0, dbg, ctrl);
   if (dbg) {
     std::vector<long long> h(32 * 16);
     FB_CUDA(p, cudaMemcpyAsync(h.data(), dbg, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost, p->stream));

@@ -25,6 +25,7 @@ F32, F64 = 0, 1
 HOST, DEVICE = 0, 1
 OK, WARN_NO_WORK, CANCELLED = 0, 1, 2
 BACKEND_AUTO, BACKEND_SIMT, BACKEND_TCGEN05 = 0, 1, 2
+PROGRESS_ASYNC = -1  # fb200_progress_fn: never interrupt the device loop, poll its pass counters
 
 PROGRESS_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int64)
 

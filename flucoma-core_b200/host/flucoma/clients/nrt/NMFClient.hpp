@@ -168,7 +168,10 @@ public:
         return x->c->task()->processUpdate(static_cast<double>(it), x->total) ? 1 : 0; // :261-267
       };
       a.progress_user = &ctx;
-      a.progress_stride = 1;
+      // The reference polls the task once per iteration and throws every output of a cancelled job away (:273-274), so
+      // the update loop need not stop at an exact iteration: the persistent device loop keeps running, the callback is
+      // fed from its pass counters and a cancel is honoured at the next pass boundary (fb200_progress_fn).
+      a.progress_stride = FB200_PROGRESS_ASYNC;
     }
     int32_t st;
     try
@@ -176,6 +179,7 @@ public:
       b200::Plan plan(win, fftSize, hop, rank);
       st = b200::B200Backend::get().bufnmf(plan.get(), &a);
       if (st < 0) return {Result::Status::kError, b200::B200Backend::get().last_error(plan.get())};
+      b200::B200Backend::get().get_stats(plan.get(), &mStats);
     }
     catch (const std::exception& e)
     {
@@ -208,8 +212,12 @@ public:
     return {Result::Status::kOk, ""};
   }
 
+  // instrumentation of the last process() call (engine used, stage times): additive, not in the reference
+  const fb200_stats& lastStats() const { return mStats; }
+
 private:
   BufNMFParams* mParams;
+  fb200_stats   mStats{};
 };
 } // namespace bufnmf
 } // namespace client

@@ -73,8 +73,20 @@ typedef struct fb200_config {
 } fb200_config;
 
 /* progress callback: NMF::addProgressCallback (algorithms/public/NMF.hpp:31,136-139,175-176).
- * Called with iteration 1..n (host thread, between device launches); return 0 to cancel. */
+ * Called on the calling thread with iteration 1..n, each exactly once and in order; return 0 to cancel.
+ * `progress_stride` of the argument structs selects how the update loop is polled:
+ *   s >= 1 (0 means 1, the reference's cadence): exact mode.  The device runs s iterations, then the callbacks of those
+ *       iterations are replayed; on cancel W/H hold the state after the last iteration of that group -- at s = 1 exactly
+ *       the reference's NMF.hpp:175-176.  Cancellation granularity is s iterations.  Both engines support it (the
+ *       tensor-core engine runs one persistent launch per group; its state round-trips exactly through fp32 W/H).
+ *   FB200_PROGRESS_ASYNC: the loop is never interrupted.  The calling thread polls device-written pass counters while the
+ *       persistent kernel runs and reports iteration i once the batch as a whole has done the work of i iterations (the
+ *       reference's FluidTask progress is channel-major in the same way, NMFClient.hpp:233-267, FluidTask.hpp:22-39).
+ *       Returning 0 raises a device-visible cancel word: every buffer in flight finishes the iteration it is in, buffers
+ *       not yet started keep their initial state, the call returns FB200_CANCELLED.  This is the mode for BufNMF, which
+ *       discards all outputs of a cancelled job (NMFClient.hpp:273-274). */
 typedef int (*fb200_progress_fn)(void* user, int64_t iteration);
+#define FB200_PROGRESS_ASYNC (-1)
 
 /* ---- plan management ------------------------------------------------------------------------------------- */
 FB200_API uint32_t fb200_abi_version(void);
@@ -117,7 +129,7 @@ typedef struct fb200_nmf_args {
   void* V1;                     /* out [batch][frames][bins] = W*H (may be NULL); untouched copy of X if cancelled */
   fb200_progress_fn progress;   /* optional */
   void* progress_user;
-  int32_t progress_stride;      /* iterations per host poll when progress != NULL (<=0 -> 1, the reference's cadence) */
+  int32_t progress_stride;      /* see fb200_progress_fn: >= 1 exact (0 -> 1), FB200_PROGRESS_ASYNC */
   int32_t reserved;
 } fb200_nmf_args;
 FB200_API int32_t fb200_nmf_process(fb200_plan* plan, const fb200_nmf_args* args);

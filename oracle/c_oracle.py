@@ -242,11 +242,11 @@ def bufnmf_batch(audio, win, fft, hop, rank, iters, seeds, resynth=False, faithf
     return bases, acts, rs
 
 
-def nmfmatch_frames(mags, W, n_iter, seed, threads=0):
+def nmfmatch_frames(mags, W, n_iter, seed, threads=0, lib_path=None):
     m = _c64(mags); W = _c64(W)
     K, B = W.shape
     acts = np.empty((m.shape[0], K))
-    lib().fo_nmfmatch_frames(_d(m), m.shape[0], _d(W), B, K, n_iter, seed, _d(acts), threads)
+    lib(lib_path).fo_nmfmatch_frames(_d(m), m.shape[0], _d(W), B, K, n_iter, seed, _d(acts), threads)
     return acts
 
 

@@ -165,6 +165,40 @@ int main(int argc, char** argv)
     bufnmf::NMFClient c3(p, ctx2);
     CHECK(c3.process<float>(ctx2).status() == Result::Status::kCancelled);
   }
+  { // BufNMF at a shape the tcgen05 engine takes (fft 256, rank 16, >= 128 frames) WITH a FluidTask: the reference
+    // always installs a progress callback (NMFClient.hpp:261-267); it must not push the job off the tensor-core engine
+    using namespace fluid::client;
+    const index n = 128 * 64, chans = 3, rank = 16;
+    auto        src = std::make_shared<MemoryBufferAdaptor>(chans, n, 44100.0);
+    for (index c = 0; c < chans; ++c)
+      for (index i = 0; i < n; ++i)
+      {
+        double t = double(i) / 44100.0, s = 0;
+        for (int h = 1; h <= 5; ++h) s += ((i / (700 * h)) % 2 ? 0.2 : 0.02) * std::sin(2 * M_PI * (300.0 * h + 50 * c) * t);
+        src->data()(i, c) = float(s);
+      }
+    auto bases = std::make_shared<MemoryBufferAdaptor>(1, 1, 44100.0);
+    auto acts = std::make_shared<MemoryBufferAdaptor>(1, 1, 44100.0);
+    bufnmf::BufNMFParams p;
+    p.source = src; p.bases = bases; p.activations = acts;
+    p.components = rank; p.iterations = 40; p.seed = 3; p.fftSettings = FFTParams(256, 64, -1);
+    FluidTask         task;
+    FluidContext      ctx(task);
+    bufnmf::NMFClient client(p, ctx);
+    Result            r = client.process<float>(ctx);
+    CHECK(r.ok());
+    CHECK(client.lastStats().backend_used == FB200_BACKEND_TCGEN05);
+    CHECK(std::abs(task.progress() - 1.0) < 1e-9); // every iteration was reported (FluidTask.hpp:27-33)
+    // the same job without a task gives bit-identical buffers: the callback path runs the same single launch
+    auto bases2 = std::make_shared<MemoryBufferAdaptor>(1, 1, 44100.0);
+    auto acts2 = std::make_shared<MemoryBufferAdaptor>(1, 1, 44100.0);
+    bufnmf::BufNMFParams q = p;
+    q.bases = bases2; q.activations = acts2;
+    FluidContext      ctxn;
+    bufnmf::NMFClient c2(q, ctxn);
+    CHECK(c2.process<float>(ctxn).ok());
+    CHECK(rangeEquals(bases->data(), bases2->data()) && rangeEquals(acts->data(), acts2->data()));
+  }
   std::printf("host shims ok\n");
   return 0;
 }

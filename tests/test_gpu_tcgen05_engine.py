@@ -91,3 +91,72 @@ def test_tc_engine_identical_buffers_stay_identical_under_stress(fb, iters, uw, 
                 ref = (W[0].clone(), H[0].clone())
                 assert bool(torch.isfinite(ref[0]).all()) and bool(torch.isfinite(ref[1]).all())
             assert bool((W == ref[0]).all()) and bool((H == ref[1]).all())
+
+
+# ---------------------------------------------------------------------------------------------- progress / cancel
+def test_tc_engine_exact_progress_and_cancel(fb, oracle):
+    """A progress callback no longer pushes the call off the tensor-core engine (the reference ALWAYS installs one,
+    NMFClient.hpp:261-267).  Exact mode at stride 1: a cancel at iteration 7 leaves W,H as after 7 reference iterations
+    and V1 = X (NMF.hpp:175-176); stride 5: every iteration is reported, in order, and the result matches."""
+    rng = np.random.default_rng(5)
+    X = lowrank(rng, 2, 256, 257)
+    seen = []
+    with fb.Plan(win=64, backend=fb.BACKEND_TCGEN05) as plan:
+        W, H, V, st = plan.nmf_process(X, 16, 20, True, True, seeds=[1, 2], progress=lambda it: seen.append(it) or it < 7)
+        assert plan.stats()["backend_used"] == fb.BACKEND_TCGEN05
+        assert st == fb.CANCELLED and seen == list(range(1, 8)) and np.array_equal(V, X)
+        seen5 = []
+        W5, H5, V5, st5 = plan.nmf_process(X, 16, 20, True, True, seeds=[1, 2], progress=lambda it: seen5.append(it) or True,
+                                           progress_stride=5)
+        Wn, Hn, Vn, _ = plan.nmf_process(X, 16, 20, True, True, seeds=[1, 2])
+    for b in range(2):
+        Wo, Ho, _, _ = oracle.nmf_process(X[b], 16, 7, True, True, 1 + b)
+        assert rel(W[b], Wo) < TOL and rel(H[b], Ho) < TOL
+    assert st5 == 0 and seen5 == list(range(1, 21))
+    assert rel(W5, Wn) < 1e-5 and rel(H5, Hn) < 1e-5 and rel(V5, Vn) < 1e-5
+
+
+@pytest.mark.parametrize("uw,uh", [(True, True), (False, True), (True, False)])
+def test_tc_engine_async_progress(fb, uw, uh):
+    """FB200_PROGRESS_ASYNC: one uninterrupted persistent launch; iterations 1..n are reported exactly once, in order,
+    and the outputs are bit-identical to the call without a callback."""
+    rng = np.random.default_rng(6)
+    X = lowrank(rng, 200, 256, 257).astype(np.float32)
+    seeds = np.arange(200)
+    seen = []
+    with fb.Plan(win=64, backend=fb.BACKEND_TCGEN05) as plan:
+        Wa, Ha, _, st = plan.nmf_process(X, 16, 30, uw, uh, seeds=seeds, want_v=False,
+                                         progress=lambda it: seen.append(it) or True, progress_stride=fb.PROGRESS_ASYNC)
+        assert plan.stats()["backend_used"] == fb.BACKEND_TCGEN05 and plan.stats()["update_kernel_launches"] == 1
+        Wn, Hn, _, _ = plan.nmf_process(X, 16, 30, uw, uh, seeds=seeds, want_v=False)
+    assert st == 0 and seen == list(range(1, 31))
+    assert np.array_equal(Wa, Wn) and np.array_equal(Ha, Hn)
+
+
+def test_tc_engine_async_cancel_finishes_the_iteration_in_flight(fb):
+    """Cancel in async mode: the call returns CANCELLED, every buffer holds the state after SOME completed iteration
+    (W and H of the same iteration: the fused schedule runs one H-only pass after the cancel), buffers not yet started
+    keep their initial state.  All buffers are copies of one problem, so a table of the uncancelled results after
+    j = 0..n iterations must contain every buffer of the cancelled call, bit for bit."""
+    torch = pytest.importorskip("torch")
+    rng = np.random.default_rng(8)
+    X1 = lowrank(rng, 1, 384, 257).astype(np.float32)
+    copies, iters = 5 * 148, 24
+    X = torch.from_numpy(X1).cuda().expand(copies, -1, -1).contiguous()
+    seeds = np.full(copies, 3, dtype=np.int64)
+    with fb.Plan(win=64, backend=fb.BACKEND_TCGEN05) as plan:
+        table = []
+        for j in range(iters + 1):
+            Wj, Hj, _, _ = plan.nmf_process(X[:1], 16, j, True, True, seeds=seeds[:1], want_v=False)
+            table.append((Wj[0].clone(), Hj[0].clone()))
+        calls = []
+        W, H, V, st = plan.nmf_process(X, 16, iters, True, True, seeds=seeds, want_v=True,
+                                       progress=lambda it: calls.append(it) or it < 5, progress_stride=fb.PROGRESS_ASYNC)
+    assert st == fb.CANCELLED and calls == [1, 2, 3, 4, 5]
+    assert bool((V == X).all())                      # NMF.hpp:175-176
+    at = []
+    for b in range(copies):
+        hit = [j for j, (Wj, Hj) in enumerate(table) if bool((W[b] == Wj).all()) and bool((H[b] == Hj).all())]
+        assert hit, f"buffer {b} is not at any completed iteration"
+        at.append(hit[0])
+    assert min(at) < iters, "the cancel arrived after everything had finished: nothing was tested"

@@ -1,6 +1,6 @@
 #!/bin/bash
 # Developer aid: link a variant of libflucoma_b200.so whose tcgen05 engine comes from another source file / extra defines.
-# usage: scratch/build_variant.sh <out.so> <kernels_nmf_tc source> [extra nvcc flags...]
+# usage: tools/build_variant.sh <out.so> <kernels_nmf_tc source> [extra nvcc flags...]
 set -e
 ROOT=$(cd "$(dirname "$0")/.." && pwd)
 OUT=$1; SRC=$2; shift 2
