@@ -18,6 +18,16 @@ static thread_local std::string g_create_error;
 
 namespace {
 
+// FB200_DEVICE arrays are used in place on the plan's own stream, which is not ordered behind the streams the caller
+// produced them on: wait for the device to go idle first (a few microseconds when it already is).  Outputs are complete
+// on return, so the caller needs no further synchronisation.
+int32_t enter(Plan* p, int mem)
+{
+  FB_CUDA(p, cudaSetDevice(p->cfg.device));
+  if (mem == FB200_DEVICE) FB_CUDA(p, cudaDeviceSynchronize());
+  return FB200_OK;
+}
+
 int64_t next_pow2_i64(int64_t x)
 { // clients/common/ParameterTypes.hpp:323-335 (up = true)
   if (x <= 0) return 0;
@@ -29,17 +39,34 @@ int64_t next_pow2_i64(int64_t x)
 
 size_t dsize(int dtype) { return dtype == FB200_F64 ? 8 : 4; }
 
+// cuFFT plans are cached per (type, batch); the cache is a small LRU so that a long-lived plan fed buffers of many
+// different lengths does not accumulate handles (each owns device workspace)
 int32_t get_fft_plan(Plan* p, cufftType type, int64_t batch, cufftHandle* out)
 {
+  constexpr size_t kMaxPlans = 8;
   auto key = std::make_pair((int) type, batch);
   auto it = p->fft_plans.find(key);
-  if (it != p->fft_plans.end()) { *out = it->second; return FB200_OK; }
+  if (it != p->fft_plans.end()) {
+    p->fft_lru[key] = ++p->fft_tick;
+    *out = it->second;
+    return FB200_OK;
+  }
   if (batch > 0x7fffffffLL) { p->err = "cuFFT batch too large"; return FB200_ERR_INVALID; }
+  if (p->fft_plans.size() >= kMaxPlans) {
+    auto victim = p->fft_lru.begin();
+    for (auto j = p->fft_lru.begin(); j != p->fft_lru.end(); ++j)
+      if (j->second < victim->second) victim = j;
+    FB_CUDA(p, cudaStreamSynchronize(p->stream)); // the evicted plan may still be executing
+    cufftDestroy(p->fft_plans[victim->first]);
+    p->fft_plans.erase(victim->first);
+    p->fft_lru.erase(victim);
+  }
   cufftHandle h;
   int n[1] = {p->fft};
   FB_CUFFT(p, cufftPlanMany(&h, 1, n, nullptr, 1, 0, nullptr, 1, 0, type, (int) batch));
   FB_CUFFT(p, cufftSetStream(h, p->stream));
   p->fft_plans[key] = h;
+  p->fft_lru[key] = ++p->fft_tick;
   *out = h;
   return FB200_OK;
 }
@@ -160,19 +187,62 @@ int32_t alloc_partials(Plan* p, NmfDev& d)
   return FB200_OK;
 }
 
-// seeds (host) -> device; negative seeds are replaced by std::random_device draws (EigenRandom.hpp:80)
-int32_t upload_seeds(Plan* p, const int64_t* seeds, int64_t batch)
+// seeds (host) -> device, two per buffer: [0, batch) seed the W draws, [batch, 2 batch) the H draws.  For seed >= 0 both
+// are the seed itself (the reference restarts the same stream for W and H, NMF.hpp:104-105,116-117); a negative seed
+// means std::random_device, and the reference then builds two generators with independent draws (EigenRandom.hpp:80) --
+// so do we.  Unseeded runs are therefore statistically, not bitwise, equivalent to the reference.
+int32_t upload_seeds(Plan* p, const int64_t* seeds, int64_t batch, bool* any_random)
 {
-  FB_CUDA(p, p->seeds.ensure(sizeof(int64_t) * (size_t) batch));
-  std::vector<int64_t> s((size_t) batch);
+  FB_CUDA(p, p->seeds.ensure(sizeof(int64_t) * 2 * (size_t) batch));
+  FB_CUDA(p, p->pin_a.ensure(sizeof(int64_t) * 2 * (size_t) batch));
+  int64_t* s = reinterpret_cast<int64_t*>(p->pin_a.p);
   std::random_device rd;
+  bool neg = false;
+  // pin_a may still feed the previous call's copy only if that call failed mid-way; every successful call ends synchronised
   for (int64_t i = 0; i < batch; i++) {
     int64_t v = seeds ? seeds[i] : -1;
-    if (v < 0) v = (int64_t) rd();
-    s[(size_t) i] = v;
+    if (v < 0) { neg = true; s[i] = (int64_t) rd(); s[batch + i] = (int64_t) rd(); }
+    else { s[i] = v; s[batch + i] = v; }
   }
-  FB_CUDA(p, cudaMemcpyAsync(p->seeds.p, s.data(), sizeof(int64_t) * (size_t) batch, cudaMemcpyHostToDevice, p->stream));
-  FB_CUDA(p, cudaStreamSynchronize(p->stream)); // `s` dies at scope exit
+  FB_CUDA(p, cudaMemcpyAsync(p->seeds.p, s, sizeof(int64_t) * 2 * (size_t) batch, cudaMemcpyHostToDevice, p->stream));
+  if (any_random) *any_random = neg;
+  return FB200_OK;
+}
+
+// uniform draws for the random initialisation: U_w (and U_h when the two streams differ) in p->rnd
+int32_t draw_uniforms(Plan* p, int64_t batch, int64_t u_stride, bool any_random, const float** U_w, const float** U_h)
+{
+  FB_CUDA(p, p->rnd.ensure(sizeof(float) * (size_t) (batch * u_stride) * (any_random ? 2 : 1)));
+  launch_mt_uniform(p, p->seeds.as<int64_t>(), batch, u_stride, p->rnd.as<float>());
+  *U_w = p->rnd.as<float>();
+  *U_h = *U_w;
+  if (any_random) {
+    launch_mt_uniform(p, p->seeds.as<int64_t>() + batch, batch, u_stride, p->rnd.as<float>() + batch * u_stride);
+    *U_h = p->rnd.as<float>() + batch * u_stride;
+  }
+  return FB200_OK;
+}
+
+// h0 of a frame stream (NMF.hpp:55): seed >= 0 -> the same K draws for every frame (*per_frame = 0); seed < 0 -> the
+// reference redraws from random_device for every processFrame call: here every frame gets its own K draws out of
+// ceil(frames / 4096) randomly seeded streams (*per_frame = 1) -- statistically equivalent
+int32_t draw_frame_h0(Plan* p, int64_t seed, int64_t frames, int64_t K, const float** U, int* per_frame)
+{
+  bool neg = false;
+  if (seed >= 0) {
+    FB_TRY(upload_seeds(p, &seed, 1, &neg));
+    FB_CUDA(p, p->rnd.ensure(sizeof(float) * (size_t) K));
+    launch_mt_uniform(p, p->seeds.as<int64_t>(), 1, K, p->rnd.as<float>());
+    *per_frame = 0;
+  } else {
+    const int64_t ns = (frames + 4095) / 4096;
+    std::vector<int64_t> none((size_t) ns, -1);
+    FB_TRY(upload_seeds(p, none.data(), ns, &neg));
+    FB_CUDA(p, p->rnd.ensure(sizeof(float) * (size_t) (ns * 4096 * K)));
+    launch_mt_uniform(p, p->seeds.as<int64_t>(), ns, 4096 * K, p->rnd.as<float>());
+    *per_frame = 1;
+  }
+  *U = p->rnd.as<float>();
   return FB200_OK;
 }
 
@@ -194,40 +264,52 @@ void simt_run_iters(Plan* p, NmfDev& d, int n, bool upd_w, bool upd_h)
   }
 }
 
-// Asynchronous progress on the persistent tensor-core engine: ONE launch runs all iterations; the calling thread polls
-// the per-CTA pass counters in host-mapped memory, reports iterations 1..n (each exactly once, in order) as the batch
-// advances, and raises the cancel word when a callback returns 0.  See `Ctl` in kernels_nmf_tc.cu.
+// Asynchronous progress on the persistent tensor-core engine: ONE launch runs all iterations.  The control words live
+// in DEVICE memory (a first version kept them in host-mapped memory: 148 CTAs sampling a sysmem word once per pass were
+// serialised on the PCIe read path and doubled the step time); the calling thread reads the per-CTA pass counters with
+// small copies on the plan's copy stream while the kernel runs, reports iterations 1..n (each exactly once, in order) as
+// the batch advances, and raises the cancel word with another small copy when a callback returns 0.  See `Ctl`.
 int32_t run_tc_async(Plan* p, NmfDev& d, int iters, bool upd_w, bool upd_h, fb200_progress_fn progress, void* user)
 {
   const int grid = tc_grid(p, d);
-  if (!p->ctrl.p) FB_CUDA(p, cudaHostAlloc(&p->ctrl.p, sizeof(unsigned int) * 1025, cudaHostAllocMapped));
-  volatile unsigned int* ctrl = reinterpret_cast<volatile unsigned int*>(p->ctrl.p);
-  for (int i = 0; i <= grid; i++) ctrl[i] = 0u;
-  unsigned int* ctrl_dev = nullptr;
-  FB_CUDA(p, cudaHostGetDevicePointer(reinterpret_cast<void**>(&ctrl_dev), p->ctrl.p, 0));
+  FB_CUDA(p, p->ctrl_dev.ensure(sizeof(unsigned int) * 1025));
+  FB_CUDA(p, p->ctrl.ensure(sizeof(unsigned int) * 1026));
+  unsigned int* host = reinterpret_cast<unsigned int*>(p->ctrl.p); // [0, 1024): counters read back; [1024]: the word "1"
+  unsigned int* dev = p->ctrl_dev.as<unsigned int>();
+  FB_CUDA(p, cudaMemsetAsync(dev, 0, sizeof(unsigned int) * 1025, p->stream));
   if (!p->ev_async) FB_CUDA(p, cudaEventCreateWithFlags(&p->ev_async, cudaEventDisableTiming));
-  FB_TRY(tc_run(p, d, iters, upd_w, upd_h, ctrl_dev));
+  FB_TRY(tc_run(p, d, iters, upd_w, upd_h, dev));
   FB_CUDA(p, cudaEventRecord(p->ev_async, p->stream));
   const int64_t npass = (upd_w && upd_h) ? iters + 1 : iters;
   const int64_t total = (int64_t) d.batch * npass;
   int64_t reported = 0;
   bool cancelled = false;
-  auto report_up_to = [&](int64_t it) {
+  auto report_up_to = [&](int64_t it) -> int32_t {
     while (!cancelled && reported < it) {
-      if (!progress(user, ++reported)) { cancelled = true; ctrl[0] = 1u; }
+      if (!progress(user, ++reported)) {
+        cancelled = true;
+        host[1024] = 1u;
+        FB_CUDA(p, cudaMemcpyAsync(dev, host + 1024, sizeof(unsigned int), cudaMemcpyHostToDevice, p->copy_stream));
+      }
     }
+    return FB200_OK;
   };
   for (;;) {
     cudaError_t q = cudaEventQuery(p->ev_async);
     if (q == cudaSuccess) break;
     if (q != cudaErrorNotReady) { p->err = std::string("CUDA error: ") + cudaGetErrorString(q); return FB200_ERR_CUDA; }
-    int64_t done = 0;
-    for (int i = 0; i < grid; i++) done += ctrl[1 + i];
-    // iteration `it` is reported once the batch as a whole has done the work of `it` iterations; the last one only at the end
-    report_up_to(std::min<int64_t>(iters - 1, done * iters / std::max<int64_t>(1, total)));
-    std::this_thread::sleep_for(std::chrono::microseconds(100));
+    if (!cancelled) {
+      FB_CUDA(p, cudaMemcpyAsync(host, dev + 1, sizeof(unsigned int) * (size_t) grid, cudaMemcpyDeviceToHost, p->copy_stream));
+      FB_CUDA(p, cudaStreamSynchronize(p->copy_stream));
+      int64_t done = 0;
+      for (int i = 0; i < grid; i++) done += host[i];
+      // iteration `it` is reported once the batch as a whole has done the work of `it` iterations; the last one at the end
+      FB_TRY(report_up_to(std::min<int64_t>(iters - 1, done * iters / std::max<int64_t>(1, total))));
+    }
+    std::this_thread::sleep_for(std::chrono::microseconds(250));
   }
-  report_up_to(iters);
+  FB_CUDA(p, cudaStreamSynchronize(p->copy_stream));
+  FB_TRY(report_up_to(iters));
   return cancelled ? FB200_CANCELLED : FB200_OK;
 }
 
@@ -246,17 +328,25 @@ int32_t run_nmf_loop(Plan* p, NmfDev& d, int iters, bool upd_w, bool upd_h, fb20
       if (!progress(user, it)) return FB200_CANCELLED;
     return FB200_OK;
   }
-  const bool use_tc = p->cfg.backend != FB200_BACKEND_SIMT && tc_eligible(d);
-  if (!use_tc && p->cfg.backend == FB200_BACKEND_TCGEN05) {
-    p->err = "FB200_BACKEND_TCGEN05 requested but the shape does not qualify (rank 16, bins = 128k+1 <= 513, frames <= 512)";
+  // engine choice: the resident tensor-core engine for its shapes (rank 16, <= 513 bins, <= 512 frames, W updated or not),
+  // the streamed one for everything else it covers (rank 9..32, any bins = 128 m + 1, any frame count, fixed-W frame
+  // streams) when there are enough independent work units to fill the SMs, the SIMT engine for the rest
+  const int be = p->cfg.backend;
+  const bool tc1 = (be == FB200_BACKEND_AUTO || be == FB200_BACKEND_TCGEN05) && tc_eligible(d);
+  const int64_t units = upd_w ? d.batch : (int64_t) d.batch * ((d.Fp / 128 + 1) / 2);
+  const bool tc2 = !tc1 && be != FB200_BACKEND_SIMT && tcs_eligible(d) && (be != FB200_BACKEND_AUTO || units >= 32);
+  if (!tc1 && !tc2 && (be == FB200_BACKEND_TCGEN05 || be == FB200_BACKEND_TCGEN05_STREAMED)) {
+    p->err = "tensor-core backend requested but the shape does not qualify (rank 9..32, bins = 128 m + 1, frames padded to 128)";
     return FB200_ERR_UNSUPPORTED;
   }
-  p->backend_used = use_tc ? FB200_BACKEND_TCGEN05 : FB200_BACKEND_SIMT;
-  if (!use_tc && upd_w) FB_TRY(alloc_partials(p, d));
-  // one launch group = n complete iterations: the tensor-core engine runs them in one persistent launch (its state
+  const bool use_tc = tc1;
+  p->backend_used = tc1 ? FB200_BACKEND_TCGEN05 : (tc2 ? FB200_BACKEND_TCGEN05_STREAMED : FB200_BACKEND_SIMT);
+  if (!tc1 && !tc2 && upd_w) FB_TRY(alloc_partials(p, d));
+  // one launch group = n complete iterations: the tensor-core engines run them in one persistent launch (their state
   // round-trips exactly through the fp32 W/H arrays), the SIMT engine as 2n+1 fused launches
   auto run_group = [&](int n) -> int32_t {
-    if (use_tc) return tc_run(p, d, n, upd_w, upd_h);
+    if (tc1) return tc_run(p, d, n, upd_w, upd_h);
+    if (tc2) return tcs_run(p, d, n, upd_w, upd_h);
     simt_run_iters(p, d, n, upd_w, upd_h);
     return FB200_OK;
   };
@@ -270,6 +360,24 @@ int32_t run_nmf_loop(Plan* p, NmfDev& d, int iters, bool upd_w, bool upd_h, fb20
     for (int j = it0 + 1; j <= it0 + n; j++)
       if (!progress(user, j)) return FB200_CANCELLED;
   }
+  return FB200_OK;
+}
+
+// activation-only solve with a fixed dictionary (NMF.hpp:72-83): the streamed tensor-core engine when the shape allows,
+// else one SIMT launch that runs all iterations per frame tile
+int32_t run_h_only(Plan* p, NmfDev& d, int iters)
+{
+  const int be = p->cfg.backend;
+  const int64_t units = (int64_t) d.batch * ((d.Fp / 128 + 1) / 2);
+  if (be != FB200_BACKEND_SIMT && tcs_eligible(d) && (be != FB200_BACKEND_AUTO || units >= 32)) {
+    p->backend_used = FB200_BACKEND_TCGEN05_STREAMED;
+    return tcs_run(p, d, iters, false, true);
+  }
+  if (be == FB200_BACKEND_TCGEN05 || be == FB200_BACKEND_TCGEN05_STREAMED) {
+    p->err = "tensor-core backend requested but the shape does not qualify (rank 9..32, bins = 128 m + 1)";
+    return FB200_ERR_UNSUPPORTED;
+  }
+  simt_launch_tile(p, d, 1, 0, iters);
   return FB200_OK;
 }
 
@@ -387,7 +495,7 @@ void fb200_plan_destroy(fb200_plan* p)
   if (p->stream) cudaStreamSynchronize(p->stream);
   for (auto& kv : p->fft_plans) cufftDestroy(kv.second);
   DevBuf* bufs[] = {&p->window, &p->audio, &p->stage, &p->frames, &p->spec, &p->cspec, &p->V, &p->W, &p->H, &p->hden,
-                    &p->wnum_part, &p->wden_part, &p->rnd, &p->seeds, &p->scale, &p->out_a, &p->out_b};
+                    &p->wnum_part, &p->wden_part, &p->rnd, &p->seeds, &p->scale, &p->out_a, &p->out_b, &p->ctrl_dev, &p->wop_buf, &p->hop_buf};
   for (auto* b : bufs) b->release();
   p->pin_a.release(); p->pin_b.release(); p->ctrl.release();
   if (p->ev_async) cudaEventDestroy(p->ev_async);
@@ -414,7 +522,7 @@ int32_t fb200_stft(fb200_plan* p, const void* audio, int64_t batch, int64_t n, v
 {
   if (!p) return FB200_ERR_INVALID;
   if (!audio || batch <= 0 || n < 0 || (!spectrum && !magnitude)) { p->err = "fb200_stft: bad arguments"; return FB200_ERR_INVALID; }
-  FB_CUDA(p, cudaSetDevice(p->cfg.device));
+  FB_TRY(enter(p, mem));
   StageTimer t(p);
   t.mark(0);
   const int B = p->bins;
@@ -459,7 +567,7 @@ int32_t fb200_istft(fb200_plan* p, const void* spectrum, int64_t batch, int64_t 
   if (!p) return FB200_ERR_INVALID;
   if (!spectrum || !audio || batch <= 0 || F <= 0 || n <= 0) { p->err = "fb200_istft: bad arguments"; return FB200_ERR_INVALID; }
   if (p->win / 2 + n > p->win + (F - 1) * p->hop + p->win + p->hop) { p->err = "fb200_istft: n_samples exceeds the overlap-add length"; return FB200_ERR_INVALID; }
-  FB_CUDA(p, cudaSetDevice(p->cfg.device));
+  FB_TRY(enter(p, mem));
   StageTimer t(p);
   t.mark(0);
   const int B = p->bins;
@@ -491,7 +599,7 @@ int32_t fb200_nmf_process(fb200_plan* p, const fb200_nmf_args* a)
     p->err = "fb200_nmf_process: bad arguments";
     return FB200_ERR_INVALID;
   }
-  FB_CUDA(p, cudaSetDevice(p->cfg.device));
+  FB_TRY(enter(p, a->mem));
   StageTimer t(p);
   t.mark(0);
   NmfDev d{};
@@ -505,7 +613,7 @@ int32_t fb200_nmf_process(fb200_plan* p, const fb200_nmf_args* a)
   FB_CUDA(p, cudaMemsetAsync(d.V, 0, sizeof(float) * (size_t) d.batch * d.Fp * d.Bp, p->stream));
   launch_copy3d(p, d_x, a->dtype, F * B, B, d.V, FB200_F32, (int64_t) d.Fp * d.Bp, d.Bp, a->batch, F, B, nullptr, 0);
   // seeds / W0 / H0
-  const float* dW0 = nullptr; const float* dH0 = nullptr; const float* U = nullptr;
+  const float* dW0 = nullptr; const float* dH0 = nullptr; const float* U = nullptr; const float* U_h = nullptr;
   int64_t u_stride = std::max(B * K, K * F);
   if (a->W0) {
     const void* raw;
@@ -522,13 +630,12 @@ int32_t fb200_nmf_process(fb200_plan* p, const fb200_nmf_args* a)
     dH0 = p->frames.as<float>();
   }
   if (!a->W0 || !a->H0) {
-    FB_TRY(upload_seeds(p, a->seeds, a->batch));
-    FB_CUDA(p, p->rnd.ensure(sizeof(float) * (size_t) (a->batch * u_stride)));
-    launch_mt_uniform(p, p->seeds.as<int64_t>(), a->batch, u_stride, p->rnd.as<float>());
-    U = p->rnd.as<float>();
+    bool any_random = false;
+    FB_TRY(upload_seeds(p, a->seeds, a->batch, &any_random));
+    FB_TRY(draw_uniforms(p, a->batch, u_stride, any_random, &U, &U_h));
   }
   t.mark(1);
-  launch_nmf_init(p, d, U, u_stride, dW0, dH0, 0);
+  launch_nmf_init(p, d, U, U_h, u_stride, dW0, dH0, 0);
   t.mark(2);
   int32_t st = run_nmf_loop(p, d, a->iterations, a->update_w != 0, a->update_h != 0, a->progress, a->progress_user,
                             a->progress_stride);
@@ -575,7 +682,7 @@ int32_t fb200_nmf_process_frames(fb200_plan* p, const fb200_frames_args* a)
     p->err = "fb200_nmf_process_frames: bad arguments";
     return FB200_ERR_INVALID;
   }
-  FB_CUDA(p, cudaSetDevice(p->cfg.device));
+  FB_TRY(enter(p, a->mem));
   StageTimer t(p);
   t.mark(0);
   NmfDev d{};
@@ -591,14 +698,13 @@ int32_t fb200_nmf_process_frames(fb200_plan* p, const fb200_frames_args* a)
   FB_TRY(to_device_raw(p, a->W0, a->mem, es * (size_t) (K * B), p->out_a, &raw_w));
   FB_CUDA(p, p->cspec.ensure(sizeof(float) * (size_t) (K * B)));
   launch_copy3d(p, raw_w, a->dtype, K * B, B, p->cspec.p, FB200_F32, K * B, B, 1, K, B, nullptr, 0);
-  int64_t seed = a->seed;
-  FB_TRY(upload_seeds(p, &seed, 1));
-  FB_CUDA(p, p->rnd.ensure(sizeof(float) * (size_t) K));
-  launch_mt_uniform(p, p->seeds.as<int64_t>(), 1, K, p->rnd.as<float>());
+  const float* U0 = nullptr;
+  int per_frame = 0;
+  FB_TRY(draw_frame_h0(p, a->seed, F, K, &U0, &per_frame));
   t.mark(1);
-  launch_nmf_init(p, d, p->rnd.as<float>(), K, p->cspec.as<float>(), nullptr, 1); // NMF.hpp:55-64
+  launch_nmf_init(p, d, U0, U0, K, p->cspec.as<float>(), nullptr, 1 + per_frame); // NMF.hpp:55-64
   t.mark(2);
-  if (a->iterations > 0) simt_launch_tile(p, d, 1, 0, a->iterations);            // NMF.hpp:72-83
+  if (a->iterations > 0) FB_TRY(run_h_only(p, d, a->iterations));                // NMF.hpp:72-83
   t.mark(3);
   auto export_arr = [&](const float* src, int64_t s_r, void* user, int64_t rows, int64_t cols, DevBuf& tmp) -> int32_t {
     size_t bytes = es * (size_t) (rows * cols);
@@ -644,7 +750,7 @@ int32_t fb200_bufnmf(fb200_plan* p, const fb200_bufnmf_args* a)
     p->err = "Bases and Activations buffers both fixed, but resynthesis disabled: no work to do";
     return FB200_WARN_NO_WORK;
   }
-  FB_CUDA(p, cudaSetDevice(p->cfg.device));
+  FB_TRY(enter(p, a->mem));
   StageTimer t(p);
   t.mark(0);
   const int64_t batch = a->batch, n = a->n_samples;
@@ -673,10 +779,8 @@ int32_t fb200_bufnmf(fb200_plan* p, const fb200_bufnmf_args* a)
     dH0 = (const float*) raw;
   }
   const int64_t u_stride = std::max(B * K, K * F);
-  if (!dW0 || !dH0) {
-    FB_TRY(upload_seeds(p, a->seeds, batch));
-    FB_CUDA(p, p->rnd.ensure(sizeof(float) * (size_t) (batch * u_stride)));
-  }
+  bool any_random = false;
+  if (!dW0 || !dH0) FB_TRY(upload_seeds(p, a->seeds, batch, &any_random));
   t.mark(1);
   // STFT + |X|  (:241-242); k_magnitude writes every interior element, only the pads need zeros
   launch_zero_pads(p, d.V, d.batch, d.F, d.Fp, d.B, d.Bp);
@@ -688,11 +792,9 @@ int32_t fb200_bufnmf(fb200_plan* p, const fb200_bufnmf_args* a)
   FB_TRY(run_stft(p, (const float*) d_audio, batch, n, F, d.V, d.Fp, d.Bp, spec_all, p->win / 2,
                   host ? (const float*) a->audio : nullptr));
   t.mark(2);
-  if (!dW0 || !dH0) {
-    launch_mt_uniform(p, p->seeds.as<int64_t>(), batch, u_stride, p->rnd.as<float>());
-    U = p->rnd.as<float>();
-  }
-  launch_nmf_init(p, d, U, u_stride, dW0, dH0, 0);
+  const float* U_h = nullptr;
+  if (!dW0 || !dH0) FB_TRY(draw_uniforms(p, batch, u_stride, any_random, &U, &U_h));
+  launch_nmf_init(p, d, U, U_h, u_stride, dW0, dH0, 0);
   t.mark(3);
   int32_t st = run_nmf_loop(p, d, a->iterations * (needs_analysis ? 1 : 0), !fix_w, !fix_h, a->progress,
                             a->progress_user, a->progress_stride);      // :268-271
@@ -758,7 +860,7 @@ int32_t fb200_nmf_filter(fb200_plan* p, const fb200_filter_args* a)
     p->err = "fb200_nmf_filter: bad arguments";
     return FB200_ERR_INVALID;
   }
-  FB_CUDA(p, cudaSetDevice(p->cfg.device));
+  FB_TRY(enter(p, a->mem));
   StageTimer t(p);
   t.mark(0);
   const int64_t n = a->n_samples, K = a->rank, B = p->bins, hop = p->hop, win = p->win;
@@ -777,10 +879,9 @@ int32_t fb200_nmf_filter(fb200_plan* p, const fb200_filter_args* a)
   const float* d_audio = (const float*) raw;
   FB_TRY(to_device_raw(p, a->bases, a->mem, sizeof(float) * (size_t) (K * B), p->out_a, &raw));
   const float* d_bases = (const float*) raw;
-  int64_t seed = a->seed;
-  FB_TRY(upload_seeds(p, &seed, 1));
-  FB_CUDA(p, p->rnd.ensure(sizeof(float) * (size_t) K));
-  launch_mt_uniform(p, p->seeds.as<int64_t>(), 1, K, p->rnd.as<float>()); // NMF.hpp:55, same h0 for every frame
+  const float* U0 = nullptr;
+  int per_frame = 0;
+  FB_TRY(draw_frame_h0(p, a->seed, frames_total, K, &U0, &per_frame)); // NMF.hpp:55: same h0 for every frame when seeded
   FB_CUDA(p, p->spec.ensure(sizeof(float2) * (size_t) (chunk * B)));
   if (a->out) FB_CUDA(p, p->cspec.ensure(sizeof(float2) * (size_t) (K * chunk * B)));
   if (host && a->out) FB_CUDA(p, p->stage.ensure(sizeof(float) * (size_t) (K * fresh * hop)));
@@ -794,8 +895,8 @@ int32_t fb200_nmf_filter(fb200_plan* p, const fb200_filter_args* a)
     FB_TRY(alloc_nmf(p, d));
     FB_CUDA(p, cudaMemsetAsync(d.V, 0, sizeof(float) * (size_t) d.Fp * d.Bp, p->stream));
     FB_TRY(run_stft(p, d_audio, 1, n, d.F, d.V, d.Fp, d.Bp, p->spec.as<float2>(), win - f_lo * hop));
-    launch_nmf_init(p, d, p->rnd.as<float>(), K, d_bases, nullptr, 1);   // NMF.hpp:55-64
-    if (a->iterations > 0) simt_launch_tile(p, d, 1, 0, a->iterations);  // NMF.hpp:72-83
+    launch_nmf_init(p, d, U0 + (per_frame ? f_lo * K : 0), nullptr, K, d_bases, nullptr, 1 + per_frame); // NMF.hpp:55-64
+    if (a->iterations > 0) FB_TRY(run_h_only(p, d, a->iterations));      // NMF.hpp:72-83
     if (a->acts_out) {
       const int64_t rows = f_hi - f_new;
       const float* src = d.H + (f_new - f_lo) * d.KP;
@@ -856,7 +957,7 @@ int32_t fb200_bufstft(fb200_plan* p, const fb200_bufstft_args* a)
   const int64_t batch = a->batch, F = a->frames, B = p->bins;
   const int host = a->mem == FB200_HOST;
   int64_t pad = 0, derived = 0;
-  FB_CUDA(p, cudaSetDevice(p->cfg.device));
+  FB_TRY(enter(p, a->mem));
   StageTimer t(p);
   t.mark(0);
   const size_t fb_bytes = sizeof(float) * (size_t) (batch * F * B);
@@ -922,7 +1023,7 @@ int32_t fb200_selftest_tcgen05(fb200_plan* p, const float* in, int64_t n_in, flo
   const int64_t need_in = 128 * 16 + 16 * 64 + 128 * 64 + 16 * 128 + 64 * 16 + 128 * 64 + 128 * 68;
   const int64_t need_out = 128 * 64 + 128 * 16 + 128 * 64 + 128 * 16 + 128 * 32;
   if (!in || !out || n_in != need_in || n_out != need_out) { p->err = "fb200_selftest_tcgen05: bad sizes"; return FB200_ERR_INVALID; }
-  FB_CUDA(p, cudaSetDevice(p->cfg.device));
+  FB_TRY(enter(p, FB200_HOST));
   StageTimer t(p);
   t.mark(0);
   FB_CUDA(p, p->stage.ensure(sizeof(float) * (size_t) n_in));

@@ -104,8 +104,12 @@ struct Plan {
   DevBuf cspec;    // float2 [wave][K][F][B] masked component spectra
   DevBuf V, W, H, hden, wnum_part, wden_part, rnd, seeds, scale, out_a, out_b;
   HostBuf pin_a, pin_b;
-  HostBuf ctrl;    // host-mapped progress / cancel words of the asynchronous progress mode
-  std::map<std::pair<int, int64_t>, cufftHandle> fft_plans; // (type, batch) -> handle
+  HostBuf ctrl;    // pinned read-back of the progress counters of the asynchronous progress mode
+  DevBuf ctrl_dev; // device control words: [0] cancel request, [1 + cta] finished (buffer, pass) units
+  DevBuf wop_buf, hop_buf; // split-bf16 operand copies of W / H for the streamed tensor-core engine
+  std::map<std::pair<int, int64_t>, cufftHandle> fft_plans; // (type, batch) -> handle, bounded LRU
+  std::map<std::pair<int, int64_t>, uint64_t> fft_lru;
+  uint64_t fft_tick = 0;
 
   bool fail(int code, const std::string& msg) { err = msg; last_code = code; return false; }
   int last_code = 0;
@@ -144,8 +148,10 @@ void launch_copy3d(Plan* p, const void* src, int src_dtype, int64_t s_b, int64_t
 // U[b][i] = i-th draw of uniform[0,1) from mt19937_64(seeds[b])  (EigenRandom.hpp:73-110 on libstdc++)
 void launch_mt_uniform(Plan* p, const int64_t* d_seeds, int64_t batch, int64_t count, float* U);
 // W/H initialisation: random or seeded, eps clamp, W row / H column L2 normalisation, hden (NMF.hpp:101-124,150-153)
-void launch_nmf_init(Plan* p, const NmfDev& d, const float* U, int64_t u_stride, const float* W0, const float* H0,
-                     int frame_mode);
+// U_w / U_h: uniform draws for W and for H (the same array unless the two streams are seeded independently).
+// frame_mode 0: NMF::process; 1: processFrame, every frame starts from h0 = U_h[0..K); 2: processFrame, frame f from U_h[f*K..]
+void launch_nmf_init(Plan* p, const NmfDev& d, const float* U_w, const float* U_h, int64_t u_stride, const float* W0,
+                     const float* H0, int frame_mode);
 // per-buffer max over the real H entries -> scale[b] = 1/max  (NMFClient.hpp:289-291)
 void launch_h_max_scale(Plan* p, const NmfDev& d, float* scale);
 
@@ -179,8 +185,12 @@ int32_t run_tc_mma_timing(Plan* p, long long* d_out, int reps);
 
 // kernels_nmf_tc.cu ---------------------------------------------------------------------------------------------
 bool tc_eligible(const NmfDev& d);
-// ctrl != nullptr: host-mapped control words (ctrl[0] cancel request, ctrl[1 + cta] finished passes), see Ctl in the .cu
+// ctrl != nullptr: device control words (ctrl[0] cancel request, ctrl[1 + cta] finished passes), see Ctl in the .cu
 int32_t tc_run(Plan* p, const NmfDev& d, int iters, bool upd_w, bool upd_h, unsigned int* ctrl = nullptr);
 int tc_grid(const Plan* p, const NmfDev& d);
+
+// kernels_nmf_tcs.cu --------------------------------------------------------------------------------------------
+bool tcs_eligible(const NmfDev& d);
+int32_t tcs_run(Plan* p, const NmfDev& d, int iters, bool upd_w, bool upd_h);
 
 } // namespace fb200

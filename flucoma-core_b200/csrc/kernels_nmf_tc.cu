@@ -92,56 +92,6 @@ __device__ __forceinline__ void pair_bar(int q) { asm volatile("bar.sync %0, 64;
 __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 88;" ::: "memory"); }
 __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 208;" ::: "memory"); }
 
-// packed convert: low half <- a, high half <- b (F2FP.BF16.F32.PACK_AB, full-rate; the C++ intrinsic compiled to two
-// scalar F2F on the XU pipe)
-__device__ __forceinline__ uint32_t cvt2(float a, float b)
-{
-  uint32_t r;
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
-  return r;
-}
-// packed fp32 pairs (FMUL2 / FADD2: one issue slot for two IEEE-rounded operations, results identical to the scalar forms)
-__device__ __forceinline__ void mul2(float& o0, float& o1, float a0, float a1, float b0, float b1)
-{
-  uint64_t a, b, c;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
-  asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(b0), "f"(b1));
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(c) : "l"(a), "l"(b));
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(o0), "=f"(o1) : "l"(c));
-}
-__device__ __forceinline__ void add2(float& o0, float& o1, float a0, float a1, float b0, float b1)
-{
-  uint64_t a, b, c;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
-  asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(b0), "f"(b1));
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(c) : "l"(a), "l"(b));
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(o0), "=f"(o1) : "l"(c));
-}
-__device__ __forceinline__ void sub2(float& o0, float& o1, float a0, float a1, float b0, float b1)
-{
-  uint64_t a, b, c;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
-  asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(b0), "f"(b1));
-  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(c) : "l"(a), "l"(b));
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(o0), "=f"(o1) : "l"(c));
-}
-__device__ __forceinline__ float rcp_fast(float x)
-{
-  float r;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-  return r;
-}
-// exact 3-way split of a pair: x = hi + mid + lo (each bf16), packed pairwise
-__device__ __forceinline__ void split3(float x0, float x1, uint32_t& h, uint32_t& m, uint32_t& l)
-{
-  h = cvt2(x0, x1);
-  x0 -= bf16lo_to_f(h); x1 -= bf16hi_to_f(h);
-  m = cvt2(x0, x1);
-  x0 -= bf16lo_to_f(m); x1 -= bf16hi_to_f(m);
-  l = cvt2(x0, x1);
-}
-__device__ __forceinline__ float bf16_bits_to_f(unsigned short u) { return __uint_as_float((uint32_t) u << 16); }
-
 // Block schedule of one pass, shared by every warp role.
 enum BlockKind { BLK_P1 = 0, BLK_PREP = 1, BLK_P2 = 2, BLK_W = 3 };
 __device__ __forceinline__ int block_count(bool p1, bool p2, int T) { return (p1 && p2) ? 3 * T + 1 : (p1 ? 2 * T : 2 * T + 1); }
@@ -185,9 +135,9 @@ struct Sched {
 };
 
 // Asynchronous progress / cancel (fb200_nmf_args.progress_stride == FB200_PROGRESS_ASYNC; NMFClient.hpp:261-274 polls a
-// FluidTask every iteration).  `ctrl` is host-mapped pinned memory: ctrl[0] is written by the host to request a cancel,
+// FluidTask every iteration).  `ctrl` is device memory: ctrl[0] is raised by the host (a 4-byte copy) to request a cancel,
 // ctrl[1 + cta] counts the (buffer, pass) units this CTA has finished.  The TMA producer is the role that runs furthest
-// ahead, so it samples the cancel word once per pass (the load is issued one pass early: no PCIe round trip on its
+// ahead, so it samples the cancel word once per pass (the load is issued one pass early: no L2 round trip on its
 // critical path) and publishes the first cancelled global pass index in shared memory; every role evaluates the same
 // pure function of (pass, global pass index, published index), so all of them leave the loops at the same point.
 // A cancelled buffer finishes the iteration it is in (fused schedule: W is one update ahead of H between passes, so one
@@ -572,17 +522,8 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
         continue;
 #endif
         float r0, r1, l0, l1;
-#ifdef FB200_TC_RCP_PAIR
-        // one MUFU.RCP per PAIR: 1/a = b * (1/(ab)), 1/b = a * (1/(ab)).  a, b >= eps = 2.2e-16, so ab >= 4.9e-32 stays a
-        // normal fp32 number; the quarter-rate XU pipe sees half the work, the FMA pipe (13 % busy) takes two multiplies.
-        const float pa = fmaxf(__uint_as_float(p[2 * j]), kEps), pb = fmaxf(__uint_as_float(p[2 * j + 1]), kEps);
-        const float t = rcp_fast(pa * pb);
-        mul2(r0, r1, v[2 * j], v[2 * j + 1], pb, pa);
-        mul2(r0, r1, r0, r1, t, t);
-#else
         mul2(r0, r1, v[2 * j], v[2 * j + 1], rcp_fast(fmaxf(__uint_as_float(p[2 * j]), kEps)),
              rcp_fast(fmaxf(__uint_as_float(p[2 * j + 1]), kEps)));
-#endif
         ph[j] = cvt2(r0, r1);
         sub2(l0, l1, r0, r1, bf16lo_to_f(ph[j]), bf16hi_to_f(ph[j]));
         pl[j] = cvt2(l0, l1);

@@ -175,18 +175,18 @@ __global__ void __launch_bounds__(256) k_init_h(NmfDev d, const float* __restric
 }
 
 // processFrame: every frame starts from the same h0 = max(U(K), eps), not normalised (NMF.hpp:55,59)
-__global__ void __launch_bounds__(256) k_init_h_frames(NmfDev d, const float* __restrict__ U)
+__global__ void __launch_bounds__(256) k_init_h_frames(NmfDev d, const float* __restrict__ U, int per_frame)
 {
   int64_t total = (int64_t) d.batch * d.Fp * d.KP;
   for (int64_t e = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; e < total; e += (int64_t) gridDim.x * blockDim.x) {
     int k = (int) (e % d.KP);
     int64_t f = (e / d.KP) % d.Fp;
-    d.H[e] = (k < d.K && f < d.F) ? fmaxf(U[k], kEps) : 0.f;
+    d.H[e] = (k < d.K && f < d.F) ? fmaxf(U[per_frame ? f * d.K + k : k], kEps) : 0.f;
   }
 }
 
-void launch_nmf_init(Plan* p, const NmfDev& d, const float* U, int64_t u_stride, const float* W0, const float* H0,
-                     int frame_mode)
+void launch_nmf_init(Plan* p, const NmfDev& d, const float* U, const float* U_h, int64_t u_stride, const float* W0,
+                     const float* H0, int frame_mode)
 {
   int nW = d.shared_w ? 1 : d.batch;
   k_init_w<<<nW, 256, 0, p->stream>>>(d, U, u_stride, W0);
@@ -194,9 +194,9 @@ void launch_nmf_init(Plan* p, const NmfDev& d, const float* U, int64_t u_stride,
   if (frame_mode) {
     int64_t total = (int64_t) d.batch * d.Fp * d.KP;
     int grid = (int) std::min<int64_t>((total + 255) / 256, (int64_t) p->sm_count * 16);
-    k_init_h_frames<<<grid, 256, 0, p->stream>>>(d, U);
+    k_init_h_frames<<<grid, 256, 0, p->stream>>>(d, U_h, frame_mode == 2);
   } else {
-    k_init_h<<<d.batch, 256, 0, p->stream>>>(d, U, u_stride, H0);
+    k_init_h<<<d.batch, 256, 0, p->stream>>>(d, U_h, u_stride, H0);
   }
   p->launches++;
 }

@@ -210,5 +210,56 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b)
 __device__ __forceinline__ float bf16lo_to_f(uint32_t p) { return __uint_as_float(p << 16); }
 __device__ __forceinline__ float bf16hi_to_f(uint32_t p) { return __uint_as_float(p & 0xFFFF0000u); }
 
+// ---- packed fp32 / bf16 arithmetic of the update epilogues -------------------------------------------------------
+// packed convert: low half <- a, high half <- b (F2FP.BF16.F32.PACK_AB, full-rate; the C++ intrinsic compiled to two
+// scalar F2F on the XU pipe)
+__device__ __forceinline__ uint32_t cvt2(float a, float b)
+{
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+// packed fp32 pairs (FMUL2 / FADD2: one issue slot for two IEEE-rounded operations, results identical to the scalar forms)
+__device__ __forceinline__ void mul2(float& o0, float& o1, float a0, float a1, float b0, float b1)
+{
+  uint64_t a, b, c;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(b0), "f"(b1));
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(c) : "l"(a), "l"(b));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(o0), "=f"(o1) : "l"(c));
+}
+__device__ __forceinline__ void add2(float& o0, float& o1, float a0, float a1, float b0, float b1)
+{
+  uint64_t a, b, c;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(b0), "f"(b1));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(c) : "l"(a), "l"(b));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(o0), "=f"(o1) : "l"(c));
+}
+__device__ __forceinline__ void sub2(float& o0, float& o1, float a0, float a1, float b0, float b1)
+{
+  uint64_t a, b, c;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(b0), "f"(b1));
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(c) : "l"(a), "l"(b));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(o0), "=f"(o1) : "l"(c));
+}
+__device__ __forceinline__ float rcp_fast(float x)
+{
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+// exact 3-way split of a pair: x = hi + mid + lo (each bf16), packed pairwise
+__device__ __forceinline__ void split3(float x0, float x1, uint32_t& h, uint32_t& m, uint32_t& l)
+{
+  h = cvt2(x0, x1);
+  x0 -= bf16lo_to_f(h); x1 -= bf16hi_to_f(h);
+  m = cvt2(x0, x1);
+  x0 -= bf16lo_to_f(m); x1 -= bf16hi_to_f(m);
+  l = cvt2(x0, x1);
+}
+__device__ __forceinline__ float bf16_bits_to_f(unsigned short u) { return __uint_as_float((uint32_t) u << 16); }
+
 } // namespace tc
 } // namespace fb200

@@ -24,7 +24,7 @@ LIB_PATH = os.path.join(_PKG, "lib", "libflucoma_b200.so")
 F32, F64 = 0, 1
 HOST, DEVICE = 0, 1
 OK, WARN_NO_WORK, CANCELLED = 0, 1, 2
-BACKEND_AUTO, BACKEND_SIMT, BACKEND_TCGEN05 = 0, 1, 2
+BACKEND_AUTO, BACKEND_SIMT, BACKEND_TCGEN05, BACKEND_TCGEN05_STREAMED = 0, 1, 2, 3
 PROGRESS_ASYNC = -1  # fb200_progress_fn: never interrupt the device loop, poll its pass counters
 
 PROGRESS_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int64)
@@ -176,6 +176,11 @@ def _is_torch(x):
     return x is not None and type(x).__module__.startswith("torch")
 
 
+def _on_device(x):
+    """True for a torch CUDA tensor (used in place, FB200_DEVICE); CPU torch tensors and numpy arrays are FB200_HOST."""
+    return _is_torch(x) and bool(x.is_cuda)
+
+
 def _ptr(x):
     if x is None:
         return None
@@ -198,6 +203,7 @@ class Plan:
 
     def __init__(self, win=1024, hop=-1, fft=-1, device=0, max_rank=64, max_batch=0, max_samples=0, backend=BACKEND_AUTO):
         self._L = load()
+        backend = int(os.environ.get("FB200_BACKEND", backend))  # developer override (tools/, A/B runs)
         cfg = Config(C.sizeof(Config), device, win, hop, fft, max_rank, max_batch, max_samples, backend, 0)
         h = C.c_void_p()
         st = self._L.fb200_plan_create(C.byref(cfg), C.byref(h))
@@ -220,6 +226,15 @@ class Plan:
 
     def __exit__(self, *a):
         self.close()
+
+    def _dev(self, x):
+        """Memory space of an argument; a CUDA tensor must live on the plan's device (its pointer is used in place)."""
+        if not _on_device(x):
+            return False
+        idx = x.device.index if x.device.index is not None else 0
+        if idx != self.device:
+            raise ValueError(f"tensor is on cuda:{idx} but the plan is bound to cuda:{self.device}")
+        return True
 
     def _check(self, st):
         if st < 0:
@@ -265,7 +280,7 @@ class Plan:
         spec = self._empty_like_space(a, (batch, F, self.bins), cplx) if want_spectrum else None
         mag = self._empty_like_space(a, (batch, F, self.bins), real) if want_magnitude else None
         self._check(self._L.fb200_stft(self._h, _ptr(a), batch, n, _ptr(spec), _ptr(mag), code,
-                                       DEVICE if _is_torch(a) else HOST))
+                                       DEVICE if self._dev(a) else HOST))
         return spec, mag
 
     def istft(self, spectrum, n_samples):
@@ -277,7 +292,7 @@ class Plan:
         code = _dtype_code(s)
         out = self._empty_like_space(s, (batch, n_samples), "float32" if code == F32 else "float64")
         self._check(self._L.fb200_istft(self._h, _ptr(s), batch, F, _ptr(out), n_samples, code,
-                                        DEVICE if _is_torch(s) else HOST))
+                                        DEVICE if self._dev(s) else HOST))
         return out
 
     # -- BufSTFT (clients/nrt/BufSTFTClient.hpp:82-190, 192-279) -----------------------------------------------------
@@ -292,7 +307,7 @@ class Plan:
         _, hops = bufstft_sizes(self.win, self.hop, padding_mode, False, n)
         mag = self._empty_like_space(a, (batch, hops, self.bins), "float32") if want_mag else None
         ph = self._empty_like_space(a, (batch, hops, self.bins), "float32") if want_phase else None
-        args = BufStftArgs(C.sizeof(BufStftArgs), DEVICE if _is_torch(a) else HOST, 0, padding_mode, batch, n, hops, _ptr(a),
+        args = BufStftArgs(C.sizeof(BufStftArgs), DEVICE if self._dev(a) else HOST, 0, padding_mode, batch, n, hops, _ptr(a),
                            _ptr(mag), _ptr(ph), None)
         self._check(self._L.fb200_bufstft(self._h, C.byref(args)))
         if squeeze:
@@ -310,7 +325,7 @@ class Plan:
         batch, frames, _ = m.shape
         _, n_out = bufstft_sizes(self.win, self.hop, padding_mode, True, frames)
         out = self._empty_like_space(m, (batch, n_out), "float32")
-        args = BufStftArgs(C.sizeof(BufStftArgs), DEVICE if _is_torch(m) else HOST, 1, padding_mode, batch, 0, frames, None,
+        args = BufStftArgs(C.sizeof(BufStftArgs), DEVICE if self._dev(m) else HOST, 1, padding_mode, batch, 0, frames, None,
                            _ptr(m), _ptr(p), _ptr(out))
         self._check(self._L.fb200_bufstft(self._h, C.byref(args)))
         return out[0] if squeeze else out
@@ -346,7 +361,7 @@ class Plan:
         H1 = self._empty_like_space(X, (batch, F, rank), real)
         V1 = self._empty_like_space(X, (batch, F, B), real) if want_v else None
         cb = PROGRESS_FN(lambda user, it: int(bool(progress(it)))) if progress else PROGRESS_FN()
-        a = NmfArgs(C.sizeof(NmfArgs), code, DEVICE if _is_torch(X) else HOST, batch, F, B, rank, iterations,
+        a = NmfArgs(C.sizeof(NmfArgs), code, DEVICE if self._dev(X) else HOST, batch, F, B, rank, iterations,
                     int(update_w), int(update_h), _ptr(X), _ptr(seeds), _ptr(W0), _ptr(H0), _ptr(W1), _ptr(H1),
                     _ptr(V1), cb, None, progress_stride, 0)
         st = self._check(self._L.fb200_nmf_process(self._h, C.byref(a)))
@@ -367,7 +382,7 @@ class Plan:
         H = self._empty_like_space(X, (F, K), real)
         V = self._empty_like_space(X, (F, B), real) if want_v else None
         Wn = self._empty_like_space(X, (K, B), real) if want_w else None
-        a = FramesArgs(C.sizeof(FramesArgs), code, DEVICE if _is_torch(X) else HOST, F, B, K, iterations, seed,
+        a = FramesArgs(C.sizeof(FramesArgs), code, DEVICE if self._dev(X) else HOST, F, B, K, iterations, seed,
                        _ptr(X), _ptr(W0), _ptr(Wn), _ptr(H), _ptr(V))
         self._check(self._L.fb200_nmf_process_frames(self._h, C.byref(a)))
         return H, V, Wn
@@ -404,7 +419,7 @@ class Plan:
         seeds = np.ascontiguousarray(seeds, dtype=np.int64)
         assert seeds.shape == (batch,)
         cb = PROGRESS_FN(lambda user, it: int(bool(progress(it)))) if progress else PROGRESS_FN()
-        a = BufNmfArgs(C.sizeof(BufNmfArgs), DEVICE if _is_torch(a_in) else HOST, batch, n, rank, iterations,
+        a = BufNmfArgs(C.sizeof(BufNmfArgs), DEVICE if self._dev(a_in) else HOST, batch, n, rank, iterations,
                        bases_mode, acts_mode, _ptr(a_in), _ptr(seeds), _ptr(bases_in), _ptr(acts_in),
                        None if fix_w else _ptr(bases), None if fix_h else _ptr(acts), _ptr(rs), cb, None,
                        progress_stride, 0)
@@ -426,7 +441,7 @@ class Plan:
         frames = (n + self.hop - 1) // self.hop
         out = self._empty_like_space(a_in, (K, n), "float32") if want_out else None
         acts = self._empty_like_space(a_in, (frames, K), "float32") if want_acts else None
-        a = FilterArgs(C.sizeof(FilterArgs), DEVICE if _is_torch(a_in) else HOST, n, K, iterations, seed, _ptr(a_in),
+        a = FilterArgs(C.sizeof(FilterArgs), DEVICE if self._dev(a_in) else HOST, n, K, iterations, seed, _ptr(a_in),
                        _ptr(W), _ptr(out), _ptr(acts))
         self._check(self._L.fb200_nmf_filter(self._h, C.byref(a)))
         return out, acts

@@ -54,8 +54,15 @@ typedef enum fb200_status {
 typedef enum fb200_dtype { FB200_F32 = 0, FB200_F64 = 1 } fb200_dtype;
 typedef enum fb200_mem { FB200_HOST = 0, FB200_DEVICE = 1 } fb200_mem;
 
-/* NMF update engine. AUTO picks TCGEN05 when the shape qualifies, else SIMT. */
-typedef enum fb200_backend { FB200_BACKEND_AUTO = 0, FB200_BACKEND_SIMT = 1, FB200_BACKEND_TCGEN05 = 2 } fb200_backend;
+/* NMF update engine.  AUTO picks a tensor-core engine when the shape qualifies and the call has enough independent
+ * buffers / frame tiles to fill the SMs, else SIMT.  fb200_stats.backend_used reports the engine that ran. */
+typedef enum fb200_backend {
+  FB200_BACKEND_AUTO = 0,
+  FB200_BACKEND_SIMT = 1,             /* fp32 CUDA-core engine: any shape */
+  FB200_BACKEND_TCGEN05 = 2,          /* tensor-core engines; as a request: whichever of the two takes the shape */
+  FB200_BACKEND_TCGEN05_STREAMED = 3  /* tensor-core engine with W/H streamed from L2 (rank 9..32, any bins = 128 m + 1, any
+                                         frame count, fixed-dictionary frame streams); as a request: force it */
+} fb200_backend;
 
 typedef struct fb200_plan fb200_plan; /* opaque; owns device memory, cuFFT plans, stream, pinned staging */
 
