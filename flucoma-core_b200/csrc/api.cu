@@ -108,7 +108,7 @@ struct StageTimer {
 // h_audio != nullptr: the audio still sits in (pinned) host memory; every wave is uploaded into d_audio on the plan's
 // copy stream while the previous waves run their kernels, so that only the first upload is exposed.
 int32_t run_stft(Plan* p, const float* d_audio, int64_t batch, int64_t n, int64_t F, float* V, int64_t Fp, int64_t Bp,
-                 float2* spec_all, int64_t half, const float* h_audio = nullptr)
+                 float2* spec_all, int64_t half, const float* h_audio = nullptr, int hop_override = 0)
 {
   const int B = p->bins;
   int64_t wave = wave_size(p, F, batch, 1);
@@ -137,7 +137,7 @@ int32_t run_stft(Plan* p, const float* d_audio, int64_t batch, int64_t n, int64_
   for (int64_t b0 = 0; b0 < batch; b0 += wave, wi++) {
     int64_t nb = std::min(wave, batch - b0);
     if (h_audio) FB_CUDA(p, cudaStreamWaitEvent(p->stream, p->cev[wi], 0));
-    launch_frame_window(p, d_audio + b0 * n, n, nb, F, p->frames.as<float>(), half);
+    launch_frame_window(p, d_audio + b0 * n, n, nb, F, p->frames.as<float>(), half, hop_override);
     cufftHandle h;
     FB_TRY(get_fft_plan(p, CUFFT_R2C, nb * F, &h));
     float2* sp = spec_all ? spec_all + b0 * F * B : spec_wave;
@@ -895,7 +895,7 @@ int32_t fb200_nmf_filter(fb200_plan* p, const fb200_filter_args* a)
     FB_TRY(alloc_nmf(p, d));
     FB_CUDA(p, cudaMemsetAsync(d.V, 0, sizeof(float) * (size_t) d.Fp * d.Bp, p->stream));
     FB_TRY(run_stft(p, d_audio, 1, n, d.F, d.V, d.Fp, d.Bp, p->spec.as<float2>(), win - f_lo * hop));
-    launch_nmf_init(p, d, U0 + (per_frame ? f_lo * K : 0), nullptr, K, d_bases, nullptr, 1 + per_frame); // NMF.hpp:55-64
+    launch_nmf_init(p, d, U0 + (per_frame ? f_lo * K : 0), U0 + (per_frame ? f_lo * K : 0), K, d_bases, nullptr, 1 + per_frame); // NMF.hpp:55-64
     if (a->iterations > 0) FB_TRY(run_h_only(p, d, a->iterations));      // NMF.hpp:72-83
     if (a->acts_out) {
       const int64_t rows = f_hi - f_new;
@@ -917,6 +917,65 @@ int32_t fb200_nmf_filter(fb200_plan* p, const fb200_filter_args* a)
                                      sizeof(float) * (size_t) len, (size_t) K, cudaMemcpyDeviceToHost, p->stream));
     }
     if (host) FB_CUDA(p, cudaStreamSynchronize(p->stream)); // staging buffers are reused by the next chunk
+  }
+  t.mark(2);
+  FB_TRY(finish(p, t, 2));
+  p->stats.ms_h2d = t.ms(0, 1); p->stats.ms_nmf = t.ms(1, 2);
+  return FB200_OK;
+}
+
+// The per-frame body of the streaming clients for a batch of frames that a host-side BufferedProcess has already cut:
+// STFT::processFrame (window + rFFT) -> |X| -> NMF::processFrame -> [NMFFilter only: estimate + RatioMask per component ->
+// ISTFT::processFrame].  NMFFilterClient.hpp:98-117, NMFMatchClient.hpp:111-118, BufferedProcess.hpp:200-216.
+int32_t fb200_nmf_filter_frames(fb200_plan* p, const fb200_filter_frames_args* a)
+{
+  if (!p) return FB200_ERR_INVALID;
+  if (!a || a->struct_size != sizeof(fb200_filter_frames_args) || !a->in || !a->bases || a->frames <= 0 || a->rank <= 0 ||
+      a->iterations < 0 || (!a->out && !a->acts_out)) {
+    p->err = "fb200_nmf_filter_frames: bad arguments";
+    return FB200_ERR_INVALID;
+  }
+  FB_TRY(enter(p, a->mem));
+  StageTimer t(p);
+  t.mark(0);
+  const int64_t F = a->frames, K = a->rank, B = p->bins, win = p->win;
+  const int host = a->mem == FB200_HOST;
+  const void* raw;
+  FB_TRY(to_device_raw(p, a->in, a->mem, sizeof(float) * (size_t) (F * win), p->audio, &raw));
+  const float* d_in = (const float*) raw;
+  FB_TRY(to_device_raw(p, a->bases, a->mem, sizeof(float) * (size_t) (K * B), p->out_a, &raw));
+  const float* d_bases = (const float*) raw;
+  const float* U0 = nullptr;
+  int per_frame = 0;
+  FB_TRY(draw_frame_h0(p, a->seed, F, K, &U0, &per_frame));
+  NmfDev d{};
+  d.batch = 1; d.F = (int) F; d.B = (int) B; d.K = (int) K; d.clamp_v = 1;
+  FB_TRY(alloc_nmf(p, d));
+  FB_CUDA(p, p->spec.ensure(sizeof(float2) * (size_t) (F * B)));
+  t.mark(1);
+  FB_CUDA(p, cudaMemsetAsync(d.V, 0, sizeof(float) * (size_t) d.Fp * d.Bp, p->stream));
+  // the frames are one contiguous "signal" cut with hop = win and no padding: frame f = in[f*win, (f+1)*win)
+  FB_TRY(run_stft(p, d_in, 1, F * win, F, d.V, d.Fp, d.Bp, p->spec.as<float2>(), 0, nullptr, (int) win));
+  launch_nmf_init(p, d, U0, U0, K, d_bases, nullptr, 1 + per_frame);     // NMF.hpp:55-64
+  if (a->iterations > 0) FB_TRY(run_h_only(p, d, a->iterations));        // NMF.hpp:72-83
+  if (a->acts_out) {
+    float* dst = a->acts_out;
+    if (host) { FB_CUDA(p, p->out_b.ensure(sizeof(float) * (size_t) (F * K))); dst = p->out_b.as<float>(); }
+    launch_copy3d(p, d.H, FB200_F32, 0, d.KP, dst, FB200_F32, 0, K, 1, F, K, nullptr, 0);
+    if (host) FB_CUDA(p, cudaMemcpyAsync(a->acts_out, dst, sizeof(float) * (size_t) (F * K), cudaMemcpyDeviceToHost, p->stream));
+  }
+  if (a->out) {
+    FB_CUDA(p, p->cspec.ensure(sizeof(float2) * (size_t) (K * F * B)));
+    launch_mask(p, d, p->spec.as<float2>(), 0, 1, p->cspec.as<float2>());  // NMFFilterClient.hpp:104-113
+    FB_CUDA(p, p->frames.ensure(sizeof(float) * (size_t) (K * F * p->fft)));
+    cufftHandle h;
+    FB_TRY(get_fft_plan(p, CUFFT_C2R, K * F, &h));
+    FB_CUFFT(p, cufftExecC2R(h, reinterpret_cast<cufftComplex*>(p->cspec.p), p->frames.as<float>()));
+    p->launches++;
+    float* dst = a->out;
+    if (host) { FB_CUDA(p, p->stage.ensure(sizeof(float) * (size_t) (F * K * win))); dst = p->stage.as<float>(); }
+    launch_window_frames(p, p->frames.as<float>(), K, F, dst);
+    if (host) FB_CUDA(p, cudaMemcpyAsync(a->out, dst, sizeof(float) * (size_t) (F * K * win), cudaMemcpyDeviceToHost, p->stream));
   }
   t.mark(2);
   FB_TRY(finish(p, t, 2));
@@ -1049,7 +1108,8 @@ const fb200_api* fb200_get_api(uint32_t abi_version)
   static const fb200_api api = {FB200_ABI_VERSION, (uint32_t) sizeof(fb200_api), fb200_device_count, fb200_plan_create,
                                 fb200_plan_destroy, fb200_last_error, fb200_num_frames, fb200_resolve_fft,
                                 fb200_shard_range, fb200_stft, fb200_istft, fb200_nmf_process, fb200_nmf_process_frames,
-                                fb200_bufnmf, fb200_nmf_filter, fb200_get_stats, fb200_bufstft_sizes, fb200_bufstft};
+                                fb200_bufnmf, fb200_nmf_filter, fb200_get_stats, fb200_bufstft_sizes, fb200_bufstft,
+                                fb200_nmf_filter_frames};
   return abi_version == FB200_ABI_VERSION ? &api : nullptr;
 }
 

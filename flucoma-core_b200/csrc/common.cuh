@@ -164,7 +164,10 @@ void launch_vhat(Plan* p, const NmfDev& d, void* dst, int dst_dtype);
 
 // kernels_stft.cu -----------------------------------------------------------------------------------------------
 void launch_hann(Plan* p);
-void launch_frame_window(Plan* p, const float* audio, int64_t n, int64_t nbuf, int64_t F, float* frames, int64_t half);
+void launch_frame_window(Plan* p, const float* audio, int64_t n, int64_t nbuf, int64_t F, float* frames, int64_t half,
+                         int hop_override = 0);
+// y [K][F][fft] (C2R output) -> out [F][K][win]: first `win` samples * window / fft  (ISTFT::processFrame, STFT.hpp:201-208)
+void launch_window_frames(Plan* p, const float* y, int64_t K, int64_t F, float* out);
 // exact zeros in the pads of V[batch][Fp][Bp] (bins >= B, frames >= F) when the interior is about to be overwritten
 void launch_zero_pads(Plan* p, float* V, int64_t batch, int64_t F, int64_t Fp, int64_t B, int64_t Bp);
 // spec [nbuf*F][B] complex -> V[nbuf][Fp][Bp] magnitudes (+ zero imag of DC/Nyquist in place, FFT.hpp:99-101)

@@ -119,9 +119,14 @@ struct Params {
   int units;           // work units: buffers (update_w) or (buffer, tile pair) (fixed W)
 };
 
-// The job sequence of one work unit, identical for every warp role.  f(phase, tile, need) with phase 0 = H job, 1 = W job;
-// `need` = number of finished jobs (of this CTA, counted over all units) the producer must see before it may load the
-// job's operands from global memory.  `jn` counts jobs.
+// The job sequence of one work unit, identical for every warp role: f(phase, tile, need_st, need_c, per_tile) with phase
+// 0 = H job, 1 = W job.  The need_* values tell the producer how many jobs of this CTA (counted over all units, `jn`)
+// must have published their tile update before it may copy operands that those updates wrote:
+//   need_st            the stationary tile (only the fixed-W mode re-reads a tile it has just updated; with W updates the
+//                      stationary tiles of a half-iteration were last written a whole half-iteration earlier)
+//   need_c + (per_tile ? i / 2 : 0)   the streamed chunk of step i: W chunks need the whole preceding W half-iteration
+//                      (the column normalisation rescales every bin), the H chunk of frames [64 i, 64 i + 64) needs only
+//                      the H job of tile i / 2 -- so a W half-iteration starts while the H half-iteration before it drains.
 template <class F>
 __device__ __forceinline__ void for_jobs(const Params& p, int unit, uint32_t& jn, F&& f)
 {
@@ -131,15 +136,19 @@ __device__ __forceinline__ void for_jobs(const Params& p, int unit, uint32_t& jn
     const int t0 = 2 * (unit % pairs);
     const int nt = (t0 + 1 < T) ? 2 : 1;
     for (int it = 0; it < p.iters; it++)
-      for (int i = 0; i < nt; i++) { f(0, t0 + i, it == 0 ? 0u : jn - (uint32_t) (nt - 1)); jn++; }
+      for (int i = 0; i < nt; i++) { f(0, t0 + i, it == 0 ? 0u : jn - (uint32_t) (nt - 1), 0u, false); jn++; }
     return;
   }
+  uint32_t hjob0 = 0;
+  bool have_h = false; // an H half-iteration of THIS unit precedes
   for (int it = 0; it < p.iters; it++) {
-    const uint32_t n0 = jn; // everything before this half-iteration finished (incl. the previous unit's last job)
-    for (int m = 0; m < MT; m++) { f(1, m, n0); jn++; }
+    // H fixed: W half-iterations follow each other directly, the W tiles were rescaled by the one just before
+    const uint32_t w_st = (p.upd_h || it == 0) ? 0u : jn;
+    for (int m = 0; m < MT; m++) { f(1, m, w_st, have_h ? hjob0 + 1 : 0u, have_h); jn++; }
     if (p.upd_h) {
       const uint32_t n1 = jn;
-      for (int t = 0; t < T; t++) { f(0, t, n1); jn++; }
+      hjob0 = n1; have_h = true;
+      for (int t = 0; t < T; t++) { f(0, t, 0u, n1, false); jn++; }
     }
   }
 }
@@ -229,7 +238,7 @@ k_nmf_tcs(Params p, const __grid_constant__ CUtensorMap tmap1, const __grid_cons
     for (int i = 0; i < NS; i++) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 4); }
     for (int i = 0; i < NSO; i++) { mbar_init(&o_full[i], 1); mbar_init(&o_empty[i], 2); }
     for (int i = 0; i < 2; i++) {
-      mbar_init(&st_full[i], 1); mbar_init(&st_empty[i], 1);
+      mbar_init(&st_full[i], 1); mbar_init(&st_empty[i], 9); // first-MMA commit + the 8 epilogue warps (tile update reads it)
       mbar_init(&p_full[i], 1); mbar_init(&r_full[i], 4); mbar_init(&b_full[i], 1); mbar_init(&p_free[i], 4);
     }
     mbar_fence_init();
@@ -254,32 +263,46 @@ k_nmf_tcs(Params p, const __grid_constant__ CUtensorMap tmap1, const __grid_cons
           const int buf = unit_buffer(p, unit);
           const __nv_bfloat16* gW = p.Wop + buf * wop_stride;
           const __nv_bfloat16* gH = p.Hop + buf * hop_stride;
-          for_jobs(p, unit, jn, [&](int phase, int tile, uint32_t need) {
-            while (*jobs_done < need) {}
-            fence_async_all(); // the tile updates were written with generic stores; the copies below read through the async proxy
+          for_jobs(p, unit, jn, [&](int phase, int tile, uint32_t need_st, uint32_t need_c, bool per_tile) {
+            const int ns = phase == 0 ? C1 : S2;
+            const uint32_t n0 = n;
+            auto issue_v = [&](int i) { // V tile of step i
+              const uint32_t nn = n0 + i, st = nn % NS, k = nn / NS;
+              mbar_wait(&v_empty[st], (k & 1) ^ 1);
+              mbar_arrive_expect_tx(&v_full[st], STAGE);
+              uint8_t* dst = smem + C::OFF_V + st * STAGE;
+              if (phase == 0) { // [128 frames][64 bins] as two 32-bin boxes
+                tma_load_3d(dst, &tmap1, 64 * i, 128 * tile, buf, &v_full[st]);
+                tma_load_3d(dst + 16384, &tmap1, 64 * i + 32, 128 * tile, buf, &v_full[st]);
+              } else { // [64 frames][128 bins] as four 32-bin boxes
+#pragma unroll
+                for (int w = 0; w < 4; w++) tma_load_3d(dst + w * 8192, &tmap2, 128 * tile + 32 * w, 64 * i, buf, &v_full[st]);
+              }
+            };
             { // stationary tile: 128 rows of H (H job) / W (W job)
+              if (need_st) {
+                while (*jobs_done < need_st) {}
+                fence_async_all(); // the tile update was written with generic stores; the copy reads through the async proxy
+              }
               const uint32_t sl = jn & 1, k = jn >> 1;
               mbar_wait(&st_empty[sl], (k & 1) ^ 1);
               mbar_arrive_expect_tx(&st_full[sl], C::TILE);
               const __nv_bfloat16* src = (phase == 0 ? gH : gW) + (int64_t) tile * 16 * 3 * KB * 64;
               bulk_g2s(smem + C::OFF_ST + sl * C::TILE, src, C::TILE, &st_full[sl]);
             }
-            const int ns = phase == 0 ? C1 : S2;
+            // |X| does not depend on anything: the first tiles of the job are requested before the producer blocks on the
+            // chunk dependencies, so a half-iteration boundary costs one L2 round trip of a chunk, not a cold pipeline
+            const int pre = ns < NS ? ns : NS;
+            for (int i = 0; i < pre; i++) issue_v(i);
+            uint32_t seen = 0;
             for (int i = 0; i < ns; i++, n++) {
-              { // V tile of the step
-                const uint32_t st = n % NS, k = n / NS;
-                mbar_wait(&v_empty[st], (k & 1) ^ 1);
-                mbar_arrive_expect_tx(&v_full[st], STAGE);
-                uint8_t* dst = smem + C::OFF_V + st * STAGE;
-                if (phase == 0) { // [128 frames][64 bins] as two 32-bin boxes
-                  tma_load_3d(dst, &tmap1, 64 * i, 128 * tile, buf, &v_full[st]);
-                  tma_load_3d(dst + 16384, &tmap1, 64 * i + 32, 128 * tile, buf, &v_full[st]);
-                } else { // [64 frames][128 bins] as four 32-bin boxes
-#pragma unroll
-                  for (int w = 0; w < 4; w++) tma_load_3d(dst + w * 8192, &tmap2, 128 * tile + 32 * w, 64 * i, buf, &v_full[st]);
-                }
-              }
+              if (i >= pre) issue_v(i);
               { // streamed operand chunk: 64 rows of W (H job) / H (W job)
+                const uint32_t need = need_c + (per_tile ? (uint32_t) (i >> 1) : 0u);
+                if (seen < need) {
+                  while ((seen = *jobs_done) < need) {}
+                  fence_async_all();
+                }
                 const uint32_t so = n % NSO, k = n / NSO;
                 mbar_wait(&o_empty[so], (k & 1) ^ 1);
                 mbar_arrive_expect_tx(&o_full[so], C::CHUNK);
@@ -301,7 +324,7 @@ k_nmf_tcs(Params p, const __grid_constant__ CUtensorMap tmap1, const __grid_cons
       const uint32_t st_a = smem_u32(smem + C::OFF_ST), o_a = smem_u32(smem + C::OFF_O);
       uint32_t n = 0, jn = 0;
       for (int unit = blockIdx.x; unit < p.units; unit += gridDim.x) {
-        for_jobs(p, unit, jn, [&](int phase, int, uint32_t) {
+        for_jobs(p, unit, jn, [&](int phase, int, uint32_t, uint32_t, bool) {
           const uint32_t sl = jn & 1;
           mbar_wait(&st_full[sl], (jn >> 1) & 1);
           const uint32_t alo = ((st_a + sl * C::TILE) >> 4) | LO_A;
@@ -342,7 +365,7 @@ k_nmf_tcs(Params p, const __grid_constant__ CUtensorMap tmap1, const __grid_cons
       const uint32_t o_a = smem_u32(smem + C::OFF_O);
       uint32_t n = 0, jn = 0;
       for (int unit = blockIdx.x; unit < p.units; unit += gridDim.x) {
-        for_jobs(p, unit, jn, [&](int phase, int, uint32_t) {
+        for_jobs(p, unit, jn, [&](int phase, int, uint32_t, uint32_t, bool) {
           const uint32_t id3 = phase == 0 ? ID_H3 : ID_W3, id1 = phase == 0 ? ID_H1 : ID_W1;
           const int ns = phase == 0 ? C1 : S2;
           for (int i = 0; i < ns; i++, n++) {
@@ -525,7 +548,7 @@ k_nmf_tcs(Params p, const __grid_constant__ CUtensorMap tmap1, const __grid_cons
       int w_tiles_done = 0;
       const int MT = BT / 128;
 
-      for_jobs(p, unit, jn, [&](int phase, int tile, uint32_t) {
+      for_jobs(p, unit, jn, [&](int phase, int tile, uint32_t, uint32_t, bool) {
         if (phase == 1 && w_tiles_done == 0) {
           // ---------------- start of a W half-iteration: denominators + Nyquist numerators from H --------------------
           if (!partials_valid) { // first iteration (or H fixed): sweep H once; later the H jobs provide them
@@ -571,10 +594,24 @@ k_nmf_tcs(Params p, const __grid_constant__ CUtensorMap tmap1, const __grid_cons
           // ---------------- H-tile update (NMF.hpp:168-170) ----------------------------------------------------------
           const int f = 128 * tile + r;
           float h[K];
-          {
-            const float4* src = reinterpret_cast<const float4*>(gH + (int64_t) f * K);
+          { // old H row = hi + mid + lo of the job's stationary tile (small parts first: exact)
+            const __nv_bfloat16* stt = reinterpret_cast<const __nv_bfloat16*>(smem + C::OFF_ST + (jn & 1) * C::TILE);
 #pragma unroll
-            for (int j = 0; j < K / 4; j++) { const float4 x = src[j]; h[4 * j] = x.x; h[4 * j + 1] = x.y; h[4 * j + 2] = x.z; h[4 * j + 3] = x.w; }
+            for (int kb = 0; kb < KB; kb++) {
+              float acc8[8];
+#pragma unroll
+              for (int j = 0; j < 8; j++) acc8[j] = 0.f;
+#pragma unroll
+              for (int pt = 2; pt >= 0; pt--) {
+                const uint4 u = *reinterpret_cast<const uint4*>(stt + op_index_h<K>(pt, r, 8 * kb));
+                acc8[0] += bf16lo_to_f(u.x); acc8[1] += bf16hi_to_f(u.x); acc8[2] += bf16lo_to_f(u.y); acc8[3] += bf16hi_to_f(u.y);
+                acc8[4] += bf16lo_to_f(u.z); acc8[5] += bf16hi_to_f(u.z); acc8[6] += bf16lo_to_f(u.w); acc8[7] += bf16hi_to_f(u.w);
+              }
+#pragma unroll
+              for (int j = 0; j < 8; j++) h[8 * kb + j] = acc8[j];
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&st_empty[jn & 1]);
           }
           float pn = 0.f;
 #pragma unroll
@@ -617,6 +654,16 @@ k_nmf_tcs(Params p, const __grid_constant__ CUtensorMap tmap1, const __grid_cons
           const int b = 128 * tile + r;
           float a[K]; // [0,K2) w^2, [K2,K) w of this warpgroup's components
           float mx = 0.f;
+          float wold[K2]; // old W of this bin = hi + mid + lo of the job's stationary tile
+          {
+            const unsigned short* stt = reinterpret_cast<const unsigned short*>(smem + C::OFF_ST + (jn & 1) * C::TILE);
+#pragma unroll
+            for (int j = 0; j < K2; j++)
+              wold[j] = bf16_bits_to_f(stt[op_index_w<K>(2, k0 + j, r)]) + bf16_bits_to_f(stt[op_index_w<K>(1, k0 + j, r)]) +
+                        bf16_bits_to_f(stt[op_index_w<K>(0, k0 + j, r)]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&st_empty[jn & 1]);
+          }
 #pragma unroll
           for (int j4 = 0; j4 < K2 / 4; j4++) {
             const int jj = k0 / 4 + j4;
@@ -626,7 +673,7 @@ k_nmf_tcs(Params p, const __grid_constant__ CUtensorMap tmap1, const __grid_cons
 #pragma unroll
             for (int i = 0; i < 4; i++) {
               const int k = k0 + 4 * j4 + i;
-              const float w = gW[(int64_t) k * Bp + b] * num[i] / fmaxf(f_wden[k], kEps);
+              const float w = wold[4 * j4 + i] * num[i] / fmaxf(f_wden[k], kEps);
               gW[(int64_t) k * Bp + b] = w;
               a[4 * j4 + i] = w * w;
               a[K2 + 4 * j4 + i] = w;

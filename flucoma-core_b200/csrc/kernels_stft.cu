@@ -55,17 +55,19 @@ __global__ void __launch_bounds__(256) k_frame_window(const float* __restrict__ 
   }
 }
 
-void launch_frame_window(Plan* p, const float* audio, int64_t n, int64_t nbuf, int64_t F, float* frames, int64_t half)
+void launch_frame_window(Plan* p, const float* audio, int64_t n, int64_t nbuf, int64_t F, float* frames, int64_t half,
+                         int hop_override)
 {
   int64_t total = nbuf * F * (int64_t) (p->fft / 4);
   if (total <= 0) return;
+  const int hop = hop_override > 0 ? hop_override : p->hop;
   int grid = (int) std::min<int64_t>((total + 255) / 256, (int64_t) p->sm_count * 32);
-  const bool vec = (p->hop % 4 == 0) && (half % 4 == 0) && (n % 4 == 0) && (p->win % 4 == 0) &&
+  const bool vec = (hop % 4 == 0) && (half % 4 == 0) && (n % 4 == 0) && (p->win % 4 == 0) &&
                    (reinterpret_cast<uintptr_t>(audio) % 16 == 0);
   if (vec)
-    k_frame_window<true><<<grid, 256, 0, p->stream>>>(audio, n, nbuf, F, p->window.as<float>(), p->win, p->fft, p->hop, half, frames);
+    k_frame_window<true><<<grid, 256, 0, p->stream>>>(audio, n, nbuf, F, p->window.as<float>(), p->win, p->fft, hop, half, frames);
   else
-    k_frame_window<false><<<grid, 256, 0, p->stream>>>(audio, n, nbuf, F, p->window.as<float>(), p->win, p->fft, p->hop, half, frames);
+    k_frame_window<false><<<grid, 256, 0, p->stream>>>(audio, n, nbuf, F, p->window.as<float>(), p->win, p->fft, hop, half, frames);
   p->launches++;
 }
 
@@ -291,6 +293,31 @@ __global__ void __launch_bounds__(256) k_ola(const float* __restrict__ y, int64_
     float r = stream_norm ? (acc != 0.f ? acc / (nrm > 0.f ? nrm : 1.f) : acc) : acc / fmaxf(nrm, kEps);
     out[s * out_stride + t] = r;
   }
+}
+
+// ISTFT::processFrame (STFT.hpp:201-208) for every frame of every component: y [K][F][fft] (cuFFT C2R output) ->
+// out [F][K][win] = y[k][f][0:win] * window / fft, the frames a FluidSink overlap-adds (BufferedProcess.hpp:208-216)
+__global__ void __launch_bounds__(256) k_window_frames(const float* __restrict__ y, int64_t K, int64_t F,
+                                                       const float* __restrict__ window, int win, int fft,
+                                                       float* __restrict__ out)
+{
+  const int64_t total = K * F * win;
+  const float scale = 1.0f / (float) fft;
+  for (int64_t e = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; e < total; e += (int64_t) gridDim.x * blockDim.x) {
+    const int j = (int) (e % win);
+    const int64_t fk = e / win;
+    const int64_t k = fk % K, f = fk / K;
+    out[e] = y[(k * F + f) * fft + j] * scale * window[j];
+  }
+}
+
+void launch_window_frames(Plan* p, const float* y, int64_t K, int64_t F, float* out)
+{
+  const int64_t total = K * F * p->win;
+  if (total <= 0) return;
+  int grid = (int) std::min<int64_t>((total + 255) / 256, (int64_t) p->sm_count * 32);
+  k_window_frames<<<grid, 256, 0, p->stream>>>(y, K, F, p->window.as<float>(), p->win, p->fft, out);
+  p->launches++;
 }
 
 void launch_ola(Plan* p, const float* y, int64_t nsig, int64_t F, int64_t n, float* out, int64_t half, int64_t out_stride,

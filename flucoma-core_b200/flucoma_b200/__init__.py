@@ -66,6 +66,12 @@ class FilterArgs(C.Structure):
                 ("out", C.c_void_p), ("acts_out", C.c_void_p)]
 
 
+class FilterFramesArgs(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("mem", C.c_int32), ("frames", C.c_int64), ("rank", C.c_int32),
+                ("iterations", C.c_int32), ("seed", C.c_int64), ("in_", C.c_void_p), ("bases", C.c_void_p),
+                ("out", C.c_void_p), ("acts_out", C.c_void_p)]
+
+
 class BufStftArgs(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("mem", C.c_int32), ("invert", C.c_int32), ("padding_mode", C.c_int32),
                 ("batch", C.c_int64), ("n_samples", C.c_int64), ("frames", C.c_int64), ("audio", C.c_void_p),
@@ -83,7 +89,7 @@ class Stats(C.Structure):
 SYMBOLS = ["fb200_abi_version", "fb200_device_count", "fb200_plan_create", "fb200_plan_destroy", "fb200_last_error",
            "fb200_num_frames", "fb200_resolve_fft", "fb200_shard_range", "fb200_stft", "fb200_istft",
            "fb200_nmf_process", "fb200_nmf_process_frames", "fb200_bufnmf", "fb200_nmf_filter", "fb200_get_stats",
-           "fb200_get_api", "fb200_selftest_tcgen05", "fb200_bufstft_sizes", "fb200_bufstft"]
+           "fb200_get_api", "fb200_selftest_tcgen05", "fb200_bufstft_sizes", "fb200_bufstft", "fb200_nmf_filter_frames"]
 
 _lib = None
 
@@ -123,7 +129,8 @@ def load(path: str | None = None):
     L.fb200_istft.restype = C.c_int32
     L.fb200_istft.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_int32]
     for name, T in (("fb200_nmf_process", NmfArgs), ("fb200_nmf_process_frames", FramesArgs),
-                    ("fb200_bufnmf", BufNmfArgs), ("fb200_nmf_filter", FilterArgs), ("fb200_bufstft", BufStftArgs)):
+                    ("fb200_bufnmf", BufNmfArgs), ("fb200_nmf_filter", FilterArgs), ("fb200_bufstft", BufStftArgs),
+                    ("fb200_nmf_filter_frames", FilterFramesArgs)):
         fn = getattr(L, name)
         fn.restype = C.c_int32
         fn.argtypes = [C.c_void_p, C.POINTER(T)]
@@ -444,4 +451,18 @@ class Plan:
         a = FilterArgs(C.sizeof(FilterArgs), DEVICE if self._dev(a_in) else HOST, n, K, iterations, seed, _ptr(a_in),
                        _ptr(W), _ptr(out), _ptr(acts))
         self._check(self._L.fb200_nmf_filter(self._h, C.byref(a)))
+        return out, acts
+
+    def nmf_filter_frames(self, frames, bases, iterations=10, seed=-1, want_out=True, want_acts=True):
+        """frames float32 [nf][win] (raw, as FluidSource::pull cuts them) + bases [K][bins] -> (out [nf][K][win] | None,
+        acts [nf][K] | None): the per-frame body of NMFFilterClient / NMFMatchClient (fb200_nmf_filter_frames)."""
+        x = self._contig(frames); W = self._contig(bases)
+        assert x.ndim == 2 and x.shape[1] == self.win and _dtype_code(x) == F32 and _dtype_code(W) == F32
+        nf, K = x.shape[0], W.shape[0]
+        assert W.shape[1] == self.bins
+        out = self._empty_like_space(x, (nf, K, self.win), "float32") if want_out else None
+        acts = self._empty_like_space(x, (nf, K), "float32") if want_acts else None
+        a = FilterFramesArgs(C.sizeof(FilterFramesArgs), DEVICE if self._dev(x) else HOST, nf, K, iterations, seed, _ptr(x),
+                             _ptr(W), _ptr(out), _ptr(acts))
+        self._check(self._L.fb200_nmf_filter_frames(self._h, C.byref(a)))
         return out, acts

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define FB200_ABI_VERSION 1u
+#define FB200_ABI_VERSION 2u
 
 #if defined(_WIN32)
 #define FB200_API __declspec(dllexport)
@@ -196,6 +196,27 @@ typedef struct fb200_filter_args {
 } fb200_filter_args;
 FB200_API int32_t fb200_nmf_filter(fb200_plan* plan, const fb200_filter_args* args);
 
+/* ---- the per-frame body of NMFFilter / NMFMatch for frames a host-side BufferedProcess has cut ------------------------ */
+/* For hosts that keep the reference's streaming structure (FluidSource / FluidSink ring buffers on the audio thread's
+ * side, clients/common/BufferedProcess.hpp:49-93) and hand the frames that fall due to the device in one batch:
+ * in [frames][win] are raw time-domain frames exactly as FluidSource::pull delivers them (FluidSource.hpp:68-89); every
+ * frame goes through STFT::processFrame (window, rFFT; STFT.hpp:110-118), STFT::magnitude, NMF::processFrame (NMF.hpp:45-89)
+ * and, when `out` is given, NMF::estimate + RatioMask::process per component and ISTFT::processFrame (STFT.hpp:201-208):
+ * out [frames][rank][win] are the windowed time-domain frames a FluidSink overlap-adds (the Normalise channel window^2 is
+ * host-side data, BufferedProcess.hpp:219-224).  acts_out [frames][rank] are the activations (NMFMatch). */
+typedef struct fb200_filter_frames_args {
+  uint32_t struct_size;
+  int32_t mem;
+  int64_t frames;
+  int32_t rank, iterations;     /* NMFMatch hard-codes 10 (NMFMatchClient.hpp:115) */
+  int64_t seed;                 /* >= 0: the same h0 for every frame; < 0: fresh draws per frame (statistically equivalent) */
+  const float* in;              /* [frames][win] */
+  const float* bases;           /* [rank][bins] */
+  float* out;                   /* optional [frames][rank][win] */
+  float* acts_out;              /* optional [frames][rank] */
+} fb200_filter_frames_args;
+FB200_API int32_t fb200_nmf_filter_frames(fb200_plan* plan, const fb200_filter_frames_args* args);
+
 /* ---- BufSTFT: BufferSTFTClient::processFwd / processInverse  (clients/nrt/BufSTFTClient.hpp:82-190, 192-279) ----- */
 /* Size rules of the client.  padding = FFTParams::padding (clients/common/ParameterTypes.hpp:315-323): mode 0 -> 0,
  * 1 -> win/2, 2 -> win-hop.  Forward (invert = 0, count = samples): padded = count + 2*padding, rounded up to a multiple of
@@ -256,6 +277,7 @@ typedef struct fb200_api {
   int32_t (*get_stats)(const fb200_plan*, fb200_stats*);
   int32_t (*bufstft_sizes)(int32_t, int32_t, int32_t, int32_t, int64_t, int64_t*, int64_t*);
   int32_t (*bufstft)(fb200_plan*, const fb200_bufstft_args*);
+  int32_t (*nmf_filter_frames)(fb200_plan*, const fb200_filter_frames_args*);
 } fb200_api;
 /* returns NULL when abi_version is not supported */
 FB200_API const fb200_api* fb200_get_api(uint32_t abi_version);

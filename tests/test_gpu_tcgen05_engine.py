@@ -141,7 +141,7 @@ def test_tc_engine_async_cancel_finishes_the_iteration_in_flight(fb):
     torch = pytest.importorskip("torch")
     rng = np.random.default_rng(8)
     X1 = lowrank(rng, 1, 384, 257).astype(np.float32)
-    copies, iters = 5 * 148, 24
+    copies, iters = 10 * 148, 24
     X = torch.from_numpy(X1).cuda().expand(copies, -1, -1).contiguous()
     seeds = np.full(copies, 3, dtype=np.int64)
     with fb.Plan(win=64, backend=fb.BACKEND_TCGEN05) as plan:
@@ -149,14 +149,17 @@ def test_tc_engine_async_cancel_finishes_the_iteration_in_flight(fb):
         for j in range(iters + 1):
             Wj, Hj, _, _ = plan.nmf_process(X[:1], 16, j, True, True, seeds=seeds[:1], want_v=False)
             table.append((Wj[0].clone(), Hj[0].clone()))
-        calls = []
-        W, H, V, st = plan.nmf_process(X, 16, iters, True, True, seeds=seeds, want_v=True,
-                                       progress=lambda it: calls.append(it) or it < 5, progress_stride=fb.PROGRESS_ASYNC)
-    assert st == fb.CANCELLED and calls == [1, 2, 3, 4, 5]
-    assert bool((V == X).all())                      # NMF.hpp:175-176
-    at = []
-    for b in range(copies):
-        hit = [j for j, (Wj, Hj) in enumerate(table) if bool((W[b] == Wj).all()) and bool((H[b] == Hj).all())]
-        assert hit, f"buffer {b} is not at any completed iteration"
-        at.append(hit[0])
-    assert min(at) < iters, "the cancel arrived after everything had finished: nothing was tested"
+        for attempt in range(3):  # the cancel races with a ~5 ms kernel: retry if the host thread was descheduled past its end
+            calls = []
+            W, H, V, st = plan.nmf_process(X, 16, iters, True, True, seeds=seeds, want_v=True,
+                                           progress=lambda it: calls.append(it) or it < 3, progress_stride=fb.PROGRESS_ASYNC)
+            assert st == fb.CANCELLED and calls == [1, 2, 3]
+            assert bool((V == X).all())                      # NMF.hpp:175-176
+            at = []
+            for b in range(copies):
+                hit = [j for j, (Wj, Hj) in enumerate(table) if bool((W[b] == Wj).all()) and bool((H[b] == Hj).all())]
+                assert hit, f"buffer {b} is not at any completed iteration"
+                at.append(hit[0])
+            if min(at) < iters:
+                break
+    assert min(at) < iters, "the cancel arrived after everything had finished in three attempts"
