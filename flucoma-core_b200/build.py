@@ -48,7 +48,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
                     raise RuntimeError("nvcc failed: " + " ".join(cmd))
     if jobs or force or _stale(LIB, objs):
         cmd = [NVCC] + ARCH + ["-shared", "-ccbin", "/usr/bin/g++", "-o", LIB] + objs + \
-              ["-lcufft", "-Xlinker", "-rpath,/usr/local/cuda/lib64"]
+              ["-lcufft", "-ldl", "-Xlinker", "-rpath,/usr/local/cuda/lib64"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)

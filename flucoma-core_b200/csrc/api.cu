@@ -133,10 +133,17 @@ int32_t run_stft(Plan* p, const float* d_audio, int64_t batch, int64_t n, int64_
     FB_CUDA(p, p->spec.ensure(sizeof(float2) * (size_t) (wave * F * B)));
     spec_wave = p->spec.as<float2>();
   }
+  const int hop_eff = hop_override > 0 ? hop_override : p->hop;
+  const bool fused = stft_fused_eligible(p, d_audio, n, std::min(wave, batch), hop_eff);
   size_t wi = 0;
   for (int64_t b0 = 0; b0 < batch; b0 += wave, wi++) {
     int64_t nb = std::min(wave, batch - b0);
     if (h_audio) FB_CUDA(p, cudaStreamWaitEvent(p->stream, p->cev[wi], 0));
+    if (fused) { // one kernel from samples to |X| (and the complex spectrum when it is kept); TMA in, no intermediates
+      FB_TRY(launch_stft_fused(p, d_audio + b0 * n, nb, n, F, V ? V + b0 * Fp * Bp : nullptr, Fp, Bp,
+                               spec_all ? spec_all + b0 * F * B : nullptr, half, hop_eff));
+      continue;
+    }
     launch_frame_window(p, d_audio + b0 * n, n, nb, F, p->frames.as<float>(), half, hop_override);
     cufftHandle h;
     FB_TRY(get_fft_plan(p, CUFFT_R2C, nb * F, &h));
@@ -268,7 +275,8 @@ void simt_run_iters(Plan* p, NmfDev& d, int n, bool upd_w, bool upd_h)
 // in DEVICE memory (a first version kept them in host-mapped memory: 148 CTAs sampling a sysmem word once per pass were
 // serialised on the PCIe read path and doubled the step time); the calling thread reads the per-CTA pass counters with
 // small copies on the plan's copy stream while the kernel runs, reports iterations 1..n (each exactly once, in order) as
-// the batch advances, and raises the cancel word with another small copy when a callback returns 0.  See `Ctl`.
+// the batch advances, and raises a cancel word in host-mapped memory when a callback returns 0 (CTA 0 relays it into the
+// device word all CTAs sample).  See `Ctl`.
 int32_t run_tc_async(Plan* p, NmfDev& d, int iters, bool upd_w, bool upd_h, fb200_progress_fn progress, void* user)
 {
   const int grid = tc_grid(p, d);
@@ -278,7 +286,10 @@ int32_t run_tc_async(Plan* p, NmfDev& d, int iters, bool upd_w, bool upd_h, fb20
   unsigned int* dev = p->ctrl_dev.as<unsigned int>();
   FB_CUDA(p, cudaMemsetAsync(dev, 0, sizeof(unsigned int) * 1025, p->stream));
   if (!p->ev_async) FB_CUDA(p, cudaEventCreateWithFlags(&p->ev_async, cudaEventDisableTiming));
-  FB_TRY(tc_run(p, d, iters, upd_w, upd_h, dev));
+  host[1024] = 0u; // the cancel request: written by this thread, read by CTA 0 through the mapping below
+  unsigned int* host_dev = nullptr;
+  FB_CUDA(p, cudaHostGetDevicePointer(reinterpret_cast<void**>(&host_dev), host, 0));
+  FB_TRY(tc_run(p, d, iters, upd_w, upd_h, dev, host_dev + 1024));
   FB_CUDA(p, cudaEventRecord(p->ev_async, p->stream));
   const int64_t npass = (upd_w && upd_h) ? iters + 1 : iters;
   const int64_t total = (int64_t) d.batch * npass;
@@ -288,8 +299,10 @@ int32_t run_tc_async(Plan* p, NmfDev& d, int iters, bool upd_w, bool upd_h, fb20
     while (!cancelled && reported < it) {
       if (!progress(user, ++reported)) {
         cancelled = true;
-        host[1024] = 1u;
-        FB_CUDA(p, cudaMemcpyAsync(dev, host + 1024, sizeof(unsigned int), cudaMemcpyHostToDevice, p->copy_stream));
+        // a plain store into pinned, device-mapped memory.  (A 4-byte cudaMemcpyAsync looked equivalent but is executed
+        // by a helper kernel, which cannot be scheduled while the persistent CTAs own every SM: the request arrived
+        // after the launch had finished.)
+        *reinterpret_cast<volatile unsigned int*>(host + 1024) = 1u;
       }
     }
     return FB200_OK;
@@ -495,7 +508,7 @@ void fb200_plan_destroy(fb200_plan* p)
   if (p->stream) cudaStreamSynchronize(p->stream);
   for (auto& kv : p->fft_plans) cufftDestroy(kv.second);
   DevBuf* bufs[] = {&p->window, &p->audio, &p->stage, &p->frames, &p->spec, &p->cspec, &p->V, &p->W, &p->H, &p->hden,
-                    &p->wnum_part, &p->wden_part, &p->rnd, &p->seeds, &p->scale, &p->out_a, &p->out_b, &p->ctrl_dev, &p->wop_buf, &p->hop_buf};
+                    &p->wnum_part, &p->wden_part, &p->rnd, &p->seeds, &p->scale, &p->out_a, &p->out_b, &p->ctrl_dev, &p->wop_buf, &p->hop_buf, &p->twiddle, &p->x0, &p->x1, &p->x2, &p->x3, &p->x4, &p->x5};
   for (auto* b : bufs) b->release();
   p->pin_a.release(); p->pin_b.release(); p->ctrl.release();
   if (p->ev_async) cudaEventDestroy(p->ev_async);
@@ -983,6 +996,143 @@ int32_t fb200_nmf_filter_frames(fb200_plan* p, const fb200_filter_frames_args* a
   return FB200_OK;
 }
 
+// GriffinLim::process (GriffinLim.hpp:29-54) on one spectrogram spec[F][B], in place.  Work arrays: x1 (phase), x2 (mag),
+// x4 / x5 (estimate / previous estimate), cspec (mag * phase, consumed by the inverse transform), audio (time signal).
+static int32_t run_griffinlim(Plan* p, float2* spec, int64_t F, int64_t n, int iters, int64_t seed)
+{
+  const int64_t B = p->bins, cnt = F * B;
+  bool neg = false;
+  FB_TRY(upload_seeds(p, &seed, 1, &neg));
+  FB_CUDA(p, p->rnd.ensure(sizeof(float) * (size_t) cnt));
+  launch_mt_uniform(p, p->seeds.as<int64_t>(), 1, cnt, p->rnd.as<float>());
+  FB_CUDA(p, p->x1.ensure(sizeof(float2) * (size_t) cnt));
+  FB_CUDA(p, p->x2.ensure(sizeof(float) * (size_t) cnt));
+  FB_CUDA(p, p->x4.ensure(sizeof(float2) * (size_t) cnt));
+  FB_CUDA(p, p->x5.ensure(sizeof(float2) * (size_t) cnt));
+  FB_CUDA(p, p->cspec.ensure(sizeof(float2) * (size_t) cnt));
+  FB_CUDA(p, p->audio.ensure(sizeof(float) * (size_t) n));
+  float2* phase = p->x1.as<float2>();
+  float* mag = p->x2.as<float>();
+  float2* est = p->x4.as<float2>();
+  float2* prev = p->x5.as<float2>();
+  launch_gl_init(p, spec, p->rnd.as<float>(), (int) F, (int) B, mag, phase);                  // :39-41
+  FB_CUDA(p, cudaMemsetAsync(est, 0, sizeof(float2) * (size_t) cnt, p->stream));              // :42-43
+  for (int i = 0; i < iters; i++) {                                                            // :44-52
+    std::swap(est, prev);                                                                      // prev = estimate
+    launch_gl_apply(p, mag, phase, cnt, p->cspec.as<float2>());                                // magnitude * phase
+    FB_TRY(run_istft(p, p->cspec.as<float2>(), 1, F, n, p->audio.as<float>(), p->win / 2));
+    FB_TRY(run_stft(p, p->audio.as<float>(), 1, n, F, nullptr, F, B, est, p->win / 2));
+    launch_gl_phase(p, est, prev, cnt, phase);
+  }
+  launch_gl_apply(p, mag, phase, cnt, spec);                                                   // :53
+  return FB200_OK;
+}
+
+// BufNMFCross: NMFCrossClient::process (clients/nrt/NMFCrossClient.hpp:85-185), channel 0 of source and target.
+int32_t fb200_bufnmfcross(fb200_plan* p, const fb200_nmfcross_args* a)
+{
+  if (!p) return FB200_ERR_INVALID;
+  if (!a || a->struct_size != sizeof(fb200_nmfcross_args) || !a->source || !a->target || (!a->out && !a->acts_out) ||
+      a->iterations < 1 || a->time_sparsity < 1 || a->polyphony < 1 || a->continuity < 1 || a->griffinlim_iterations < 0) {
+    p->err = "fb200_bufnmfcross: bad arguments";
+    return FB200_ERR_INVALID;
+  }
+  if (a->n_source <= 0) { p->err = "Empty source buffer"; return FB200_ERR_INVALID; }               // :110
+  if (a->n_target <= 0) { p->err = "Empty target buffer"; return FB200_ERR_INVALID; }               // :112
+  const int64_t ns = a->n_source, nt = a->n_target, B = p->bins;
+  const int64_t Fs = fb200_num_frames(ns, p->win, p->hop), Ft = fb200_num_frames(nt, p->win, p->hop); // :103-108
+  if (a->time_sparsity > Ft) { p->err = "Time Sparsity is larger than target frames"; return FB200_ERR_INVALID; } // :114-116
+  if (a->continuity > Ft) { p->err = "Continuity is larger than target frames"; return FB200_ERR_INVALID; }       // :117-119
+  FB_TRY(enter(p, a->mem));
+  StageTimer t(p);
+  t.mark(0);
+  const int host = a->mem == FB200_HOST;
+  const int64_t R = Fs;                                                                           // rank = source frames (:140)
+  const int poly = (int) std::min<int64_t>(Fs, a->polyphony);                                     // :160
+  const void* raw;
+  FB_TRY(to_device_raw(p, a->source, a->mem, sizeof(float) * (size_t) ns, p->audio, &raw));
+  const float* d_src = (const float*) raw;
+  FB_TRY(to_device_raw(p, a->target, a->mem, sizeof(float) * (size_t) nt, p->stage, &raw));
+  const float* d_tgt = (const float*) raw;
+  t.mark(1);
+  // source: spectrum S[R][B] (kept for the resynthesis) and W = |S|; target: V = |T|   (:134-139)
+  FB_CUDA(p, p->spec.ensure(sizeof(float2) * (size_t) (Fs * B)));
+  FB_CUDA(p, p->W.ensure(sizeof(float) * (size_t) (R * B)));
+  FB_CUDA(p, p->V.ensure(sizeof(float) * (size_t) (Ft * B)));
+  FB_CUDA(p, p->cspec.ensure(sizeof(float2) * (size_t) (Ft * B)));
+  FB_TRY(run_stft(p, d_src, 1, ns, Fs, p->W.as<float>(), Fs, B, p->spec.as<float2>(), p->win / 2));
+  FB_TRY(run_stft(p, d_tgt, 1, nt, Ft, p->V.as<float>(), Ft, B, p->cspec.as<float2>(), p->win / 2));
+  t.mark(2);
+  // NMFCross::process (:60-76): H = U(R x F) column-major == H[F][R] in storage order; W clamped at eps
+  FB_CUDA(p, p->hden.ensure(sizeof(float) * (size_t) (2 * R)));
+  float* energy = p->hden.as<float>();
+  float* hden = energy + R;
+  launch_cross_prepare(p, p->W.as<float>(), (int) R, (int) B, energy, hden);                      // :156-159, :169
+  FB_CUDA(p, p->x0.ensure(sizeof(float) * (size_t) (Ft * R)));
+  FB_CUDA(p, p->x1.ensure(sizeof(float) * (size_t) (Ft * R)));
+  FB_CUDA(p, p->x2.ensure(sizeof(float) * (size_t) (Ft * B)));
+  float* H = p->x0.as<float>();
+  float* T1 = p->x1.as<float>();
+  float* ratio = p->x2.as<float>();
+  {
+    bool neg = false;
+    int64_t seed = a->seed;
+    FB_TRY(upload_seeds(p, &seed, 1, &neg));
+    launch_mt_uniform(p, p->seeds.as<int64_t>(), 1, R * Ft, H);                                    // :72-73
+  }
+  t.mark(3);
+  p->backend_used = FB200_BACKEND_SIMT;
+  bool cancelled = false;
+  for (int i = 0; i < a->iterations && !cancelled; i++) {                                          // :160-176
+    // 1 - ((i + 1) / iterations) in INTEGER arithmetic (:119, :136): 1 until the last iteration, 0 in the last
+    const float factor = 1.0f - (float) ((i + 1) / a->iterations);
+    if (factor != 1.0f) {
+      launch_cross_sparseness(p, H, T1, (int) Ft, (int) R, a->time_sparsity, factor);              // :163
+      launch_cross_polyphony(p, T1, H, (int) Ft, (int) R, energy, poly, factor);                   // :164
+    }
+    launch_cross_continuity(p, H, T1, (int) Ft, (int) R, a->continuity);                           // :165
+    launch_cross_ratio(p, T1, p->W.as<float>(), p->V.as<float>(), ratio, (int) Ft, (int) B, (int) R);          // :167-168
+    launch_cross_update(p, ratio, p->W.as<float>(), T1, H, hden, (int) Ft, (int) B, (int) R);      // :168-170
+    if (a->progress) {
+      FB_CUDA(p, cudaStreamSynchronize(p->stream));
+      if (!a->progress(a->progress_user, i + 1)) cancelled = true;                                 // :174-175
+    }
+  }
+  t.mark(4);
+  if (cancelled) {
+    FB_TRY(finish(p, t, 4));
+    return FB200_CANCELLED;
+  }
+  if (a->acts_out) {
+    float* dst = a->acts_out;
+    const size_t bytes = sizeof(float) * (size_t) (Ft * R);
+    if (host) FB_CUDA(p, cudaMemcpyAsync(dst, H, bytes, cudaMemcpyDeviceToHost, p->stream));
+    else FB_CUDA(p, cudaMemcpyAsync(dst, H, bytes, cudaMemcpyDeviceToDevice, p->stream));
+  }
+  if (a->out) {
+    // NMFCross::synthesize (:50-58): result[F][B] = H[F][R] * S[R][B]; S complex == [R][2B] real
+    FB_CUDA(p, p->x3.ensure(sizeof(float2) * (size_t) (Ft * B)));
+    launch_sgemm_nn(p, H, reinterpret_cast<const float*>(p->spec.p), p->x3.as<float>(), (int) Ft, (int) (2 * B), (int) R);
+    if (a->progress && !a->progress(a->progress_user, a->iterations + 1)) cancelled = true;        // :168-169
+    if (!cancelled) {
+      FB_TRY(run_griffinlim(p, p->x3.as<float2>(), Ft, nt, a->griffinlim_iterations, a->seed));    // :171-173
+      if (a->progress && !a->progress(a->progress_user, a->iterations + 2)) cancelled = true;
+    }
+    if (!cancelled) {
+      float* d_out = a->out;
+      if (host) { FB_CUDA(p, p->out_a.ensure(sizeof(float) * (size_t) nt)); d_out = p->out_a.as<float>(); }
+      FB_TRY(run_istft(p, p->x3.as<float2>(), 1, Ft, nt, d_out, p->win / 2));                      // :178
+      if (host) FB_CUDA(p, cudaMemcpyAsync(a->out, d_out, sizeof(float) * (size_t) nt, cudaMemcpyDeviceToHost, p->stream));
+      if (a->progress && !a->progress(a->progress_user, a->iterations + 3)) cancelled = true;
+    }
+  }
+  t.mark(5);
+  FB_TRY(finish(p, t, 5));
+  p->stats.ms_h2d = t.ms(0, 1); p->stats.ms_stft = t.ms(1, 2); p->stats.ms_init = t.ms(2, 3); p->stats.ms_nmf = t.ms(3, 4);
+  p->stats.ms_resynth = t.ms(4, 5);
+  return cancelled ? FB200_CANCELLED : FB200_OK;
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 int32_t fb200_bufstft_sizes(int32_t win, int32_t hop, int32_t padding_mode, int32_t invert, int64_t count, int64_t* padding,
                             int64_t* out)
@@ -1109,7 +1259,7 @@ const fb200_api* fb200_get_api(uint32_t abi_version)
                                 fb200_plan_destroy, fb200_last_error, fb200_num_frames, fb200_resolve_fft,
                                 fb200_shard_range, fb200_stft, fb200_istft, fb200_nmf_process, fb200_nmf_process_frames,
                                 fb200_bufnmf, fb200_nmf_filter, fb200_get_stats, fb200_bufstft_sizes, fb200_bufstft,
-                                fb200_nmf_filter_frames};
+                                fb200_nmf_filter_frames, fb200_bufnmf_sharded, fb200_bufnmfcross};
   return abi_version == FB200_ABI_VERSION ? &api : nullptr;
 }
 

@@ -35,6 +35,18 @@ struct DevBuf {
     if (e == cudaSuccess) cap = bytes;
     return e;
   }
+  // grow without losing the first `keep` bytes
+  cudaError_t ensure_keep(size_t bytes, size_t keep)
+  {
+    if (bytes <= cap) return cudaSuccess;
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, bytes);
+    if (e != cudaSuccess) return e;
+    if (p && keep) e = cudaMemcpy(q, p, keep < cap ? keep : cap, cudaMemcpyDeviceToDevice);
+    if (p) cudaFree(p);
+    p = q; cap = bytes;
+    return e;
+  }
   void release()
   {
     if (p) cudaFree(p);
@@ -106,6 +118,8 @@ struct Plan {
   HostBuf pin_a, pin_b;
   HostBuf ctrl;    // pinned read-back of the progress counters of the asynchronous progress mode
   DevBuf ctrl_dev; // device control words: [0] cancel request, [1 + cta] finished (buffer, pass) units
+  DevBuf twiddle;  // float2 [fft/2 + fft/2 + 1] twiddles of the fused STFT kernel
+  DevBuf x0, x1, x2, x3, x4, x5; // BufNMFCross / Griffin-Lim work arrays
   DevBuf wop_buf, hop_buf; // split-bf16 operand copies of W / H for the streamed tensor-core engine
   std::map<std::pair<int, int64_t>, cufftHandle> fft_plans; // (type, batch) -> handle, bounded LRU
   std::map<std::pair<int, int64_t>, uint64_t> fft_lru;
@@ -181,6 +195,24 @@ void launch_mask(Plan* p, const NmfDev& d, const float2* spec, int64_t b0, int64
 void launch_ola(Plan* p, const float* y, int64_t nsig, int64_t F, int64_t n, float* out, int64_t half, int64_t out_stride,
                 int stream_norm);
 
+// kernels_stft_fused.cu -----------------------------------------------------------------------------------------
+bool stft_fused_eligible(const Plan* p, const float* audio, int64_t n, int64_t batch, int hop);
+// audio [batch][n] -> V[batch][Fp][Bp] magnitudes (may be null) and/or spec [batch][F][B] (may be null); one kernel
+int32_t launch_stft_fused(Plan* p, const float* audio, int64_t batch, int64_t n, int64_t F, float* V, int64_t Fp, int64_t Bp,
+                          float2* spec, int64_t half, int hop);
+
+// kernels_cross.cu (BufNMFCross: NMFCross.hpp:60-185, GriffinLim.hpp:29-54) -----------------------------------------
+void launch_sgemm_nn(Plan* p, const float* A, const float* B, float* C, int M, int N, int K); // C[M][N] = A[M][K] B[K][N]
+void launch_cross_prepare(Plan* p, float* W, int R, int B, float* energy, float* hden);
+void launch_cross_ratio(Plan* p, const float* H, const float* W, const float* V, float* ratio, int F, int B, int R);
+void launch_cross_update(Plan* p, const float* ratio, const float* W, const float* H_in, float* H_out, const float* hden, int F, int B, int R);
+void launch_cross_sparseness(Plan* p, const float* H, float* out, int F, int R, int size, float factor);
+void launch_cross_polyphony(Plan* p, const float* H, float* out, int F, int R, const float* energy, int poly, float factor);
+void launch_cross_continuity(Plan* p, const float* H, float* out, int F, int R, int size);
+void launch_gl_init(Plan* p, const float2* spec, const float* U, int F, int B, float* mag, float2* phase);
+void launch_gl_apply(Plan* p, const float* mag, const float2* phase, int64_t total, float2* out);
+void launch_gl_phase(Plan* p, const float2* est, const float2* prev, int64_t total, float2* phase);
+
 // kernels_tc_selftest.cu ---------------------------------------------------------------------------------------
 int32_t make_v_tensor_map(Plan* p, void* tmap_out, const float* V, int64_t Bp, int64_t Fp, int64_t batch, int box_rows);
 int32_t run_tc_selftest(Plan* p, const float* in, float* out);
@@ -189,11 +221,14 @@ int32_t run_tc_mma_timing(Plan* p, long long* d_out, int reps);
 // kernels_nmf_tc.cu ---------------------------------------------------------------------------------------------
 bool tc_eligible(const NmfDev& d);
 // ctrl != nullptr: device control words (ctrl[0] cancel request, ctrl[1 + cta] finished passes), see Ctl in the .cu
-int32_t tc_run(Plan* p, const NmfDev& d, int iters, bool upd_w, bool upd_h, unsigned int* ctrl = nullptr);
+int32_t tc_run(Plan* p, const NmfDev& d, int iters, bool upd_w, bool upd_h, unsigned int* ctrl = nullptr,
+               const unsigned int* host_cancel = nullptr);
 int tc_grid(const Plan* p, const NmfDev& d);
 
 // kernels_nmf_tcs.cu --------------------------------------------------------------------------------------------
 bool tcs_eligible(const NmfDev& d);
 int32_t tcs_run(Plan* p, const NmfDev& d, int iters, bool upd_w, bool upd_h);
+// kernels_nmf_tcr.cu: rank 16 with the stationary operand in TMEM (tcs_run dispatches to it)
+int32_t tcr_run(Plan* p, const NmfDev& d, int iters, bool upd_w, bool upd_h);
 
 } // namespace fb200

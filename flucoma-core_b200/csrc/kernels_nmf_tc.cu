@@ -135,7 +135,8 @@ struct Sched {
 };
 
 // Asynchronous progress / cancel (fb200_nmf_args.progress_stride == FB200_PROGRESS_ASYNC; NMFClient.hpp:261-274 polls a
-// FluidTask every iteration).  `ctrl` is device memory: ctrl[0] is raised by the host (a 4-byte copy) to request a cancel,
+// FluidTask every iteration).  `ctrl` is device memory: ctrl[0] is the cancel request (the host raises a word in
+// host-mapped memory, CTA 0 relays it),
 // ctrl[1 + cta] counts the (buffer, pass) units this CTA has finished.  The TMA producer is the role that runs furthest
 // ahead, so it samples the cancel word once per pass (the load is issued one pass early: no L2 round trip on its
 // critical path) and publishes the first cancelled global pass index in shared memory; every role evaluates the same
@@ -171,7 +172,7 @@ using namespace tcn;
 
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_constant__ CUtensorMap tmap2, int iters, int upd_w, int upd_h,
-         long long* dbg, unsigned int* ctrl)
+         long long* dbg, unsigned int* ctrl, const unsigned int* host_cancel)
 {
   extern __shared__ __align__(1024) uint8_t smem[];
   __nv_bfloat16* wop = reinterpret_cast<__nv_bfloat16*>(smem + OFF_WOP);
@@ -227,7 +228,7 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
   if (warp == 0) {
     // =========================================== TMA producer ===========================================
     if (lane == 0) {
-      uint32_t n = 0, gp = 0, cancel_pre = 0;
+      uint32_t n = 0, gp = 0, cancel_pre = 0, relay_pre = 0;
       bool stop = false;
       for (int buf = blockIdx.x; buf < d.batch && !stop; buf += gridDim.x) {
         for (int pass = 0; pass < sc.npass; pass++, gp++) {
@@ -236,6 +237,12 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
             __threadfence_block();
             slot[1] = gp + 1;
             cancel_pre = *reinterpret_cast<volatile unsigned int*>(ctrl);
+            // CTA 0 relays the host's request (a word in host-mapped memory, one PCIe read per pass of ONE CTA) into the
+            // device word everybody samples; the value read now is used one pass later, like cancel_pre
+            if (blockIdx.x == 0) {
+              if (relay_pre) *reinterpret_cast<volatile unsigned int*>(ctrl) = 1u;
+              relay_pre = *reinterpret_cast<const volatile unsigned int*>(host_cancel);
+            }
           }
           const int mode = ctl.mode(sc, pass, gp);
           if (mode == PASS_STOP) { stop = true; break; }
@@ -835,7 +842,7 @@ bool tc_eligible(const NmfDev& d)
 
 int tc_grid(const Plan* p, const NmfDev& d) { return std::min(d.batch, p->sm_count); }
 
-int32_t tc_run(Plan* p, const NmfDev& d, int iters, bool upd_w, bool upd_h, unsigned int* ctrl)
+int32_t tc_run(Plan* p, const NmfDev& d, int iters, bool upd_w, bool upd_h, unsigned int* ctrl, const unsigned int* host_cancel)
 {
   alignas(64) CUtensorMap tmap1, tmap2;
   FB_TRY(make_v_tensor_map(p, &tmap1, d.V, d.Bp, d.Fp, d.batch, 128));
@@ -855,7 +862,7 @@ int32_t tc_run(Plan* p, const NmfDev& d, int iters, bool upd_w, bool upd_h, unsi
     dbg = p->out_b.as<long long>();
   }
 #endif
-  k_nmf_tc<<<grid, NTHREADS, SMEM_BYTES, p->stream>>>(d, tmap1, tmap2, iters, upd_w ? 1 : 0, upd_h ? 1 : 0, dbg, ctrl);
+  k_nmf_tc<<<grid, NTHREADS, SMEM_BYTES, p->stream>>>(d, tmap1, tmap2, iters, upd_w ? 1 : 0, upd_h ? 1 : 0, dbg, ctrl, host_cancel);
   if (dbg) {
     std::vector<long long> h(32 * 16);
     FB_CUDA(p, cudaMemcpyAsync(h.data(), dbg, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost, p->stream));

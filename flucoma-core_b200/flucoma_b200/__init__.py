@@ -72,6 +72,19 @@ class FilterFramesArgs(C.Structure):
                 ("out", C.c_void_p), ("acts_out", C.c_void_p)]
 
 
+class NmfCrossArgs(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("mem", C.c_int32), ("n_source", C.c_int64), ("n_target", C.c_int64),
+                ("time_sparsity", C.c_int32), ("polyphony", C.c_int32), ("continuity", C.c_int32), ("iterations", C.c_int32),
+                ("seed", C.c_int64), ("griffinlim_iterations", C.c_int32), ("reserved", C.c_int32), ("source", C.c_void_p),
+                ("target", C.c_void_p), ("out", C.c_void_p), ("acts_out", C.c_void_p), ("progress", PROGRESS_FN),
+                ("progress_user", C.c_void_p)]
+
+
+class ShardedArgs(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("n_devices", C.c_int32), ("plans", C.POINTER(C.c_void_p)),
+                ("job", C.POINTER(BufNmfArgs)), ("gathered_acts", C.POINTER(C.c_void_p))]
+
+
 class BufStftArgs(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("mem", C.c_int32), ("invert", C.c_int32), ("padding_mode", C.c_int32),
                 ("batch", C.c_int64), ("n_samples", C.c_int64), ("frames", C.c_int64), ("audio", C.c_void_p),
@@ -89,7 +102,7 @@ class Stats(C.Structure):
 SYMBOLS = ["fb200_abi_version", "fb200_device_count", "fb200_plan_create", "fb200_plan_destroy", "fb200_last_error",
            "fb200_num_frames", "fb200_resolve_fft", "fb200_shard_range", "fb200_stft", "fb200_istft",
            "fb200_nmf_process", "fb200_nmf_process_frames", "fb200_bufnmf", "fb200_nmf_filter", "fb200_get_stats",
-           "fb200_get_api", "fb200_selftest_tcgen05", "fb200_bufstft_sizes", "fb200_bufstft", "fb200_nmf_filter_frames"]
+           "fb200_get_api", "fb200_selftest_tcgen05", "fb200_bufstft_sizes", "fb200_bufstft", "fb200_nmf_filter_frames", "fb200_bufnmf_sharded", "fb200_bufnmfcross"]
 
 _lib = None
 
@@ -130,10 +143,12 @@ def load(path: str | None = None):
     L.fb200_istft.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_int32]
     for name, T in (("fb200_nmf_process", NmfArgs), ("fb200_nmf_process_frames", FramesArgs),
                     ("fb200_bufnmf", BufNmfArgs), ("fb200_nmf_filter", FilterArgs), ("fb200_bufstft", BufStftArgs),
-                    ("fb200_nmf_filter_frames", FilterFramesArgs)):
+                    ("fb200_nmf_filter_frames", FilterFramesArgs), ("fb200_bufnmfcross", NmfCrossArgs)):
         fn = getattr(L, name)
         fn.restype = C.c_int32
         fn.argtypes = [C.c_void_p, C.POINTER(T)]
+    L.fb200_bufnmf_sharded.restype = C.c_int32
+    L.fb200_bufnmf_sharded.argtypes = [C.POINTER(ShardedArgs)]
     L.fb200_get_stats.restype = C.c_int32
     L.fb200_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
     L.fb200_bufstft_sizes.restype = C.c_int32
@@ -453,6 +468,22 @@ class Plan:
         self._check(self._L.fb200_nmf_filter(self._h, C.byref(a)))
         return out, acts
 
+    def bufnmfcross(self, source, target, time_sparsity=7, polyphony=11, continuity=7, iterations=50, seed=-1,
+                    griffinlim_iterations=50, want_out=True, want_acts=True, progress=None):
+        """BufNMFCross (NMFCrossClient.hpp:85-185): mono float32 source [ns], target [nt] -> (out [nt] | None,
+        acts [target frames][source frames] | None, status)."""
+        s_ = self._contig(source); t_ = self._contig(target)
+        assert s_.ndim == 1 and t_.ndim == 1 and _dtype_code(s_) == F32 and _dtype_code(t_) == F32
+        ns, nt = s_.shape[0], t_.shape[0]
+        Fs, Ft = num_frames(ns, self.win, self.hop), num_frames(nt, self.win, self.hop)
+        out = self._empty_like_space(t_, (nt,), "float32") if want_out else None
+        acts = self._empty_like_space(t_, (Ft, Fs), "float32") if want_acts else None
+        cb = PROGRESS_FN(lambda user, it: int(bool(progress(it)))) if progress else PROGRESS_FN()
+        a = NmfCrossArgs(C.sizeof(NmfCrossArgs), DEVICE if self._dev(t_) else HOST, ns, nt, time_sparsity, polyphony, continuity,
+                         iterations, seed, griffinlim_iterations, 0, _ptr(s_), _ptr(t_), _ptr(out), _ptr(acts), cb, None)
+        st = self._check(self._L.fb200_bufnmfcross(self._h, C.byref(a)))
+        return out, acts, st
+
     def nmf_filter_frames(self, frames, bases, iterations=10, seed=-1, want_out=True, want_acts=True):
         """frames float32 [nf][win] (raw, as FluidSource::pull cuts them) + bases [K][bins] -> (out [nf][K][win] | None,
         acts [nf][K] | None): the per-frame body of NMFFilterClient / NMFMatchClient (fb200_nmf_filter_frames)."""
@@ -466,3 +497,36 @@ class Plan:
                              _ptr(W), _ptr(out), _ptr(acts))
         self._check(self._L.fb200_nmf_filter_frames(self._h, C.byref(a)))
         return out, acts
+
+
+def bufnmf_sharded(plans, audio, rank, iterations, seeds=None, resynth=False, gather=False, progress=None,
+                   progress_stride=PROGRESS_ASYNC):
+    """BufNMF of host audio float32 [batch][n] over several plans (one per device) in ONE call (fb200_bufnmf_sharded).
+    Returns dict(bases, acts, resynth | None, status, gathered | None); `gathered` is a list of torch tensors, one per
+    device, each [n_dev * ceil(batch / n_dev)][F][K]."""
+    L = load()
+    a_in = np.ascontiguousarray(audio, dtype=np.float32)
+    batch, n = a_in.shape
+    p0 = plans[0]
+    F, B = num_frames(n, p0.win, p0.hop), p0.bins
+    bases = np.empty((batch, rank, B), np.float32)
+    acts = np.empty((batch, F, rank), np.float32)
+    rs = np.empty((batch, rank, n), np.float32) if resynth else None
+    if seeds is None:
+        seeds = [-1] * batch
+    seeds = np.ascontiguousarray(seeds, dtype=np.int64)
+    cb = PROGRESS_FN(lambda user, it: int(bool(progress(it)))) if progress else PROGRESS_FN()
+    job = BufNmfArgs(C.sizeof(BufNmfArgs), HOST, batch, n, rank, iterations, 0, 0, _ptr(a_in), _ptr(seeds), None, None,
+                     _ptr(bases), _ptr(acts), _ptr(rs), cb, None, progress_stride, 0)
+    handles = (C.c_void_p * len(plans))(*[p._h for p in plans])
+    gathered, gptr = None, None
+    if gather:
+        import torch
+        per = (batch + len(plans) - 1) // len(plans)
+        gathered = [torch.empty((len(plans) * per, F, rank), dtype=torch.float32, device=f"cuda:{p.device}") for p in plans]
+        gptr = (C.c_void_p * len(plans))(*[g.data_ptr() for g in gathered])
+    args = ShardedArgs(C.sizeof(ShardedArgs), len(plans), handles, C.pointer(job), gptr)
+    st = L.fb200_bufnmf_sharded(C.byref(args))
+    if st < 0:
+        raise FlucomaB200Error(st, L.fb200_last_error(plans[0]._h).decode())
+    return dict(bases=bases, acts=acts, resynth=rs, status=st, gathered=gathered)

@@ -196,6 +196,50 @@ typedef struct fb200_filter_args {
 } fb200_filter_args;
 FB200_API int32_t fb200_nmf_filter(fb200_plan* plan, const fb200_filter_args* args);
 
+/* ---- BufNMFCross: NMFCrossClient::process  (clients/nrt/NMFCrossClient.hpp:85-185) -------------------------------------- */
+/* Resynthesises `target` out of the frames of `source` (channel 0 of each, as the client does): STFT of both, NMFCross::process
+ * (algorithms/public/NMFCross.hpp:60-185: activation-only KL updates with the source magnitude spectrogram as dictionary,
+ * rank = source frames, and temporal-sparseness / polyphony / continuity post-processing of H every iteration),
+ * NMFCross::synthesize (H times the complex source spectrogram), GriffinLim::process (algorithms/public/GriffinLim.hpp:29-54,
+ * the client hard-codes 50 iterations) and ISTFT::process.  The attenuation factor of the sparseness / polyphony steps is
+ * computed as the reference writes it, with integer operands (NMFCross.hpp:119,136).
+ * progress is called with 1..iterations during the updates, then iterations+1 .. +3 after synthesis, Griffin-Lim and the
+ * inverse transform (the client's progressTotal = iterations + 3, :152). */
+typedef struct fb200_nmfcross_args {
+  uint32_t struct_size;
+  int32_t mem;
+  int64_t n_source, n_target;
+  int32_t time_sparsity, polyphony, continuity;   /* defaults 7, 11, 7 (odd) */
+  int32_t iterations;                              /* default 50 */
+  int64_t seed;                                    /* H init and Griffin-Lim phases; < 0 -> nondeterministic */
+  int32_t griffinlim_iterations;                   /* 50 in the client (:172) */
+  int32_t reserved;
+  const float* source;                             /* [n_source] */
+  const float* target;                             /* [n_target] */
+  float* out;                                      /* [n_target] (may be NULL when only the activations are wanted) */
+  float* acts_out;                                 /* optional [target frames][source frames] */
+  fb200_progress_fn progress;
+  void* progress_user;
+} fb200_nmfcross_args;
+FB200_API int32_t fb200_bufnmfcross(fb200_plan* plan, const fb200_nmfcross_args* args);
+
+/* ---- BufNMF over several devices of one process ------------------------------------------------------------ */
+/* The channels / buffers of a BufNMF job are independent (NMFClient.hpp:233 loops over them), so the job is cut into
+ * contiguous shards (fb200_shard_range), one per plan; every shard runs the whole pipeline on its plan's device from its
+ * own host thread and writes straight into the job's (host) arrays.  There is no collective on the data path.  With
+ * gathered_acts != NULL the final activations of ALL buffers are additionally gathered onto EVERY device with one
+ * ncclAllGather (libnccl.so.2 is dlopen'ed on first use): gathered_acts[d] is a device pointer on plans[d]'s device to
+ * float [n_devices * per][frames][rank], per = ceil(batch / n_devices); shard r occupies rows [r * per, r * per + count_r).
+ * A progress callback sees the minimum iteration over the shards, each iteration once; a cancel stops every shard. */
+typedef struct fb200_sharded_args {
+  uint32_t struct_size;
+  int32_t n_devices;
+  fb200_plan* const* plans;         /* [n_devices] plans with identical FFT settings on distinct devices */
+  const fb200_bufnmf_args* job;     /* the whole job, mem == FB200_HOST */
+  float* const* gathered_acts;      /* optional [n_devices] device pointers (see above) */
+} fb200_sharded_args;
+FB200_API int32_t fb200_bufnmf_sharded(const fb200_sharded_args* args);
+
 /* ---- the per-frame body of NMFFilter / NMFMatch for frames a host-side BufferedProcess has cut ------------------------ */
 /* For hosts that keep the reference's streaming structure (FluidSource / FluidSink ring buffers on the audio thread's
  * side, clients/common/BufferedProcess.hpp:49-93) and hand the frames that fall due to the device in one batch:
@@ -278,6 +322,8 @@ typedef struct fb200_api {
   int32_t (*bufstft_sizes)(int32_t, int32_t, int32_t, int32_t, int64_t, int64_t*, int64_t*);
   int32_t (*bufstft)(fb200_plan*, const fb200_bufstft_args*);
   int32_t (*nmf_filter_frames)(fb200_plan*, const fb200_filter_frames_args*);
+  int32_t (*bufnmf_sharded)(const fb200_sharded_args*);
+  int32_t (*bufnmfcross)(fb200_plan*, const fb200_nmfcross_args*);
 } fb200_api;
 /* returns NULL when abi_version is not supported */
 FB200_API const fb200_api* fb200_get_api(uint32_t abi_version);

@@ -72,6 +72,12 @@ def lib(path: str | None = None):
     L.fo_nmfmatch_frames.argtypes = [_pd, _i64, _pd, _i64, _i64, _i64, _i64, _pd, C.c_int]
     L.fo_stream_frames_mag.argtypes = [_pd, _i64, _i64, _i64, _i64, _i64, _pd, _pd]
     L.fo_nmffilter_stream.argtypes = [_pd, _i64, _i64, _i64, _i64, _pd, _i64, _i64, _i64, _pd, _pd]
+    L.fo_nmfcross_process.restype = C.c_int
+    L.fo_nmfcross_process.argtypes = [_pd, _i64, _i64, _pd, _i64, _i64, _i64, _i64, _i64, _i64, _pd, C.c_void_p, C.c_void_p]
+    L.fo_nmfcross_synthesize.argtypes = [_pd, _pd, _i64, _i64, _i64, _pd]
+    L.fo_griffinlim.argtypes = [_pd, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64]
+    L.fo_bufnmfcross.restype = C.c_int
+    L.fo_bufnmfcross.argtypes = [_pf, _i64, _pf, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _pf, _pd]
     L.fo_num_threads.restype = C.c_int
     L.fo_bufstft_sizes.restype = C.c_int
     L.fo_bufstft_sizes.argtypes = [_i64, _i64, _i64, C.c_int, _i64, _pi64, _pi64]
@@ -299,6 +305,45 @@ def bufstft_inv(mag, phase, win, fft, hop, mode=1):
     out = np.empty(n_out, np.float32)
     assert lib().fo_bufstft_inv(_f(m), _f(p), frames, win, fft, hop, mode, _f(out)) == 0
     return out
+
+
+def nmfcross_process(X, W0, n_iter, r, p, c, seed):
+    """NMFCross::process: X[F][B] target magnitudes, W0[R][B] source magnitudes -> H[F][R]."""
+    X = _c64(X); W0 = _c64(W0)
+    F, B = X.shape
+    R = W0.shape[0]
+    H = np.empty((F, R))
+    lib().fo_nmfcross_process(_d(X), F, B, _d(W0), R, n_iter, r, p, c, seed, _d(H), None, None)
+    return H
+
+
+def nmfcross_synthesize(H, S):
+    H = _c64(H); S = np.ascontiguousarray(S, dtype=np.complex128)
+    F, R = H.shape
+    B = S.shape[1]
+    out = np.empty((F, B), np.complex128)
+    lib().fo_nmfcross_synthesize(_d(H), _d(S.view(np.float64)), F, R, B, _d(out.view(np.float64)))
+    return out
+
+
+def griffinlim(spec, n_samples, n_iter, win, fft, hop, seed):
+    S = np.ascontiguousarray(spec, dtype=np.complex128).copy()
+    F, B = S.shape
+    lib().fo_griffinlim(_d(S.view(np.float64)), F, B, n_samples, n_iter, win, fft, hop, seed)
+    return S
+
+
+def bufnmfcross(source, target, win, fft, hop, time_sparsity=7, polyphony=11, continuity=7, iters=50, seed=-1, gl_iters=50):
+    """BufNMFCross client (NMFCrossClient.hpp:85-185) on mono float32 buffers -> (out float32 [n_target], H [Ft][Fs])."""
+    s = np.ascontiguousarray(source, dtype=np.float32); t = np.ascontiguousarray(target, dtype=np.float32)
+    Fs, Ft = num_frames(s.size, win, hop), num_frames(t.size, win, hop)
+    out = np.empty(t.size, np.float32)
+    H = np.empty((Ft, Fs))
+    rc = lib().fo_bufnmfcross(_f(s), s.size, _f(t), t.size, win, fft, hop, time_sparsity, polyphony, continuity, iters, seed,
+                              gl_iters, _f(out), _d(H))
+    if rc != 0:
+        raise ValueError("bufnmfcross: invalid arguments (empty buffer, or sparsity / continuity larger than the target)")
+    return out, H
 
 
 def num_threads():

@@ -873,6 +873,192 @@ FO_EXPORT void fo_nmffilter_stream(const double* audio, int64_t n, int64_t win, 
   free(msp); free(sp); free(frame); free(w);
 }
 
+/* ------------------------------------------------------------------------------------------------
+ * NMFCross  algorithms/public/NMFCross.hpp:60-185  (BufNMFCross: resynthesise a target out of a source's frames)
+ * Layouts as everywhere here: X[F][B] target magnitudes, W0[R][B] source magnitudes (rank R = source frames),
+ * H[F][R] (== Eigen column-major R x F).  H starts as U(0,1) from mt19937_64(seed), column-major fill (:72-73), and is
+ * NOT clamped or normalised; W is clamped at eps (:156) and never updated.
+ * Every iteration i (:161-176): H <- sparseness(H, r, i); H <- polyphony(H, p, i); H <- continuity(H, c); then the KL
+ * H-update with plain column sums as denominator.  NOTE (:119, :136): the attenuation factor is written
+ * 1 - ((iteration + 1) / mIterations) with INTEGER operands, i.e. 1 for every iteration but the last and 0 for the
+ * last: sparseness and polyphony are no-ops until the final iteration, where they zero every entry that is not a local
+ * temporal maximum / not among the p strongest of its frame.  Restated as written.
+ * ---------------------------------------------------------------------------------------------- */
+static void fo_cross_sparseness(const double* H, int64_t F, int64_t R, int64_t size, double factor, double* out)
+{ /* :104-127: entry (k, f) keeps its value iff the FIRST maximum of H[k][f-half .. f-half+size) (zero padded) is itself */
+  int64_t half = (size - 1) / 2;
+  for (int64_t f = 0; f < F; f++)
+    for (int64_t k = 0; k < R; k++) {
+      int64_t arg = 0;
+      double best = -INFINITY;
+      for (int64_t t = 0; t < size; t++) {
+        int64_t ff = f + t - half;
+        double v = (ff >= 0 && ff < F) ? H[ff * R + k] : 0.0;
+        if (v > best) { best = v; arg = t; }
+      }
+      out[f * R + k] = arg != half ? H[f * R + k] * factor : H[f * R + k];
+    }
+}
+
+typedef struct { double v; int64_t i; } fo_vi;
+static int fo_vi_desc(const void* a, const void* b)
+{
+  double x = ((const fo_vi*) a)->v, y = ((const fo_vi*) b)->v;
+  if (x > y) return -1;
+  if (x < y) return 1;
+  int64_t i = ((const fo_vi*) a)->i, j = ((const fo_vi*) b)->i; /* ties: the reference's std::sort order is unspecified */
+  return i < j ? -1 : (i > j ? 1 : 0);
+}
+static void fo_cross_polyphony(const double* H, int64_t F, int64_t R, const double* energy, int64_t p, double factor,
+                               double* out)
+{ /* :130-143: per frame, the p components with the largest H * energy keep their value, the rest are attenuated */
+  fo_vi* v = (fo_vi*) malloc(sizeof(fo_vi) * (size_t) R);
+  for (int64_t f = 0; f < F; f++) {
+    for (int64_t k = 0; k < R; k++) { v[k].v = H[f * R + k] * energy[k]; v[k].i = k; out[f * R + k] = H[f * R + k] * factor; }
+    qsort(v, (size_t) R, sizeof(fo_vi), fo_vi_desc);
+    for (int64_t t = 0; t < p && t < R; t++) out[f * R + v[t].i] = H[f * R + v[t].i];
+  }
+  free(v);
+}
+
+static void fo_cross_continuity(const double* H, int64_t F, int64_t R, int64_t size, double* out)
+{ /* :86-102: sum along the diagonal (component and frame advance together), zero padded */
+  int64_t half = (size - 1) / 2;
+  for (int64_t f = 0; f < F; f++)
+    for (int64_t k = 0; k < R; k++) {
+      double s = 0.0;
+      for (int64_t d = 0; d < size; d++) {
+        int64_t kk = k + d - half, ff = f + d - half;
+        if (kk >= 0 && kk < R && ff >= 0 && ff < F) s += H[ff * R + kk];
+      }
+      out[f * R + k] = s;
+    }
+}
+
+FO_EXPORT int fo_nmfcross_process(const double* X, int64_t F, int64_t B, const double* W0, int64_t R, int64_t n_iter,
+                                  int64_t r, int64_t p, int64_t c, int64_t seed, double* H1, fo_progress_cb cb, void* user)
+{
+  double* W = (double*) malloc(sizeof(double) * (size_t) (R * B));
+  double* H = (double*) malloc(sizeof(double) * (size_t) (F * R));
+  double* T = (double*) malloc(sizeof(double) * (size_t) (F * R));
+  double* P = (double*) malloc(sizeof(double) * (size_t) (F * B));
+  double* num = (double*) malloc(sizeof(double) * (size_t) (F * R));
+  double* energy = (double*) malloc(sizeof(double) * (size_t) R);
+  double* hden = (double*) malloc(sizeof(double) * (size_t) R);
+  fo_random_uniform(seed, R * F, H);                                          /* :72-73 */
+  for (int64_t i = 0; i < R * B; i++) W[i] = W0[i] > FO_EPS ? W0[i] : FO_EPS;  /* :156 */
+  for (int64_t k = 0; k < R; k++) {
+    double e = 0.0, s = 0.0;
+    for (int64_t b = 0; b < B; b++) { e += W[k * B + b] * W[k * B + b]; s += W[k * B + b]; }
+    energy[k] = e;                                                            /* :159 */
+    hden[k] = s > FO_EPS ? s : FO_EPS;                                        /* :169-170 */
+  }
+  int cancelled = 0;
+  for (int64_t i = 0; i < n_iter; i++) {
+    double factor = 1.0 - (double) ((i + 1) / n_iter);                        /* integer division, see above */
+    fo_cross_sparseness(H, F, R, r, factor, T);                               /* :163 */
+    fo_cross_polyphony(T, F, R, energy, p, factor, H);                        /* :164 */
+    fo_cross_continuity(H, F, R, c, T);                                       /* :165 */
+    memcpy(H, T, sizeof(double) * (size_t) (F * R));
+    fo_wh(W, H, B, F, R, P, 1);                                               /* :167 */
+    for (int64_t e = 0; e < F * B; e++) P[e] = X[e] / P[e];
+    fo_wt_r(W, P, B, F, R, num);                                              /* :168 */
+    for (int64_t f = 0; f < F; f++)
+      for (int64_t k = 0; k < R; k++) H[f * R + k] = H[f * R + k] * num[f * R + k] / hden[k]; /* :170 */
+    if (cb && !cb(user, i + 1)) { cancelled = 1; break; }                     /* :174-175 */
+  }
+  memcpy(H1, H, sizeof(double) * (size_t) (F * R));
+  free(W); free(H); free(T); free(P); free(num); free(energy); free(hden);
+  return cancelled;
+}
+
+/* NMFCross::synthesize :50-58: out[F][B] (complex) = H[F][R] * S[R][B] (complex source spectrogram) */
+FO_EXPORT void fo_nmfcross_synthesize(const double* H, const double* S, int64_t F, int64_t R, int64_t B, double* out)
+{
+  memset(out, 0, sizeof(double) * (size_t) (2 * F * B));
+  for (int64_t f = 0; f < F; f++)
+    for (int64_t k = 0; k < R; k++) {
+      double h = H[f * R + k];
+      const double* s = S + 2 * k * B;
+      double* o = out + 2 * f * B;
+      for (int64_t b = 0; b < 2 * B; b++) o[b] += h * s[b];
+    }
+}
+
+/* GriffinLim::process  algorithms/public/GriffinLim.hpp:29-54.  spec[F][B] complex, in place.
+ * Random phase: EigenRandomPhase (EigenRandom.hpp:146-160): polar(1, U(0, 2 pi)) from mt19937_64(seed), filling a
+ * column-major F x B array in storage order: entry (f, b) is draw b * F + f; libstdc++'s uniform_real_distribution(a, b)
+ * is generate_canonical * (b - a) + a. */
+FO_EXPORT void fo_griffinlim(double* spec, int64_t F, int64_t B, int64_t n_samples, int64_t n_iter, int64_t win,
+                             int64_t fft, int64_t hop, int64_t seed)
+{
+  const double momentum = 0.9, twopi = 2.0 * 3.14159265358979323846; /* 2 * M_PI */
+  int64_t cnt = F * B;
+  double* mag = (double*) malloc(sizeof(double) * (size_t) cnt);
+  double* phase = (double*) malloc(sizeof(double) * (size_t) (2 * cnt));
+  double* est = (double*) calloc((size_t) (2 * cnt), sizeof(double));
+  double* prev = (double*) calloc((size_t) (2 * cnt), sizeof(double));
+  double* sg = (double*) malloc(sizeof(double) * (size_t) (2 * cnt));
+  double* tmp = (double*) calloc((size_t) n_samples, sizeof(double));
+  for (int64_t e = 0; e < cnt; e++) mag[e] = hypot(spec[2 * e], spec[2 * e + 1]);   /* :39 */
+  {
+    fo_mt64 g; fo_mt64_seed(&g, (uint64_t) seed);
+    for (int64_t b = 0; b < B; b++)
+      for (int64_t f = 0; f < F; f++) {
+        double th = fo_mt64_uniform(&g) * (twopi - 0.0) + 0.0;
+        phase[2 * (f * B + b)] = cos(th);
+        phase[2 * (f * B + b) + 1] = sin(th);
+      }
+  }
+  for (int64_t i = 0; i < n_iter; i++) {                                            /* :44-52 */
+    memcpy(prev, est, sizeof(double) * (size_t) (2 * cnt));
+    for (int64_t e = 0; e < cnt; e++) { sg[2 * e] = mag[e] * phase[2 * e]; sg[2 * e + 1] = mag[e] * phase[2 * e + 1]; }
+    fo_istft(sg, F, win, fft, hop, tmp, n_samples);
+    fo_stft(tmp, n_samples, win, fft, hop, est);
+    for (int64_t e = 0; e < cnt; e++) {
+      double re = est[2 * e] - (momentum / (1 + momentum)) * prev[2 * e];
+      double im = est[2 * e + 1] - (momentum / (1 + momentum)) * prev[2 * e + 1];
+      double a = hypot(re, im) + FO_EPS;
+      phase[2 * e] = re / a; phase[2 * e + 1] = im / a;
+    }
+  }
+  for (int64_t e = 0; e < cnt; e++) { spec[2 * e] = mag[e] * phase[2 * e]; spec[2 * e + 1] = mag[e] * phase[2 * e + 1]; } /* :53 */
+  free(mag); free(phase); free(est); free(prev); free(sg); free(tmp);
+}
+
+/* BufNMFCross  clients/nrt/NMFCrossClient.hpp:85-185: mono source and target (channel 0), output [n_target] float.
+ * H_out (optional, [Ft][Fs]) returns the activations for tests. */
+FO_EXPORT int fo_bufnmfcross(const float* source, int64_t ns, const float* target, int64_t nt, int64_t win, int64_t fft,
+                             int64_t hop, int64_t time_sparsity, int64_t polyphony, int64_t continuity, int64_t n_iter,
+                             int64_t seed, int64_t gl_iter, float* out, double* H_out)
+{
+  int64_t B = fft / 2 + 1;
+  int64_t Fs = fo_stft_num_frames(ns, win, hop), Ft = fo_stft_num_frames(nt, win, hop);   /* :103-108 */
+  if (ns <= 0 || nt <= 0 || time_sparsity > Ft || continuity > Ft) return -1;             /* :110-119 */
+  double* sa = (double*) malloc(sizeof(double) * (size_t) ns);
+  double* ta = (double*) malloc(sizeof(double) * (size_t) nt);
+  for (int64_t i = 0; i < ns; i++) sa[i] = (double) source[i];
+  for (int64_t i = 0; i < nt; i++) ta[i] = (double) target[i];
+  double* S = (double*) malloc(sizeof(double) * (size_t) (2 * Fs * B));
+  double* T = (double*) malloc(sizeof(double) * (size_t) (2 * Ft * B));
+  double* W = (double*) malloc(sizeof(double) * (size_t) (Fs * B));
+  double* M = (double*) malloc(sizeof(double) * (size_t) (Ft * B));
+  double* H = (double*) malloc(sizeof(double) * (size_t) (Ft * Fs));
+  double* res = (double*) malloc(sizeof(double) * (size_t) (2 * Ft * B));
+  double* audio = (double*) malloc(sizeof(double) * (size_t) nt);
+  fo_stft(sa, ns, win, fft, hop, S); fo_magnitude(S, Fs * B, W);                          /* :134-136 */
+  fo_stft(ta, nt, win, fft, hop, T); fo_magnitude(T, Ft * B, M);                          /* :137-139 */
+  int64_t p = polyphony < Fs ? polyphony : Fs;                                            /* :160 */
+  fo_nmfcross_process(M, Ft, B, W, Fs, n_iter, time_sparsity, p, continuity, seed, H, NULL, NULL); /* :158-161 */
+  if (H_out) memcpy(H_out, H, sizeof(double) * (size_t) (Ft * Fs));
+  fo_nmfcross_synthesize(H, S, Ft, Fs, B, res);                                           /* :166 */
+  fo_griffinlim(res, Ft, B, nt, gl_iter, win, fft, hop, seed);                            /* :171-173 (50 iterations) */
+  fo_istft(res, Ft, win, fft, hop, audio, nt);                                            /* :178 */
+  for (int64_t i = 0; i < nt; i++) out[i] = (float) audio[i];                             /* :183 */
+  free(sa); free(ta); free(S); free(T); free(W); free(M); free(H); free(res); free(audio);
+  return 0;
+}
+
 FO_EXPORT int fo_num_threads(void)
 {
 #ifdef _OPENMP

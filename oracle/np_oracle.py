@@ -339,3 +339,63 @@ def bufstft_inv(mag_f32, phase_f32, win, fft, hop, mode=1):
         nrm[i * hop:i * hop + win] += w * w
     out = acc / np.maximum(nrm, EPS)
     return out[pad:pad + n_out].astype(np.float32)
+
+
+# ---- NMFCross.hpp:60-185, GriffinLim.hpp:29-54, NMFCrossClient.hpp:85-185 -----------------------------------------
+def nmfcross_process(X, W0, n_iter, r, p, c, seed):
+    """X[F][B] target magnitudes, W0[R][B] source magnitudes -> H[F][R]; written in the reference's orientation
+    (W: B x R, H: R x F) with numpy building blocks (sliding windows, argsort, trace-like diagonal sums, BLAS)."""
+    V = np.asarray(X, dtype=np.float64).T                      # B x F
+    W = np.maximum(np.asarray(W0, dtype=np.float64).T, EPS)    # B x R   (:156)
+    R, F = W.shape[1], V.shape[1]
+    H = random_uniform(seed, R * F).reshape(F, R).T.copy()     # column-major fill of R x F (:72-73)
+    energy = (W ** 2).sum(axis=0)                              # :159
+    hden = np.maximum(W.sum(axis=0), EPS)[:, None]
+    for i in range(n_iter):
+        factor = 1.0 - float((i + 1) // n_iter)                # integer division as written (:119, :136)
+        # temporal sparseness (:104-127)
+        half = (r - 1) // 2
+        pad = np.zeros((R, F + r)); pad[:, half:half + F] = H
+        win = np.lib.stride_tricks.sliding_window_view(pad, r, axis=1)[:, :F, :]
+        keep = win.argmax(axis=2) == half                      # first maximum, like Eigen's maxCoeff(&index)
+        H = np.where(keep, H, H * factor)
+        # polyphony (:130-143)
+        score = H * energy[:, None]
+        out = H * factor
+        top = np.argsort(-score, axis=0, kind="stable")[:p, :]
+        cols = np.arange(F)[None, :]
+        out[top, cols] = H[top, cols]
+        H = out
+        # continuity (:86-102): sums along the diagonal
+        half = (c - 1) // 2
+        pad = np.zeros((R + c, F + c)); pad[half:half + R, half:half + F] = H
+        H = sum(pad[d:d + R, d:d + F] for d in range(c))
+        # KL update of H, W fixed (:167-170)
+        V2 = np.maximum(W @ H, EPS)
+        H = H * (W.T @ (V / V2)) / hden
+    return H.T.copy()
+
+
+def griffinlim(spec, n_samples, n_iter, win, fft, hop, seed):
+    S = np.asarray(spec, dtype=np.complex128)
+    F, B = S.shape
+    mag = np.abs(S)
+    theta = random_uniform(seed, F * B) * (2 * np.pi - 0.0) + 0.0     # uniform_real_distribution(0, 2 pi)
+    phase = np.exp(1j * theta).reshape(B, F).T                        # column-major fill of an F x B array
+    est = np.zeros((F, B), np.complex128)
+    for _ in range(n_iter):
+        prev = est
+        est = stft(istft(mag * phase, win, fft, hop, n_samples), win, fft, hop)
+        phase = est - (0.9 / 1.9) * prev
+        phase = phase / (np.abs(phase) + EPS)
+    return mag * phase
+
+
+def bufnmfcross(source_f32, target_f32, win, fft, hop, time_sparsity=7, polyphony=11, continuity=7, iters=50, seed=-1,
+                gl_iters=50):
+    s = np.asarray(source_f32, dtype=np.float32).astype(np.float64)
+    t = np.asarray(target_f32, dtype=np.float32).astype(np.float64)
+    S = stft(s, win, fft, hop); T = stft(t, win, fft, hop)
+    H = nmfcross_process(np.abs(T), np.abs(S), iters, time_sparsity, min(S.shape[0], polyphony), continuity, seed)
+    res = griffinlim(H @ S, t.size, gl_iters, win, fft, hop, seed)
+    return istft(res, win, fft, hop, t.size).astype(np.float32), H

@@ -181,13 +181,69 @@ def bufstft():
     np.savez_compressed(os.path.join(HERE, "bufstft.npz"), **out)
 
 
+def nmfcross():
+    """BufNMFCross (NMFCrossClient.hpp:85-185) on two short synthetic buffers: win 256, hop 64, sparsity 7, polyphony 11,
+    continuity 7, 30 iterations, seed 5, 50 Griffin-Lim iterations.  C oracle output, cross-checked against numpy."""
+    src = synth_audio(31, 6000); tgt = synth_audio(32, 5000)
+    out, H = co.bufnmfcross(src, tgt, 256, 256, 64, 7, 11, 7, 30, 5, 50)
+    out2, H2 = no.bufnmfcross(src, tgt, 256, 256, 64, 7, 11, 7, 30, 5, 50)
+    assert np.abs(H - H2).max() <= 1e-10 * np.abs(H2).max() and np.abs(out - out2).max() <= 1e-6 * np.abs(out2).max()
+    np.savez_compressed(os.path.join(HERE, "nmfcross.npz"), source=src, target=tgt, out=out, H=H)
+
+
+def read_wav_mono_int(path):
+    """Integer samples of a mono PCM file (16 / 24 bit) and the scale that turns them into the floats a host loads."""
+    import struct
+    with open(path, "rb") as f:
+        d = f.read()
+    pos = 12; fmt = None; data = None
+    while pos + 8 <= len(d):
+        cid = d[pos:pos + 4]; sz = struct.unpack("<I", d[pos + 4:pos + 8])[0]
+        body = d[pos + 8:pos + 8 + sz]
+        if cid == b"fmt ":
+            fmt = struct.unpack("<HHIIHH", body[:16])
+        elif cid == b"data":
+            data = body
+        pos += 8 + sz + (sz & 1)
+    _, ch, sr, _, _, bits = fmt
+    assert ch == 1
+    if bits == 16:
+        return np.frombuffer(data, "<i2").astype(np.int32), bits, sr
+    b = np.frombuffer(data, np.uint8).reshape(-1, 3).astype(np.int32)
+    v = b[:, 0] | (b[:, 1] << 8) | (b[:, 2] << 16)
+    return np.where(v & 0x800000, v - (1 << 24), v).astype(np.int32), bits, sr
+
+
+def config1_full():
+    """BASELINE config 1 at FULL length (the round-1 fixture held the first 32768 samples only): both reference
+    WAVs, fft 1024 hop 256 rank 4, 100 iterations, seed 42.  The samples are stored losslessly as integers (the GPU box has
+    no /root/reference); bases / activations and per-component resynthesis energies pin the oracle's full-length output."""
+    for name in ("Tremblay-AaS-SynthTwoVoices-M", "Nicol-LoopE-M"):
+        pcm, bits, sr = read_wav_mono_int(os.path.join(REF_AUDIO, name + ".wav"))
+        a = (pcm.astype(np.float64) / float(1 << (bits - 1))).astype(np.float32)
+        x, _ = read_wav_mono(os.path.join(REF_AUDIO, name + ".wav"))
+        assert np.array_equal(a, x.astype(np.float32))
+        r = co.bufnmf_channel(a, 1024, 1024, 256, 4, 100, 42, resynth=True)
+        F = co.num_frames(a.size, 1024, 256)
+        assert r["acts"].shape == (F, 4)
+        np.savez_compressed(os.path.join(HERE, f"config1_{name.split('-')[0].lower()}.npz"),
+                            pcm=pcm.astype(np.int32 if bits > 16 else np.int16), bits=bits, sr=sr, bases=r["bases"], acts=r["acts"],
+                            resynth_energy=(r["resynth"].astype(np.float64) ** 2).sum(axis=1),
+                            resynth_head=r["resynth"][:, :4096].astype(np.float32))
+        print(name, a.size, "samples ->", F, "frames")
+
+
 if __name__ == "__main__":
     co.build()
-    if len(sys.argv) > 1 and sys.argv[1] == "stream":
+    if len(sys.argv) > 1 and sys.argv[1] == "config1":
+        config1_full()
+    elif len(sys.argv) > 1 and sys.argv[1] == "nmfcross":
+        nmfcross()
+    elif len(sys.argv) > 1 and sys.argv[1] == "stream":
         nmffilter_stream()
     elif len(sys.argv) > 1 and sys.argv[1] == "bufstft":
         bufstft()
     else:
-        rng_kat(); fft_kat(); nmf_small(); bufnmf_wav(); nmffilter_stream(); bufstft()
+        rng_kat(); fft_kat(); nmf_small(); bufnmf_wav(); nmffilter_stream(); bufstft(); config1_full(); nmfcross()
     for f in sorted(os.listdir(HERE)):
         print(f, os.path.getsize(os.path.join(HERE, f)))

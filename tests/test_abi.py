@@ -38,8 +38,8 @@ def test_exports_every_declared_symbol(fb):
 
 def test_abi_version_and_table(fb):
     L = fb.load()
-    assert L.fb200_abi_version() == 1
-    assert L.fb200_get_api(1) is not None and L.fb200_get_api(999) is None
+    assert L.fb200_abi_version() == 2  # round 2: new entry points appended to the table, FB200_PROGRESS_ASYNC
+    assert L.fb200_get_api(2) is not None and L.fb200_get_api(1) is None and L.fb200_get_api(999) is None
 
 
 def test_struct_sizes_match_header_layout(fb):
@@ -49,6 +49,7 @@ def test_struct_sizes_match_header_layout(fb):
     assert C.sizeof(fb.FramesArgs) == 88
     assert C.sizeof(fb.BufNmfArgs) == 120
     assert C.sizeof(fb.Stats) == 64
+    assert C.sizeof(fb.FilterFramesArgs) == 64 and C.sizeof(fb.NmfCrossArgs) == 104 and C.sizeof(fb.ShardedArgs) == 32
 
 
 def test_size_rules(fb, oracle):

@@ -428,3 +428,74 @@ def test_bufstft_batch_device_roundtrip(fb, oracle, synth, n, win, fft, hop, mod
     with fb.Plan(win=win, hop=hop, fft=fft) as plan:
         with pytest.raises(fb.FlucomaB200Error):
             plan.bufstft(a[:, :max(1, win // 4)], padding_mode=0)                            # shorter than one window
+
+
+# ---------------------------------------------------------------------------------------------- round 2 additions
+@pytest.mark.parametrize("name,frames", [("tremblay", 2013), ("nicol", 1774)])
+def test_config1_full_length_wav(fb, oracle, golden_dir, name, frames):
+    """BASELINE config 1 on the two reference WAVs at FULL length (F = 2013 / 1774), resynthesis included."""
+    g = np.load(os.path.join(golden_dir, f"config1_{name}.npz"))
+    a = (g["pcm"].astype(np.float64) / float(1 << (int(g["bits"]) - 1))).astype(np.float32)
+    with fb.Plan(win=1024, hop=256, fft=1024) as plan:
+        r = plan.bufnmf(a, 4, 100, seeds=42, resynth=True)
+    assert r["acts"].shape == (1, frames, 4)
+    assert rel(r["bases"][0], g["bases"]) < TOL and rel(r["acts"][0], g["acts"]) < TOL
+    o = oracle.bufnmf_channel(a, 1024, 1024, 256, 4, 100, 42, resynth=True)
+    for k in ("bases", "acts", "resynth"):
+        assert rel(r[k][0], o[k]) < TOL, (k, rel(r[k][0], o[k]))
+    assert np.abs(r["resynth"][0].sum(axis=0) - a).max() < 1e-4  # the masks sum to one: the components add up to the input
+
+
+@pytest.mark.parametrize("backend,K", [("BACKEND_AUTO", 5), ("BACKEND_TCGEN05", 16), ("BACKEND_TCGEN05_STREAMED", 32)])
+def test_kl_divergence_tracks_the_oracle_per_iteration(fb, oracle, backend, K):
+    """A final-state Frobenius check can hide drift along flat directions; the objective cannot.  After j iterations the
+    KL divergence of the GPU factors must equal the oracle's to 1e-5 relative (fp32 factors), and never increase."""
+    from tests.test_oracle import kl_divergence
+    rng = np.random.default_rng(12)
+    V = (rng.random((256, 7)) ** 3) @ (rng.random((7, 257)) ** 3) + 1e-3 * rng.random((256, 257))
+    prev = None
+    with fb.Plan(win=64, backend=getattr(fb, backend)) as plan:
+        for it in (1, 2, 3, 5, 8, 13, 21, 34, 55, 89, 144):
+            W, H, _, _ = plan.nmf_process(V, K, it, True, True, seeds=4, want_v=False)
+            Wo, Ho, _, _ = oracle.nmf_process(V, K, it, True, True, 4)
+            d, do = kl_divergence(V, W.astype(np.float64), H.astype(np.float64)), kl_divergence(V, Wo, Ho)
+            assert abs(d - do) <= 1e-5 * abs(do), (it, d, do)
+            if prev is not None:
+                assert d <= prev * (1 + 1e-6), (it, d, prev)
+            prev = d
+
+
+def test_config4_rank64_500_iterations(fb, oracle, synth):
+    """BASELINE config 4 (fft 4096, hop 1024, rank 64) at its FULL iteration count, on 128 frames so that the fp64 oracle
+    finishes in seconds: W, H within 1e-4 after 500 iterations."""
+    a = np.stack([synth(3000 + b, 127 * 1024) for b in range(2)])
+    with fb.Plan(win=4096, hop=1024, fft=4096) as plan:
+        r = plan.bufnmf(a, 64, 500, seeds=[0, 1])
+    bases, acts, _ = oracle.bufnmf_batch(a, 4096, 4096, 1024, 64, 500, np.arange(2), faithful=False)
+    for b in range(2):
+        assert rel(r["bases"][b], bases[b]) < TOL and rel(r["acts"][b], acts[b]) < TOL, (b, rel(r["bases"][b], bases[b]))
+
+
+@pytest.mark.parametrize("n,win,fft,hop", [(8192, 256, 256, 64), (6000, 400, 512, 100), (130816, 1024, 1024, 256),
+                                           (40000, 2048, 2048, 512), (70000, 4096, 4096, 1024), (12000, 1000, 4096, 250),
+                                           (4096, 512, 512, 512)])
+def test_fused_stft_kernel_vs_oracle_and_cufft_path(fb, oracle, n, win, fft, hop):
+    """The fused TMA + shared-memory FFT kernel (kernels_stft_fused.cu) against the fp64 oracle, and against the cuFFT
+    pipeline it replaces (FB200_STFT_CUFFT=1 forces the fallback)."""
+    rng = np.random.default_rng(n + fft)
+    x = rng.standard_normal((3, n)).astype(np.float32)
+    with fb.Plan(win=win, hop=hop, fft=fft) as plan:
+        spec, mag = plan.stft(x, want_spectrum=True, want_magnitude=True)
+        launches_fused = plan.stats()["launches_total"]
+        os.environ["FB200_STFT_CUFFT"] = "1"
+        try:
+            spec_c, mag_c = plan.stft(x, want_spectrum=True, want_magnitude=True)
+            launches_cufft = plan.stats()["launches_total"]
+        finally:
+            del os.environ["FB200_STFT_CUFFT"]
+    assert launches_fused < launches_cufft  # one kernel instead of three per wave
+    for b in range(3):
+        S = oracle.stft(x[b].astype(np.float64), win, fft, hop)
+        assert rel(spec[b], S) < 2e-6 and rel(mag[b], np.abs(S)) < 2e-6, (rel(spec[b], S), rel(mag[b], np.abs(S)))
+        assert rel(spec[b], spec_c[b]) < 2e-6
+    assert np.all(spec[..., 0].imag == 0) and np.all(spec[..., -1].imag == 0)  # FFT.hpp:99-101

@@ -89,3 +89,48 @@ def test_bufstft_client_gpu_vs_oracle(oracle):
     assert mag.shape == mo.shape and np.linalg.norm(z - zo) / np.linalg.norm(zo) < 2e-6
     ro = oracle.bufstft_inv(mo, po, 256, 256, 64, 1)
     assert res.shape == (ro.size, 1) and np.linalg.norm(res[:, 0] - ro) / np.linalg.norm(ro) < 1e-4
+
+
+def test_rt_client_ring_buffers_cpu():
+    """FluidSource / FluidSink / BufferedProcess mirrors: the reference's own ring-buffer tests restated
+    (tests/clients/common/TestFluidSource.cpp:39-55, TestBufferedProcess.cpp:20-70) -- no device needed."""
+    with tempfile.TemporaryDirectory() as t:
+        exe = compile_cpp("test_rt_clients_gpu.cpp", os.path.join(t, "a"))
+        r = subprocess.run([exe], capture_output=True, text=True)
+        assert r.returncode == 0 and "rt clients cpu ok" in r.stdout, r.stdout + r.stderr
+
+
+def _read_dumps(path, count):
+    out = []
+    with open(path, "rb") as f:
+        for _ in range(count):
+            r, c = np.frombuffer(f.read(16), np.int64)
+            out.append(np.frombuffer(f.read(4 * r * c), np.float32).reshape(r, c))
+    return out
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("host", [64, 100, 256])
+def test_rt_clients_gpu_vs_oracle_stream(oracle, host):
+    """NMFFilterClient / NMFMatchClient mirrors driven block by block like an audio callback (host vectors of 64, 100 and
+    256 samples) against the oracle's simulation of the reference's streaming clients."""
+    win, hop, rank = 256, 64, 5
+    with tempfile.TemporaryDirectory() as t:
+        exe = compile_cpp("test_rt_clients_gpu.cpp", os.path.join(t, "a"))
+        dump = os.path.join(t, "dump.bin")
+        r = subprocess.run([exe, dump, str(host)], capture_output=True, text=True, env=dict(os.environ, FLUCOMA_B200_LIB=LIB))
+        assert r.returncode == 0 and "rt clients ok" in r.stdout, r.stdout + r.stderr
+        audio, W, fout, mout = _read_dumps(dump, 4)
+    audio = audio[0]
+    n_out = fout.shape[1]
+    out_o, acts_o = oracle.nmffilter_stream(audio.astype(np.float64), win, win, hop, W.astype(np.float64), 10, 42)
+    for k in range(rank):  # NMFFilterClient.hpp:98-117 through STFTBufferedProcess<true>
+        assert np.linalg.norm(fout[k] - out_o[k, :n_out]) / np.linalg.norm(out_o[k, :n_out]) < 1e-4
+    assert np.all(fout[rank:] == 0)  # channels beyond the rank of the bases buffer stay silent
+    # NMFMatchClient.hpp:110-118: a block reports the activations of the last frame of the block before
+    assert np.all(mout[0] == 0)
+    for b in range(1, mout.shape[0]):
+        f_last = -(-b * host // hop) - 1
+        ref = acts_o[f_last]
+        assert np.linalg.norm(mout[b, :rank] - ref) / max(np.linalg.norm(ref), 1e-30) < 1e-4, b
+    assert np.all(mout[:, rank:] == 0)

@@ -12,6 +12,6 @@ cp "$SRC" $ROOT/flucoma-core_b200/csrc/.variant_tc.cu
   --expt-relaxed-constexpr "$@" -c $ROOT/flucoma-core_b200/csrc/.variant_tc.cu -o $TMP/tc.o
 rm -f $ROOT/flucoma-core_b200/csrc/.variant_tc.cu
 OBJS=$(ls $B/*.o | grep -v kernels_nmf_tc.o)
-/usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -shared -ccbin /usr/bin/g++ -o "$OUT" $OBJS $TMP/tc.o -lcufft -Xlinker -rpath,/usr/local/cuda/lib64
+/usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -shared -ccbin /usr/bin/g++ -o "$OUT" $OBJS $TMP/tc.o -lcufft -ldl -Xlinker -rpath,/usr/local/cuda/lib64
 rm -rf $TMP
 echo "$OUT"
