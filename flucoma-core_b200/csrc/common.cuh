@@ -228,7 +228,5 @@ int tc_grid(const Plan* p, const NmfDev& d);
 // kernels_nmf_tcs.cu --------------------------------------------------------------------------------------------
 bool tcs_eligible(const NmfDev& d);
 int32_t tcs_run(Plan* p, const NmfDev& d, int iters, bool upd_w, bool upd_h);
-// kernels_nmf_tcr.cu: rank 16 with the stationary operand in TMEM (tcs_run dispatches to it)
-int32_t tcr_run(Plan* p, const NmfDev& d, int iters, bool upd_w, bool upd_h);
 
 } // namespace fb200

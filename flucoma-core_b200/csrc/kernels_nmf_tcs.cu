@@ -820,9 +820,7 @@ static int32_t tcs_run_t(Plan* p, const NmfDev& d, int iters, bool upd_w, bool u
 
 int32_t tcs_run(Plan* p, const NmfDev& d, int iters, bool upd_w, bool upd_h)
 {
-  // rank 16: the variant that keeps the stationary operand and the running sums in TMEM (kernels_nmf_tcr.cu);
-  // FB200_TCS16=1 selects the all-shared-memory kernel of this file for A/B runs
-  if (d.KP == 16) return getenv("FB200_TCS16") ? tcs_run_t<16>(p, d, iters, upd_w, upd_h) : tcr_run(p, d, iters, upd_w, upd_h);
+  if (d.KP == 16) return tcs_run_t<16>(p, d, iters, upd_w, upd_h);
   return tcs_run_t<32>(p, d, iters, upd_w, upd_h);
 }
 

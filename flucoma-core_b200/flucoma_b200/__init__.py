@@ -19,7 +19,7 @@ import os
 import numpy as np
 
 _PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_PATH = os.path.join(_PKG, "lib", "libflucoma_b200.so")
+LIB_PATH = os.environ.get("FB200_LIB") or os.path.join(_PKG, "lib", "libflucoma_b200.so")  # FB200_LIB: developer A/B builds
 
 F32, F64 = 0, 1
 HOST, DEVICE = 0, 1

@@ -78,6 +78,9 @@ def lib(path: str | None = None):
     L.fo_griffinlim.argtypes = [_pd, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64]
     L.fo_bufnmfcross.restype = C.c_int
     L.fo_bufnmfcross.argtypes = [_pf, _i64, _pf, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _pf, _pd]
+    L.fo_melbands.argtypes = [_pd, _i64, _i64, C.c_double, C.c_double, _i64, C.c_double, _i64, C.c_int, C.c_int, C.c_int, _pd]
+    L.fo_melbands_init.argtypes = [C.c_double, C.c_double, _i64, _i64, C.c_double, _i64, _pd, _pd, _pd]
+    L.fo_hpss.argtypes = [_pd, _i64, _i64, _i64, _i64, _i64] + [C.c_double] * 8 + [_pd]
     L.fo_num_threads.restype = C.c_int
     L.fo_bufstft_sizes.restype = C.c_int
     L.fo_bufstft_sizes.argtypes = [_i64, _i64, _i64, C.c_int, _i64, _pi64, _pi64]
@@ -344,6 +347,31 @@ def bufnmfcross(source, target, win, fft, hop, time_sparsity=7, polyphony=11, co
     if rc != 0:
         raise ValueError("bufnmfcross: invalid arguments (empty buffer, or sparsity / continuity larger than the target)")
     return out, H
+
+
+def melbands(mags, lo, hi, n_bands, sample_rate, win, mag_norm=True, use_power=False, log_output=False):
+    """MelBands::init + processFrame per frame: mags[F][B] -> bands[F][nBands]."""
+    m = _c64(mags)
+    F, B = m.shape
+    out = np.empty((F, n_bands))
+    lib().fo_melbands(_d(m), F, B, lo, hi, n_bands, sample_rate, win, int(mag_norm), int(use_power), int(log_output), _d(out))
+    return out
+
+
+def melbands_filters(lo, hi, n_bands, n_bins, sample_rate, win):
+    filt = np.empty((n_bands, n_bins)); s1 = np.empty(1); s2 = np.empty(1)
+    lib().fo_melbands_init(lo, hi, n_bands, n_bins, sample_rate, win, _d(filt), _d(s1), _d(s2))
+    return filt, float(s1[0]), float(s2[0])
+
+
+def hpss(spec, v_size, h_size, mode=0, h_thresh=(0.0, 1.0, 1.0, 1.0), p_thresh=(0.0, 1.0, 1.0, 1.0)):
+    """HPSS::processFrame over spec[F][B] from init state -> out[3][F][B] complex (harmonic, percussive, residual)."""
+    S = np.ascontiguousarray(spec, dtype=np.complex128)
+    F, B = S.shape
+    out = np.empty((3, F, B), np.complex128)
+    lib().fo_hpss(_d(S.view(np.float64)), F, B, v_size, h_size, mode, *[float(x) for x in h_thresh], *[float(x) for x in p_thresh],
+                  _d(out.view(np.float64)))
+    return out
 
 
 def num_threads():

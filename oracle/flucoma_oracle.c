@@ -1059,6 +1059,177 @@ FO_EXPORT int fo_bufnmfcross(const float* source, int64_t ns, const float* targe
   return 0;
 }
 
+/* ------------------------------------------------------------------------------------------------
+ * MelBands  algorithms/public/MelBands.hpp:35-101  (an epilogue on |X|: SURVEY 8f rank 4)
+ * Eigen's LinSpaced(n, a, b) for doubles (Eigen 3.4 linspaced_op_impl, non-integer): step = (b - a) / (n - 1); when
+ * |b| < |a| the sequence is evaluated from the top (b - (n-1-i) step, first element exactly a), else from the bottom
+ * (a + i step, last element exactly b).
+ * ---------------------------------------------------------------------------------------------- */
+static double fo_linspaced(int64_t n, double a, double b, int64_t i)
+{
+  if (n == 1) return b;
+  double step = (b - a) / (double) (n - 1);
+  int flip = fabs(b) < fabs(a);
+  if (flip) return i == 0 ? a : b - (double) (n - 1 - i) * step;
+  return i == n - 1 ? b : a + (double) i * step;
+}
+
+/* init :43-80: filters[nBands][nBins] triangular, scale1 / scale2 */
+FO_EXPORT void fo_melbands_init(double lo, double hi, int64_t n_bands, int64_t n_bins, double sample_rate, int64_t win,
+                                double* filters, double* scale1, double* scale2)
+{
+  int64_t fft = 2 * (n_bins - 1);
+  *scale1 = 1.0 / ((double) win / 4.0);                                   /* :50 */
+  *scale2 = 1.0 / (2.0 * (double) fft / (double) win);                    /* :53 */
+  double mlo = 1127.01048 * log(lo / 700.0 + 1.0), mhi = 1127.01048 * log(hi / 700.0 + 1.0); /* :38-41 */
+  double* mel = (double*) malloc(sizeof(double) * (size_t) (n_bands + 2));
+  for (int64_t i = 0; i < n_bands + 2; i++) mel[i] = 700.0 * (exp(fo_linspaced(n_bands + 2, mlo, mhi, i) / 1127.01048) - 1.0); /* :55-56 */
+  for (int64_t i = 0; i < n_bands; i++) {
+    double d0 = fabs(mel[i] - mel[i + 1]), d1 = fabs(mel[i + 1] - mel[i + 2]);                  /* :62-64 */
+    for (int64_t b = 0; b < n_bins; b++) {
+      double f = fo_linspaced(n_bins, 0.0, sample_rate / 2.0, b);                               /* :60 */
+      double lower = -(mel[i] - f) / d0, upper = (mel[i + 2] - f) / d1;                          /* :72-73 */
+      double v = lower < upper ? lower : upper;
+      filters[i * n_bins + b] = v > 0.0 ? v : 0.0;                                               /* :74 */
+    }
+  }
+  free(mel);
+}
+
+/* processFrame :82-101.  NOTE: the reference scales / squares the caller's frame IN PLACE (the Eigen map aliases `in`);
+ * `frame` is mutated here in the same way. */
+FO_EXPORT void fo_melbands_frame(const double* filters, int64_t n_bands, int64_t n_bins, double scale1, double scale2,
+                                 double* frame, double* out, int mag_norm, int use_power, int log_output)
+{
+  if (mag_norm) for (int64_t b = 0; b < n_bins; b++) frame[b] *= scale1;     /* :90 */
+  double energy = 0.0;
+  for (int64_t b = 0; b < n_bins; b++) energy += frame[b];
+  energy *= scale2;                                                           /* :91 */
+  if (use_power) for (int64_t b = 0; b < n_bins; b++) frame[b] *= frame[b];  /* :92 */
+  double sum = 0.0;
+  for (int64_t i = 0; i < n_bands; i++) {                                     /* :94-95 */
+    double s = 0.0;
+    for (int64_t b = 0; b < n_bins; b++) s += filters[i * n_bins + b] * frame[b];
+    out[i] = s;
+    sum += s;
+  }
+  if (mag_norm) { double d = sum > FO_EPS ? sum : FO_EPS; for (int64_t i = 0; i < n_bands; i++) out[i] = out[i] * energy / d; } /* :97 */
+  if (log_output) for (int64_t i = 0; i < n_bands; i++) out[i] = 20.0 * log10(out[i] > FO_EPS ? out[i] : FO_EPS);              /* :99 */
+}
+
+/* mags[F][B] -> bands[F][nBands]: init + processFrame per frame (the client's call: MelBandsClient.hpp:96-113) */
+FO_EXPORT void fo_melbands(const double* mags, int64_t F, int64_t n_bins, double lo, double hi, int64_t n_bands,
+                           double sample_rate, int64_t win, int mag_norm, int use_power, int log_output, double* bands)
+{
+  double* filt = (double*) malloc(sizeof(double) * (size_t) (n_bands * n_bins));
+  double* frame = (double*) malloc(sizeof(double) * (size_t) n_bins);
+  double s1, s2;
+  fo_melbands_init(lo, hi, n_bands, n_bins, sample_rate, win, filt, &s1, &s2);
+  for (int64_t f = 0; f < F; f++) {
+    memcpy(frame, mags + f * n_bins, sizeof(double) * (size_t) n_bins);
+    fo_melbands_frame(filt, n_bands, n_bins, s1, s2, frame, bands + f * n_bands, mag_norm, use_power, log_output);
+  }
+  free(filt); free(frame);
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * HPSS  algorithms/public/HPSS.hpp:47-162 + algorithms/util/MedianFilter.hpp:36-57, frame by frame from init() state.
+ * spec[F][B] complex in -> out[3][F][B] complex (harmonic, percussive, residual), exactly what processFrame emits per
+ * frame: the output of frame t belongs to input frame t - (hSize - 1) (zeros while the delay line fills).
+ * Restated literally, including the placement quirks: the vertical median of bin b runs over bins b .. b + vSize - 1
+ * (padded.segment(v2 * 3, nBins) of a causal filter over an array padded by v2 at the front, :79-89), the horizontal
+ * median is written to column h2 + 1 of its delay line (:91-93) and therefore reaches column 0 h2 + 1 frames later.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct { double* unsorted; double* sorted; int64_t n; } fo_median;
+static void fo_median_init(fo_median* m, int64_t n) { m->n = n; memset(m->unsorted, 0, sizeof(double) * (size_t) n); memset(m->sorted, 0, sizeof(double) * (size_t) n); }
+static double fo_median_push(fo_median* m, double val)
+{ /* MedianFilter::processSample :47-57 */
+  int64_t n = m->n;
+  double old = m->unsorted[0];
+  memmove(m->unsorted, m->unsorted + 1, sizeof(double) * (size_t) (n - 1));
+  m->unsorted[n - 1] = val;
+  int64_t lo = 0;                       /* lower_bound(old): first element >= old */
+  while (lo < n && m->sorted[lo] < old) lo++;
+  memmove(m->sorted + lo, m->sorted + lo + 1, sizeof(double) * (size_t) (n - 1 - lo));
+  int64_t up = 0;                       /* upper_bound(val) in the n-1 remaining: first element > val */
+  while (up < n - 1 && !(val < m->sorted[up])) up++;
+  memmove(m->sorted + up + 1, m->sorted + up, sizeof(double) * (size_t) (n - 1 - up));
+  m->sorted[up] = val;
+  return m->sorted[n / 2];
+}
+
+static void fo_hpss_threshold(int64_t n_bins, double x1, double y1, double x2, double y2, double* th)
+{ /* makeThreshold :164-181 */
+  int64_t ks = (int64_t) floor(x1 * (double) n_bins), ke = (int64_t) floor(x2 * (double) n_bins), kl = ke - ks;
+  for (int64_t i = 0; i < n_bins; i++) th[i] = 1.0;
+  for (int64_t i = 0; i < ks; i++) th[i] = pow(10.0, y1 / 20.0);
+  for (int64_t i = 0; i < kl; i++) th[ks + i] = pow(10.0, fo_linspaced(kl, y1, y2, i) / 20.0);
+  for (int64_t i = ke; i < n_bins; i++) th[i] = pow(10.0, y2 / 20.0);
+}
+
+FO_EXPORT void fo_hpss(const double* spec, int64_t F, int64_t B, int64_t v_size, int64_t h_size, int64_t mode, double hx1,
+                       double hy1, double hx2, double hy2, double px1, double py1, double px2, double py2, double* out)
+{
+  int64_t h2 = (h_size - 1) / 2, v2 = (v_size - 1) / 2;
+  double* v = (double*) calloc((size_t) (B * h_size), sizeof(double));
+  double* h = (double*) calloc((size_t) (B * h_size), sizeof(double));
+  double* buf = (double*) calloc((size_t) (2 * B * h_size), sizeof(double));
+  double* padded = (double*) malloc(sizeof(double) * (size_t) (2 * v_size + B));
+  double* hstore = (double*) calloc((size_t) (2 * B * h_size), sizeof(double));
+  fo_median* hf = (fo_median*) malloc(sizeof(fo_median) * (size_t) B);
+  for (int64_t b = 0; b < B; b++) { hf[b].unsorted = hstore + 2 * b * h_size; hf[b].sorted = hf[b].unsorted + h_size; fo_median_init(&hf[b], h_size); } /* :57-60 */
+  double* vstore = (double*) malloc(sizeof(double) * (size_t) (2 * v_size));
+  fo_median vf; vf.unsorted = vstore; vf.sorted = vstore + v_size;
+  double* th_h = (double*) malloc(sizeof(double) * (size_t) B);
+  double* th_p = (double*) malloc(sizeof(double) * (size_t) B);
+  fo_hpss_threshold(B, hx1, hy1, hx2, hy2, th_h);
+  fo_hpss_threshold(B, px1, py1, px2, py2, th_p);
+  for (int64_t t = 0; t < F; t++) {
+    const double* in = spec + 2 * t * B;
+    for (int64_t b = 0; b < B; b++) {                                       /* :74-76 shift the delay lines */
+      memmove(v + b * h_size, v + b * h_size + 1, sizeof(double) * (size_t) (h_size - 1));
+      memmove(h + b * h_size, h + b * h_size + 1, sizeof(double) * (size_t) (h_size - 1));
+      memmove(buf + 2 * b * h_size, buf + 2 * b * h_size + 2, sizeof(double) * (size_t) (2 * (h_size - 1)));
+    }
+    for (int64_t i = 0; i < 2 * v_size + B; i++) padded[i] = 0.0;           /* :78-79 */
+    for (int64_t b = 0; b < B; b++) padded[v2 + b] = hypot(in[2 * b], in[2 * b + 1]); /* :81 */
+    fo_median_init(&vf, v_size);                                            /* :82 */
+    for (int64_t i = 0; i < 2 * v_size + B; i++) padded[i] = fo_median_push(&vf, padded[i]); /* :83-86 */
+    for (int64_t b = 0; b < B; b++) {
+      v[b * h_size + h_size - 1] = padded[v2 * 3 + b];                      /* :88 */
+      buf[2 * (b * h_size + h_size - 1)] = in[2 * b];                       /* :89 */
+      buf[2 * (b * h_size + h_size - 1) + 1] = in[2 * b + 1];
+      h[b * h_size + h2 + 1] = fo_median_push(&hf[b], hypot(in[2 * b], in[2 * b + 1])); /* :90-92 */
+    }
+    for (int64_t b = 0; b < B; b++) {
+      double h0 = h[b * h_size], v0 = v[b * h_size];
+      double hm, pm, rm = mode == 2 ? 1.0 : 0.0;                            /* :97-98 */
+      if (mode == 0) {                                                      /* :101-107 */
+        double d = h0 + v0;
+        double mult = 1.0 / (d > FO_EPS ? d : FO_EPS);
+        hm = h0 * mult; pm = v0 * mult;
+      } else if (mode == 1) {                                               /* :108-115 */
+        hm = (h0 / v0) > th_h[b] ? 1.0 : 0.0;
+        pm = 1.0 - hm;
+      } else {                                                              /* :116-135 */
+        hm = (h0 / v0) > th_h[b] ? 1.0 : 0.0;
+        pm = (v0 / h0) > th_p[b] ? 1.0 : 0.0;
+        rm = rm * (1.0 - hm);
+        rm = rm * (1.0 - pm);
+        double nrm = 1.0 / (hm + pm + rm);
+        nrm = nrm > FO_EPS ? nrm : FO_EPS;
+        hm *= nrm; pm *= nrm; rm *= nrm;
+      }
+      double re = buf[2 * b * h_size], im = buf[2 * b * h_size + 1];
+      double m0 = hm < 1.0 ? hm : 1.0, m1 = pm < 1.0 ? pm : 1.0, m2 = rm < 1.0 ? rm : 1.0; /* :138-140 */
+      out[2 * ((0 * F + t) * B + b)] = re * m0; out[2 * ((0 * F + t) * B + b) + 1] = im * m0;
+      out[2 * ((1 * F + t) * B + b)] = re * m1; out[2 * ((1 * F + t) * B + b) + 1] = im * m1;
+      out[2 * ((2 * F + t) * B + b)] = re * m2; out[2 * ((2 * F + t) * B + b) + 1] = im * m2;
+    }
+  }
+  free(v); free(h); free(buf); free(padded); free(hstore); free(hf); free(vstore); free(th_h); free(th_p);
+}
+
 FO_EXPORT int fo_num_threads(void)
 {
 #ifdef _OPENMP

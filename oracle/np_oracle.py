@@ -399,3 +399,78 @@ def bufnmfcross(source_f32, target_f32, win, fft, hop, time_sparsity=7, polyphon
     H = nmfcross_process(np.abs(T), np.abs(S), iters, time_sparsity, min(S.shape[0], polyphony), continuity, seed)
     res = griffinlim(H @ S, t.size, gl_iters, win, fft, hop, seed)
     return istft(res, win, fft, hop, t.size).astype(np.float32), H
+
+
+# ---- MelBands.hpp:35-101 -------------------------------------------------------------------------------------------
+def melbands(mags, lo, hi, n_bands, sample_rate, win, mag_norm=True, use_power=False, log_output=False):
+    """mags[F][B] -> bands[F][nBands] (vectorised over frames; numpy.linspace == Eigen's LinSpaced for increasing ranges)."""
+    M = np.array(mags, dtype=np.float64)
+    B = M.shape[1]
+    fft = 2 * (B - 1)
+    s1 = 1.0 / (win / 4.0)
+    s2 = 1.0 / (2.0 * fft / win)
+    mel = np.linspace(1127.01048 * np.log(lo / 700.0 + 1.0), 1127.01048 * np.log(hi / 700.0 + 1.0), n_bands + 2)
+    mel = 700.0 * (np.exp(mel / 1127.01048) - 1.0)
+    freqs = np.linspace(0.0, sample_rate / 2.0, B)
+    d = np.abs(mel[:-1] - mel[1:])
+    ramps = mel[:, None] - freqs[None, :]
+    filt = np.maximum(np.minimum(-ramps[:-2] / d[:-1, None], ramps[2:] / d[1:, None]), 0.0)
+    if mag_norm:
+        M = M * s1
+    energy = M.sum(axis=1) * s2
+    if use_power:
+        M = M * M
+    out = M @ filt.T
+    if mag_norm:
+        out = out * energy[:, None] / np.maximum(EPS, out.sum(axis=1))[:, None]
+    if log_output:
+        out = 20.0 * np.log10(np.maximum(out, EPS))
+    return out
+
+
+# ---- HPSS.hpp:47-162 (+ MedianFilter.hpp:36-57), closed form of the streaming recursion -------------------------------
+def hpss(spec, v_size, h_size, mode=0, h_thresh=(0.0, 1.0, 1.0, 1.0), p_thresh=(0.0, 1.0, 1.0, 1.0)):
+    """spec[F][B] -> out[3][F][B].  Instead of replaying the delay lines this writes down what they hold:
+       output frame t carries input frame u = t - (hSize - 1);
+       v0(t)[b] = median(|X[u]|[b .. b + vSize - 1]) (zeros past the last bin)        -- the causal filter over the padded frame
+       h0(t)[b] = median(|X[w - hSize + 1 .. w]|[b]) with w = t - (h2 + 1) (zeros before the stream) -- column h2 + 1, shifted out later."""
+    S = np.asarray(spec, dtype=np.complex128)
+    F, B = S.shape
+    A = np.abs(S)
+    h2 = (h_size - 1) // 2
+    vpad = np.concatenate([A, np.zeros((F, v_size - 1))], axis=1)
+    vmed = np.median(np.lib.stride_tricks.sliding_window_view(vpad, v_size, axis=1), axis=2)          # [F][B]
+    hpad = np.concatenate([np.zeros((h_size - 1, B)), A], axis=0)
+    hmed = np.median(np.lib.stride_tricks.sliding_window_view(hpad, h_size, axis=0), axis=2)          # [F][B], causal in time
+
+    def delayed(X, d):
+        Y = np.zeros_like(X)
+        if d < F:
+            Y[d:] = X[:F - d]
+        return Y
+    X0 = delayed(S, h_size - 1)
+    v0 = delayed(vmed, h_size - 1)
+    h0 = delayed(hmed, h2 + 1)
+
+    def threshold(x1, y1, x2, y2):
+        th = np.ones(B)
+        ks, ke = int(np.floor(x1 * B)), int(np.floor(x2 * B))
+        th[:ks] = 10.0 ** (y1 / 20.0)
+        if ke > ks:
+            th[ks:ke] = 10.0 ** (np.linspace(y1, y2, ke - ks) / 20.0)
+        th[ke:] = 10.0 ** (y2 / 20.0)
+        return th
+    with np.errstate(divide="ignore", invalid="ignore"):
+        if mode == 0:
+            mult = 1.0 / np.maximum(h0 + v0, EPS)
+            hm, pm, rm = h0 * mult, v0 * mult, np.zeros_like(h0)
+        elif mode == 1:
+            hm = ((h0 / v0) > threshold(*h_thresh)[None, :]).astype(np.float64)
+            pm, rm = 1.0 - hm, np.zeros_like(h0)
+        else:
+            hm = ((h0 / v0) > threshold(*h_thresh)[None, :]).astype(np.float64)
+            pm = ((v0 / h0) > threshold(*p_thresh)[None, :]).astype(np.float64)
+            rm = (1.0 - hm) * (1.0 - pm)
+            nrm = np.maximum(1.0 / (hm + pm + rm), EPS)
+            hm, pm, rm = hm * nrm, pm * nrm, rm * nrm
+    return np.stack([X0 * np.minimum(hm, 1.0), X0 * np.minimum(pm, 1.0), X0 * np.minimum(rm, 1.0)])
