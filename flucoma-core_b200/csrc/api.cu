@@ -1133,6 +1133,228 @@ int32_t fb200_bufnmfcross(fb200_plan* p, const fb200_nmfcross_args* a)
   return cancelled ? FB200_CANCELLED : FB200_OK;
 }
 
+// NMFSeed: NMFSeedClient::process (clients/nrt/NMFSeedClient.hpp:74-133) = STFT -> magnitude -> NNDSVD::process
+// (algorithms/public/NNDSVD.hpp:30-131) -> bases rows / activations scaled by 1 / max
+int32_t fb200_nmfseed(fb200_plan* p, const fb200_nmfseed_args* a)
+{
+  if (!p) return FB200_ERR_INVALID;
+  if (!a || a->struct_size != sizeof(fb200_nmfseed_args) || (!a->audio && !a->mags) || !a->rank_out || a->min_rank < 0 ||
+      a->max_rank < 1 || a->min_rank > a->max_rank || a->method < 0 || a->method > 3 || a->coverage < 0 || a->coverage > 1 ||
+      !(a->coverage > 0 || a->min_rank > 0)) {   // NNDSVD.hpp:39 assert(amount > 0 || minRank > 0)
+    p->err = "fb200_nmfseed: bad arguments";
+    return FB200_ERR_INVALID;
+  }
+  FB_TRY(enter(p, a->mem));
+  StageTimer t(p);
+  t.mark(0);
+  const int64_t B = p->bins;
+  const int host = a->mem == FB200_HOST;
+  int64_t F = a->frames;
+  const float* d_mags = nullptr;
+  if (a->audio) {
+    if (a->n_samples <= 0) { p->err = "fb200_nmfseed: audio given without n_samples"; return FB200_ERR_INVALID; }
+    F = fb200_num_frames(a->n_samples, p->win, p->hop);                                       // :84-86
+    const void* raw;
+    FB_TRY(to_device_raw(p, a->audio, a->mem, sizeof(float) * (size_t) a->n_samples, p->audio, &raw));
+    FB_CUDA(p, p->V.ensure(sizeof(float) * (size_t) (F * B)));
+    FB_TRY(run_stft(p, (const float*) raw, 1, a->n_samples, F, p->V.as<float>(), F, B, nullptr, p->win / 2)); // :99-100
+    d_mags = p->V.as<float>();
+  } else {
+    if (F <= 0) { p->err = "fb200_nmfseed: frames must be positive"; return FB200_ERR_INVALID; }
+    const void* raw;
+    FB_TRY(to_device_raw(p, a->mags, a->mem, sizeof(float) * (size_t) (F * B), p->stage, &raw));
+    d_mags = (const float*) raw;
+  }
+  t.mark(1);
+  int n = 0;
+  FB_TRY(run_seed_svd(p, d_mags, (int) F, (int) B, &n));
+  // singular values to the host: order, coverage -> rank  (NNDSVD.hpp:46-58)
+  std::vector<double> nrm((size_t) n);
+  FB_CUDA(p, cudaMemcpyAsync(nrm.data(), p->x3.p, sizeof(double) * (size_t) n, cudaMemcpyDeviceToHost, p->stream));
+  FB_CUDA(p, cudaStreamSynchronize(p->stream));
+  std::vector<int> ord((size_t) n);
+  for (int i = 0; i < n; i++) ord[(size_t) i] = i;
+  std::stable_sort(ord.begin(), ord.end(), [&](int x, int y) { return nrm[(size_t) x] > nrm[(size_t) y]; });
+  const int64_t r = std::min<int64_t>(B, F);
+  int64_t k = 0;
+  if (a->coverage == 0) k = a->min_rank;
+  else {
+    double cur = 0, total = 0;
+    for (int64_t i = 0; i < r; i++) total += nrm[(size_t) ord[(size_t) i]];
+    while ((cur / total) < a->coverage && k < r) cur += nrm[(size_t) ord[(size_t) k++]];
+  }
+  if (k < a->min_rank) k = a->min_rank;
+  if (k > a->max_rank) k = a->max_rank;
+  if (k > r) k = r;
+  *a->rank_out = (int32_t) k;
+  if (a->singular_values)
+    for (int64_t i = 0; i < r; i++) a->singular_values[i] = nrm[(size_t) ord[(size_t) i]];
+  const int64_t R = a->max_rank;
+  FB_CUDA(p, p->W.ensure(sizeof(float) * (size_t) (R * B)));
+  FB_CUDA(p, p->H.ensure(sizeof(float) * (size_t) (F * R)));
+  FB_CUDA(p, cudaMemsetAsync(p->W.p, 0, sizeof(float) * (size_t) (R * B), p->stream));      // the client allocates zero-filled tensors (:93-94)
+  FB_CUDA(p, cudaMemsetAsync(p->H.p, 0, sizeof(float) * (size_t) (F * R), p->stream));
+  FB_CUDA(p, p->x4.ensure(sizeof(int) * (size_t) n));
+  FB_CUDA(p, cudaMemcpyAsync(p->x4.p, ord.data(), sizeof(int) * (size_t) n, cudaMemcpyHostToDevice, p->stream));
+  launch_seed_build(p, p->x4.as<int>(), (int) k, (int) F, (int) B, n, (int) R, a->method, p->W.as<float>(), p->H.as<float>());
+  if (a->method == 1 || a->method == 2) {
+    const float* U = nullptr;
+    if (a->method == 1) { // both generators restart from the seed (:108-113); one stream long enough for the larger matrix
+      bool neg = false;
+      int64_t seed = a->seed;
+      FB_TRY(upload_seeds(p, &seed, 1, &neg));
+      const int64_t cnt = std::max(R * B, F * R);
+      FB_CUDA(p, p->rnd.ensure(sizeof(float) * (size_t) cnt));
+      launch_mt_uniform(p, p->seeds.as<int64_t>(), 1, cnt, p->rnd.as<float>());
+      U = p->rnd.as<float>();
+    }
+    launch_seed_fill(p, p->W.as<float>(), p->H.as<float>(), (int) F, (int) B, (int) R, a->method, d_mags, U);
+  }
+  FB_CUDA(p, cudaStreamSynchronize(p->stream)); // `ord` dies at scope exit
+  t.mark(2);
+  // outputs: bases [max_rank][B]; activations [F][max_rank], scaled by 1 / max over ALL of H as the client does (:119-128)
+  if (a->bases) {
+    const size_t bytes = sizeof(float) * (size_t) (R * B);
+    FB_CUDA(p, cudaMemcpyAsync(a->bases, p->W.p, bytes, host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, p->stream));
+  }
+  if (a->acts) {
+    NmfDev d{};
+    d.batch = 1; d.F = (int) F; d.Fp = (int) F; d.K = (int) R; d.KP = (int) R; d.H = p->H.as<float>();
+    const float* scale = nullptr;
+    if (a->scale_acts) {
+      FB_CUDA(p, p->scale.ensure(sizeof(float)));
+      launch_h_max_scale(p, d, p->scale.as<float>());
+      scale = p->scale.as<float>();
+    }
+    float* dst = a->acts;
+    const size_t bytes = sizeof(float) * (size_t) (F * R);
+    if (host) { FB_CUDA(p, p->out_b.ensure(bytes)); dst = p->out_b.as<float>(); }
+    launch_copy3d(p, p->H.p, FB200_F32, 0, R, dst, FB200_F32, 0, R, 1, F, R, scale, 0);
+    if (host) FB_CUDA(p, cudaMemcpyAsync(a->acts, dst, bytes, cudaMemcpyDeviceToHost, p->stream));
+  }
+  t.mark(3);
+  FB_TRY(finish(p, t, 3));
+  p->stats.ms_h2d = t.ms(0, 1); p->stats.ms_init = t.ms(1, 2); p->stats.ms_d2h = t.ms(2, 3);
+  return FB200_OK;
+}
+
+// MelBands over a frame sequence: MelBands::init (MelBands.hpp:43-80, evaluated on the host in fp64) + processFrame (:82-101)
+int32_t fb200_melbands(fb200_plan* p, const fb200_melbands_args* a)
+{
+  if (!p) return FB200_ERR_INVALID;
+  if (!a || a->struct_size != sizeof(fb200_melbands_args) || a->batch <= 0 || !a->bands || (!a->mags && !a->audio) ||
+      a->n_bands < 2 || !(a->hi > a->lo) || a->sample_rate <= 0) {   // asserts of init(): hi > lo, nBands > 1
+    p->err = "fb200_melbands: bad arguments";
+    return FB200_ERR_INVALID;
+  }
+  FB_TRY(enter(p, a->mem));
+  StageTimer t(p);
+  t.mark(0);
+  const int64_t B = p->bins, nb = a->n_bands;
+  const int host = a->mem == FB200_HOST;
+  int64_t F = a->frames;
+  const float* d_mags = nullptr;
+  if (a->audio) { // STFT::process + magnitude first (STFT.hpp:90-108, 61-66)
+    if (a->n_samples <= 0) { p->err = "fb200_melbands: audio given without n_samples"; return FB200_ERR_INVALID; }
+    F = fb200_num_frames(a->n_samples, p->win, p->hop);
+    const void* raw;
+    FB_TRY(to_device_raw(p, a->audio, a->mem, sizeof(float) * (size_t) (a->batch * a->n_samples), p->audio, &raw));
+    FB_CUDA(p, p->V.ensure(sizeof(float) * (size_t) (a->batch * F * B)));
+    FB_TRY(run_stft(p, (const float*) raw, a->batch, a->n_samples, F, p->V.as<float>(), F, B, nullptr, p->win / 2));
+    d_mags = p->V.as<float>();
+  } else {
+    if (F <= 0) { p->err = "fb200_melbands: frames must be positive"; return FB200_ERR_INVALID; }
+    const void* raw;
+    FB_TRY(to_device_raw(p, a->mags, a->mem, sizeof(float) * (size_t) (a->batch * F * B), p->stage, &raw));
+    d_mags = (const float*) raw;
+  }
+  // MelBands::init: triangular filters between nBands + 2 points equally spaced on the mel scale
+  std::vector<float> filt((size_t) (nb * B));
+  const double fft = 2.0 * (double) (B - 1);
+  const double scale1 = 1.0 / ((double) p->win / 4.0), scale2 = 1.0 / (2.0 * fft / (double) p->win);   // :50-53
+  {
+    auto hz2mel = [](double x) { return 1127.01048 * std::log(x / 700.0 + 1.0); };                   // :38-41
+    const double mlo = hz2mel(a->lo), mhi = hz2mel(a->hi);
+    auto lin = [](int64_t n, double lo, double hi, int64_t i) {  // Eigen LinSpaced for doubles (evaluated from the end nearer zero)
+      if (n == 1) return hi;
+      const double step = (hi - lo) / (double) (n - 1);
+      if (std::fabs(hi) < std::fabs(lo)) return i == 0 ? lo : hi - (double) (n - 1 - i) * step;
+      return i == n - 1 ? hi : lo + (double) i * step;
+    };
+    std::vector<double> mel((size_t) (nb + 2));
+    for (int64_t i = 0; i < nb + 2; i++) mel[(size_t) i] = 700.0 * (std::exp(lin(nb + 2, mlo, mhi, i) / 1127.01048) - 1.0); // :55-56
+    for (int64_t i = 0; i < nb; i++) {
+      const double d0 = std::fabs(mel[(size_t) i] - mel[(size_t) i + 1]), d1 = std::fabs(mel[(size_t) i + 1] - mel[(size_t) i + 2]);
+      for (int64_t b = 0; b < B; b++) {
+        const double f = lin(B, 0.0, a->sample_rate / 2.0, b);                                         // :60
+        const double lower = -(mel[(size_t) i] - f) / d0, upper = (mel[(size_t) i + 2] - f) / d1;      // :72-73
+        filt[(size_t) (i * B + b)] = (float) std::max(0.0, std::min(lower, upper));                    // :74
+      }
+    }
+  }
+  FB_CUDA(p, p->x0.ensure(sizeof(float) * filt.size()));
+  FB_CUDA(p, cudaMemcpyAsync(p->x0.p, filt.data(), sizeof(float) * filt.size(), cudaMemcpyHostToDevice, p->stream));
+  FB_CUDA(p, cudaStreamSynchronize(p->stream)); // `filt` dies at scope exit
+  t.mark(1);
+  float* d_out = a->bands;
+  const size_t obytes = sizeof(float) * (size_t) (a->batch * F * nb);
+  if (host) { FB_CUDA(p, p->out_a.ensure(obytes)); d_out = p->out_a.as<float>(); }
+  launch_melbands(p, d_mags, p->x0.as<float>(), a->batch * F, (int) B, (int) nb, (float) scale1, (float) scale2, a->flags, d_out);
+  if (host) FB_CUDA(p, cudaMemcpyAsync(a->bands, d_out, obytes, cudaMemcpyDeviceToHost, p->stream));
+  t.mark(2);
+  FB_TRY(finish(p, t, 2));
+  p->stats.ms_h2d = t.ms(0, 1); p->stats.ms_post = t.ms(1, 2);
+  return FB200_OK;
+}
+
+// HPSS::processFrame over frame sequences from init() state (HPSS.hpp:47-162): spectrum [batch][F][B] -> out [batch][3][F][B]
+int32_t fb200_hpss(fb200_plan* p, const fb200_hpss_args* a)
+{
+  if (!p) return FB200_ERR_INVALID;
+  if (!a || a->struct_size != sizeof(fb200_hpss_args) || a->batch <= 0 || a->frames <= 0 || !a->spectrum || !a->out ||
+      a->v_size < 3 || a->h_size < 3 || !(a->v_size & 1) || !(a->h_size & 1) || a->v_size > 129 || a->h_size > 129 ||
+      a->v_size > p->bins || a->mode < 0 || a->mode > 2) {   // MedianFilter::init asserts size >= 3 and odd; processFrame vSize <= bins
+    p->err = "fb200_hpss: bad arguments (filter sizes must be odd, 3 .. 129, percussive size <= bins; mode 0 .. 2)";
+    return FB200_ERR_INVALID;
+  }
+  FB_TRY(enter(p, a->mem));
+  StageTimer t(p);
+  t.mark(0);
+  const int64_t B = p->bins, F = a->frames, cnt = a->batch * F * B;
+  const int host = a->mem == FB200_HOST;
+  const void* raw;
+  FB_TRY(to_device_raw(p, a->spectrum, a->mem, sizeof(float2) * (size_t) cnt, p->stage, &raw));
+  // makeThreshold (:164-181), fp64 on the host
+  std::vector<float> th((size_t) (2 * B), 1.0f);
+  for (int which = 0; which < 2; which++) {
+    const double x1 = a->thresholds[4 * which], y1 = a->thresholds[4 * which + 1], x2 = a->thresholds[4 * which + 2], y2 = a->thresholds[4 * which + 3];
+    const int64_t ks = (int64_t) std::floor(x1 * (double) B), ke = (int64_t) std::floor(x2 * (double) B), kl = ke - ks;
+    float* th1 = th.data() + which * B;
+    for (int64_t i = 0; i < ks && i < B; i++) th1[i] = (float) std::pow(10.0, y1 / 20.0);
+    for (int64_t i = 0; i < kl && ks + i < B; i++) {
+      const double step = kl > 1 ? (y2 - y1) / (double) (kl - 1) : 0.0;
+      const double y = kl == 1 ? y2 : (std::fabs(y2) < std::fabs(y1) ? (i == 0 ? y1 : y2 - (double) (kl - 1 - i) * step) : (i == kl - 1 ? y2 : y1 + (double) i * step));
+      th1[ks + i] = (float) std::pow(10.0, y / 20.0);
+    }
+    for (int64_t i = std::max<int64_t>(ke, 0); i < B; i++) th1[i] = (float) std::pow(10.0, y2 / 20.0);
+  }
+  FB_CUDA(p, p->x0.ensure(sizeof(float) * th.size()));
+  FB_CUDA(p, cudaMemcpyAsync(p->x0.p, th.data(), sizeof(float) * th.size(), cudaMemcpyHostToDevice, p->stream));
+  FB_CUDA(p, cudaStreamSynchronize(p->stream));
+  FB_CUDA(p, p->x1.ensure(sizeof(float) * (size_t) cnt));
+  t.mark(1);
+  float2* d_out = reinterpret_cast<float2*>(a->out);
+  const size_t obytes = sizeof(float2) * (size_t) (3 * cnt);
+  if (host) { FB_CUDA(p, p->cspec.ensure(obytes)); d_out = p->cspec.as<float2>(); }
+  launch_hpss(p, (const float2*) raw, p->x1.as<float>(), a->batch, (int) F, (int) B, a->v_size, a->h_size, a->mode, p->x0.as<float>(),
+              p->x0.as<float>() + B, d_out);
+  if (host) FB_CUDA(p, cudaMemcpyAsync(a->out, d_out, obytes, cudaMemcpyDeviceToHost, p->stream));
+  t.mark(2);
+  FB_TRY(finish(p, t, 2));
+  p->stats.ms_h2d = t.ms(0, 1); p->stats.ms_post = t.ms(1, 2);
+  return FB200_OK;
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 int32_t fb200_bufstft_sizes(int32_t win, int32_t hop, int32_t padding_mode, int32_t invert, int64_t count, int64_t* padding,
                             int64_t* out)
@@ -1259,7 +1481,7 @@ const fb200_api* fb200_get_api(uint32_t abi_version)
                                 fb200_plan_destroy, fb200_last_error, fb200_num_frames, fb200_resolve_fft,
                                 fb200_shard_range, fb200_stft, fb200_istft, fb200_nmf_process, fb200_nmf_process_frames,
                                 fb200_bufnmf, fb200_nmf_filter, fb200_get_stats, fb200_bufstft_sizes, fb200_bufstft,
-                                fb200_nmf_filter_frames, fb200_bufnmf_sharded, fb200_bufnmfcross};
+                                fb200_nmf_filter_frames, fb200_bufnmf_sharded, fb200_bufnmfcross, fb200_melbands, fb200_hpss, fb200_nmfseed};
   return abi_version == FB200_ABI_VERSION ? &api : nullptr;
 }
 

@@ -201,6 +201,18 @@ bool stft_fused_eligible(const Plan* p, const float* audio, int64_t n, int64_t b
 int32_t launch_stft_fused(Plan* p, const float* audio, int64_t batch, int64_t n, int64_t F, float* V, int64_t Fp, int64_t Bp,
                           float2* spec, int64_t half, int hop);
 
+// kernels_seed.cu (NNDSVD.hpp:30-131) ---------------------------------------------------------------------------------
+// one-sided Jacobi SVD of X^T in fp64: leaves A (rotated rows) in x1, J (accumulated rotations) in x2, row norms in x3
+int32_t run_seed_svd(Plan* p, const float* mags, int F, int B, int* n_out);
+void launch_seed_build(Plan* p, const int* d_ord, int k, int F, int B, int n, int max_rank, int method, float* W, float* H);
+void launch_seed_fill(Plan* p, float* W, float* H, int F, int B, int max_rank, int method, const float* mags, const float* U);
+
+// kernels_spectral.cu (MelBands.hpp:35-101, HPSS.hpp:47-162) ------------------------------------------------------
+void launch_melbands(Plan* p, const float* mags, const float* filt, int64_t frames, int B, int nb, float scale1, float scale2, int flags,
+                     float* bands);
+void launch_hpss(Plan* p, const float2* spec, float* mag, int64_t batch, int F, int B, int vsize, int hsize, int mode, const float* th_h,
+                 const float* th_p, float2* out);
+
 // kernels_cross.cu (BufNMFCross: NMFCross.hpp:60-185, GriffinLim.hpp:29-54) -----------------------------------------
 void launch_sgemm_nn(Plan* p, const float* A, const float* B, float* C, int M, int N, int K); // C[M][N] = A[M][K] B[K][N]
 void launch_cross_prepare(Plan* p, float* W, int R, int B, float* energy, float* hden);

@@ -80,6 +80,25 @@ class NmfCrossArgs(C.Structure):
                 ("progress_user", C.c_void_p)]
 
 
+class MelBandsArgs(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("mem", C.c_int32), ("batch", C.c_int64), ("frames", C.c_int64),
+                ("n_samples", C.c_int64), ("n_bands", C.c_int32), ("flags", C.c_int32), ("lo", C.c_double), ("hi", C.c_double),
+                ("sample_rate", C.c_double), ("mags", C.c_void_p), ("audio", C.c_void_p), ("bands", C.c_void_p)]
+
+
+class HpssArgs(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("mem", C.c_int32), ("batch", C.c_int64), ("frames", C.c_int64),
+                ("v_size", C.c_int32), ("h_size", C.c_int32), ("mode", C.c_int32), ("reserved", C.c_int32),
+                ("thresholds", C.c_double * 8), ("spectrum", C.c_void_p), ("out", C.c_void_p)]
+
+
+class NmfSeedArgs(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("mem", C.c_int32), ("n_samples", C.c_int64), ("frames", C.c_int64),
+                ("min_rank", C.c_int32), ("max_rank", C.c_int32), ("coverage", C.c_double), ("method", C.c_int32),
+                ("scale_acts", C.c_int32), ("seed", C.c_int64), ("audio", C.c_void_p), ("mags", C.c_void_p),
+                ("bases", C.c_void_p), ("acts", C.c_void_p), ("singular_values", C.c_void_p), ("rank_out", C.c_void_p)]
+
+
 class ShardedArgs(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("n_devices", C.c_int32), ("plans", C.POINTER(C.c_void_p)),
                 ("job", C.POINTER(BufNmfArgs)), ("gathered_acts", C.POINTER(C.c_void_p))]
@@ -102,7 +121,7 @@ class Stats(C.Structure):
 SYMBOLS = ["fb200_abi_version", "fb200_device_count", "fb200_plan_create", "fb200_plan_destroy", "fb200_last_error",
            "fb200_num_frames", "fb200_resolve_fft", "fb200_shard_range", "fb200_stft", "fb200_istft",
            "fb200_nmf_process", "fb200_nmf_process_frames", "fb200_bufnmf", "fb200_nmf_filter", "fb200_get_stats",
-           "fb200_get_api", "fb200_selftest_tcgen05", "fb200_bufstft_sizes", "fb200_bufstft", "fb200_nmf_filter_frames", "fb200_bufnmf_sharded", "fb200_bufnmfcross"]
+           "fb200_get_api", "fb200_selftest_tcgen05", "fb200_bufstft_sizes", "fb200_bufstft", "fb200_nmf_filter_frames", "fb200_bufnmf_sharded", "fb200_bufnmfcross", "fb200_melbands", "fb200_hpss", "fb200_nmfseed"]
 
 _lib = None
 
@@ -143,7 +162,8 @@ def load(path: str | None = None):
     L.fb200_istft.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_int32]
     for name, T in (("fb200_nmf_process", NmfArgs), ("fb200_nmf_process_frames", FramesArgs),
                     ("fb200_bufnmf", BufNmfArgs), ("fb200_nmf_filter", FilterArgs), ("fb200_bufstft", BufStftArgs),
-                    ("fb200_nmf_filter_frames", FilterFramesArgs), ("fb200_bufnmfcross", NmfCrossArgs)):
+                    ("fb200_nmf_filter_frames", FilterFramesArgs), ("fb200_bufnmfcross", NmfCrossArgs),
+                    ("fb200_melbands", MelBandsArgs), ("fb200_hpss", HpssArgs), ("fb200_nmfseed", NmfSeedArgs)):
         fn = getattr(L, name)
         fn.restype = C.c_int32
         fn.argtypes = [C.c_void_p, C.POINTER(T)]
@@ -483,6 +503,64 @@ class Plan:
                          iterations, seed, griffinlim_iterations, 0, _ptr(s_), _ptr(t_), _ptr(out), _ptr(acts), cb, None)
         st = self._check(self._L.fb200_bufnmfcross(self._h, C.byref(a)))
         return out, acts, st
+
+    def nmfseed(self, mags=None, audio=None, min_rank=1, max_rank=200, coverage=0.5, method=0, seed=-1, scale_acts=False):
+        """NMFSeed / NNDSVD (NNDSVD.hpp:30-131, NMFSeedClient.hpp:74-133): magnitudes float32 [F][bins] or mono audio [n] ->
+        (rank, bases [max_rank][bins], acts [F][max_rank], singular values)."""
+        x = self._contig(mags if mags is not None else audio)
+        assert _dtype_code(x) == F32
+        if mags is not None:
+            F, n = x.shape[0], 0
+            assert x.shape[1] == self.bins
+        else:
+            n = x.shape[0]
+            F = num_frames(n, self.win, self.hop)
+        bases = self._empty_like_space(x, (max_rank, self.bins), "float32")
+        acts = self._empty_like_space(x, (F, max_rank), "float32")
+        sv = np.zeros(min(F, self.bins))
+        rank = C.c_int32(0)
+        a = NmfSeedArgs(C.sizeof(NmfSeedArgs), DEVICE if self._dev(x) else HOST, n, F, min_rank, max_rank, float(coverage), method,
+                        int(scale_acts), seed, _ptr(x) if mags is None else None, _ptr(x) if mags is not None else None, _ptr(bases),
+                        _ptr(acts), _ptr(sv), C.cast(C.pointer(rank), C.c_void_p))
+        self._check(self._L.fb200_nmfseed(self._h, C.byref(a)))
+        return int(rank.value), bases, acts, sv
+
+    def melbands(self, mags=None, audio=None, n_bands=40, lo=20.0, hi=20000.0, sample_rate=44100.0, mag_norm=True, use_power=False,
+                 log_output=False):
+        """MelBands (MelBands.hpp:43-101) of magnitudes float32 [batch][F][bins] (or [F][bins]) or of audio [batch][n]."""
+        x = self._contig(mags if mags is not None else audio)
+        assert _dtype_code(x) == F32
+        squeeze = x.ndim == (2 if mags is not None else 1)
+        if squeeze:
+            x = x[None]
+        batch = x.shape[0]
+        if mags is not None:
+            F, n = x.shape[1], 0
+            assert x.shape[2] == self.bins
+        else:
+            n = x.shape[1]
+            F = num_frames(n, self.win, self.hop)
+        out = self._empty_like_space(x, (batch, F, n_bands), "float32")
+        flags = (1 if mag_norm else 0) | (2 if use_power else 0) | (4 if log_output else 0)
+        a = MelBandsArgs(C.sizeof(MelBandsArgs), DEVICE if self._dev(x) else HOST, batch, F, n, n_bands, flags, lo, hi, sample_rate,
+                         _ptr(x) if mags is not None else None, _ptr(x) if mags is None else None, _ptr(out))
+        self._check(self._L.fb200_melbands(self._h, C.byref(a)))
+        return out[0] if squeeze else out
+
+    def hpss(self, spectrum, v_size=31, h_size=17, mode=0, h_thresh=(0.0, 1.0, 1.0, 1.0), p_thresh=(0.0, 1.0, 1.0, 1.0)):
+        """HPSS::processFrame over spectrum complex64 [batch][F][bins] (or [F][bins]) -> [batch][3][F][bins]."""
+        s_ = self._contig(spectrum)
+        assert _dtype_code(s_) == F32
+        squeeze = s_.ndim == 2
+        if squeeze:
+            s_ = s_[None]
+        batch, F, B = s_.shape
+        assert B == self.bins
+        out = self._empty_like_space(s_, (batch, 3, F, B), "complex64")
+        a = HpssArgs(C.sizeof(HpssArgs), DEVICE if self._dev(s_) else HOST, batch, F, v_size, h_size, mode, 0,
+                     (C.c_double * 8)(*[float(v) for v in (*h_thresh, *p_thresh)]), _ptr(s_), _ptr(out))
+        self._check(self._L.fb200_hpss(self._h, C.byref(a)))
+        return out[0] if squeeze else out
 
     def nmf_filter_frames(self, frames, bases, iterations=10, seed=-1, want_out=True, want_acts=True):
         """frames float32 [nf][win] (raw, as FluidSource::pull cuts them) + bases [K][bins] -> (out [nf][K][win] | None,

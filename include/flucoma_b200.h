@@ -223,6 +223,67 @@ typedef struct fb200_nmfcross_args {
 } fb200_nmfcross_args;
 FB200_API int32_t fb200_bufnmfcross(fb200_plan* plan, const fb200_nmfcross_args* args);
 
+/* ---- NMFSeed: NMFSeedClient::process  (clients/nrt/NMFSeedClient.hpp:74-133; NNDSVD.hpp:30-131) --------------------------- */
+/* SVD-based seeds for BufNMF's bases / activations (feed them to fb200_bufnmf with bases_mode = acts_mode = 1).  Input: mono
+ * audio [n_samples] (STFT::process + magnitude run first) or magnitudes [frames][bins].  The thin SVD of X^T is computed on
+ * the device (one-sided Jacobi, fp64).  *rank_out = number of components that cover `coverage` of the singular-value sum,
+ * clamped to [min_rank, max_rank] (:46-58).  bases [max_rank][bins] and acts [frames][max_rank] have their first *rank_out
+ * rows / columns filled (the rest: zeros, or the fill of methods 1 / 2, exactly as the reference's full-size matrices).
+ * method 0 NMF-SVD, 1 NNDSVDar, 2 NNDSVDa, 3 NNDSVD.  Methods 1-3 depend on the sign of each singular pair through the
+ * reference's `yNNorm = xN.norm()` (:84, kept as written); Eigen's BDCSVD sign is unspecified, this library fixes it by making
+ * the largest-magnitude entry of every left vector positive.  scale_acts != 0 multiplies acts by 1 / max(acts) (:121-128). */
+typedef struct fb200_nmfseed_args {
+  uint32_t struct_size;
+  int32_t mem;
+  int64_t n_samples, frames;
+  int32_t min_rank, max_rank;      /* client defaults 1, 200 */
+  double coverage;                 /* 0.5 */
+  int32_t method, scale_acts;
+  int64_t seed;                    /* method 1 */
+  const float* audio;              /* or NULL */
+  const float* mags;               /* or NULL */
+  float* bases;                    /* optional out */
+  float* acts;                     /* optional out */
+  double* singular_values;         /* optional out, HOST memory, [min(bins, frames)] descending */
+  int32_t* rank_out;               /* HOST memory */
+} fb200_nmfseed_args;
+FB200_API int32_t fb200_nmfseed(fb200_plan* plan, const fb200_nmfseed_args* args);
+
+/* ---- epilogues on the STFT output: MelBands and HPSS over whole frame sequences ------------------------------ */
+/* MelBands::init + processFrame (algorithms/public/MelBands.hpp:43-101; MelBandsClient.hpp:96-113 calls it with usePower =
+ * false).  Input either magnitudes mags [batch][frames][bins] or audio [batch][n_samples] (then STFT::process + magnitude run
+ * first, frames = fb200_num_frames(n_samples)); bands [batch][frames][n_bands].  The window size of the scale factors is the
+ * plan's.  flags: 1 magNorm (client: normalize), 2 usePower, 4 logOutput (client: scale = dB). */
+typedef struct fb200_melbands_args {
+  uint32_t struct_size;
+  int32_t mem;
+  int64_t batch, frames, n_samples;
+  int32_t n_bands, flags;
+  double lo, hi, sample_rate;       /* client defaults: 20, 20000 Hz; 40 bands */
+  const float* mags;                /* or NULL */
+  const float* audio;               /* or NULL */
+  float* bands;
+} fb200_melbands_args;
+FB200_API int32_t fb200_melbands(fb200_plan* plan, const fb200_melbands_args* args);
+
+/* HPSS::processFrame (algorithms/public/HPSS.hpp:66-162, median filters algorithms/util/MedianFilter.hpp:36-57) applied to
+ * the frames of spectrum [batch][frames][bins] (complex, interleaved) in order from init() state.  out [batch][3][frames][bins]:
+ * harmonic, percussive, residual spectra exactly as processFrame emits them, i.e. output frame t belongs to input frame
+ * t - (h_size - 1) (zeros while the delay line fills; HPSSClient::latency adds one window, HPSSClient.hpp:80-84).
+ * v_size = percussive (vertical, across bins) filter size, h_size = harmonic (horizontal, across frames) filter size, both
+ * odd; mode 0 classic soft masks, 1 coupled, 2 advanced; thresholds = {hX1, hY1, hX2, hY2, pX1, pY1, pX2, pY2} (x as a
+ * fraction of the bins, y in dB; used by modes 1 and 2, makeThreshold :164-181). */
+typedef struct fb200_hpss_args {
+  uint32_t struct_size;
+  int32_t mem;
+  int64_t batch, frames;
+  int32_t v_size, h_size, mode, reserved;
+  double thresholds[8];
+  const float* spectrum;
+  float* out;
+} fb200_hpss_args;
+FB200_API int32_t fb200_hpss(fb200_plan* plan, const fb200_hpss_args* args);
+
 /* ---- BufNMF over several devices of one process ------------------------------------------------------------ */
 /* The channels / buffers of a BufNMF job are independent (NMFClient.hpp:233 loops over them), so the job is cut into
  * contiguous shards (fb200_shard_range), one per plan; every shard runs the whole pipeline on its plan's device from its
@@ -324,6 +385,9 @@ typedef struct fb200_api {
   int32_t (*nmf_filter_frames)(fb200_plan*, const fb200_filter_frames_args*);
   int32_t (*bufnmf_sharded)(const fb200_sharded_args*);
   int32_t (*bufnmfcross)(fb200_plan*, const fb200_nmfcross_args*);
+  int32_t (*melbands)(fb200_plan*, const fb200_melbands_args*);
+  int32_t (*hpss)(fb200_plan*, const fb200_hpss_args*);
+  int32_t (*nmfseed)(fb200_plan*, const fb200_nmfseed_args*);
 } fb200_api;
 /* returns NULL when abi_version is not supported */
 FB200_API const fb200_api* fb200_get_api(uint32_t abi_version);

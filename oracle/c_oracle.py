@@ -81,6 +81,8 @@ def lib(path: str | None = None):
     L.fo_melbands.argtypes = [_pd, _i64, _i64, C.c_double, C.c_double, _i64, C.c_double, _i64, C.c_int, C.c_int, C.c_int, _pd]
     L.fo_melbands_init.argtypes = [C.c_double, C.c_double, _i64, _i64, C.c_double, _i64, _pd, _pd, _pd]
     L.fo_hpss.argtypes = [_pd, _i64, _i64, _i64, _i64, _i64] + [C.c_double] * 8 + [_pd]
+    L.fo_nndsvd.restype = _i64
+    L.fo_nndsvd.argtypes = [_pd, _i64, _i64, _i64, _i64, C.c_double, _i64, _i64, _pd, _pd, _pd]
     L.fo_num_threads.restype = C.c_int
     L.fo_bufstft_sizes.restype = C.c_int
     L.fo_bufstft_sizes.argtypes = [_i64, _i64, _i64, C.c_int, _i64, _pi64, _pi64]
@@ -372,6 +374,15 @@ def hpss(spec, v_size, h_size, mode=0, h_thresh=(0.0, 1.0, 1.0, 1.0), p_thresh=(
     lib().fo_hpss(_d(S.view(np.float64)), F, B, v_size, h_size, mode, *[float(x) for x in h_thresh], *[float(x) for x in p_thresh],
                   _d(out.view(np.float64)))
     return out
+
+
+def nndsvd(X, min_rank=1, max_rank=200, amount=0.5, method=0, seed=-1):
+    """NNDSVD::process: X[F][B] -> (k, W[max_rank][B], H[F][max_rank], singular values)."""
+    X = _c64(X)
+    F, B = X.shape
+    W = np.zeros((max_rank, B)); H = np.zeros((F, max_rank)); sv = np.zeros(min(F, B))
+    k = lib().fo_nndsvd(_d(X), F, B, min_rank, max_rank, float(amount), method, seed, _d(W), _d(H), _d(sv))
+    return int(k), W, H, sv
 
 
 def num_threads():

@@ -1230,6 +1230,131 @@ FO_EXPORT void fo_hpss(const double* spec, int64_t F, int64_t B, int64_t v_size,
   free(v); free(h); free(buf); free(padded); free(hstore); free(hf); free(vstore); free(th_h); free(th_p);
 }
 
+/* ------------------------------------------------------------------------------------------------
+ * NNDSVD  algorithms/public/NNDSVD.hpp:30-131  (NMFSeed: SVD-based seeds for W and H)
+ * The reference calls Eigen::BDCSVD (thin U, V) on X^T (bins x frames).  The SVD is restated as a one-sided Jacobi
+ * iteration in fp64 (singular values and, up to the sign of each (u, v) pair, singular vectors are unique for distinct
+ * singular values).  Method 0 takes absolute values, so the sign does not matter.  Methods 1-3 split u, v into positive
+ * and negative parts, and -- because of the reference's `yNNorm = xN.norm()` (:84), restated as written -- their result
+ * DOES depend on the sign BDCSVD happens to return, which no public contract fixes.  This restatement (and the GPU path)
+ * fix it by a convention: the entry of u of largest magnitude is positive.
+ * X[F][B] -> W[max_rank][B], H[F][max_rank] (both must come in zero-filled, as the client allocates them); returns k.
+ * ---------------------------------------------------------------------------------------------- */
+static void fo_svd_jacobi(const double* X, int64_t F, int64_t B, double* U /*[r][B] rows = left vectors of X^T*/,
+                          double* s /*[r]*/, double* V /*[r][F]*/)
+{ /* columns of A = X (F x B) are orthogonalised: A J = Q Sigma  =>  X^T = J Sigma Q^T */
+  double* A = (double*) malloc(sizeof(double) * (size_t) (B * F)); /* A^T: row b = column b of X */
+  double* J = (double*) calloc((size_t) (B * B), sizeof(double));  /* J^T: row b = column b of J */
+  for (int64_t b = 0; b < B; b++) { J[b * B + b] = 1.0; for (int64_t f = 0; f < F; f++) A[b * F + f] = X[f * B + b]; }
+  for (int sweep = 0; sweep < 60; sweep++) {
+    double off = 0.0;
+    for (int64_t i = 0; i < B - 1; i++)
+      for (int64_t j = i + 1; j < B; j++) {
+        double a = 0.0, bb = 0.0, c = 0.0;
+        const double *x = A + i * F, *y = A + j * F;
+        for (int64_t f = 0; f < F; f++) { a += x[f] * x[f]; bb += y[f] * y[f]; c += x[f] * y[f]; }
+        if (c == 0.0 || a == 0.0 || bb == 0.0) continue;
+        double rel = fabs(c) / sqrt(a * bb);
+        if (rel > off) off = rel;
+        if (rel < 1e-15) continue;
+        double zeta = (bb - a) / (2.0 * c);
+        double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+        double cs = 1.0 / sqrt(1.0 + t * t), sn = cs * t;
+        double *xi = A + i * F, *yj = A + j * F;
+        for (int64_t f = 0; f < F; f++) { double p = xi[f], q = yj[f]; xi[f] = cs * p - sn * q; yj[f] = sn * p + cs * q; }
+        double *ji = J + i * B, *jj = J + j * B;
+        for (int64_t k = 0; k < B; k++) { double p = ji[k], q = jj[k]; ji[k] = cs * p - sn * q; jj[k] = sn * p + cs * q; }
+      }
+    if (off < 1e-14) break;
+  }
+  int64_t r = B < F ? B : F;
+  double* nrm = (double*) malloc(sizeof(double) * (size_t) B);
+  int64_t* ord = (int64_t*) malloc(sizeof(int64_t) * (size_t) B);
+  for (int64_t b = 0; b < B; b++) { double a = 0.0; for (int64_t f = 0; f < F; f++) a += A[b * F + f] * A[b * F + f]; nrm[b] = sqrt(a); ord[b] = b; }
+  for (int64_t i = 1; i < B; i++) { /* insertion sort, descending */
+    int64_t o = ord[i]; int64_t k = i - 1;
+    while (k >= 0 && nrm[ord[k]] < nrm[o]) { ord[k + 1] = ord[k]; k--; }
+    ord[k + 1] = o;
+  }
+  for (int64_t c = 0; c < r; c++) {
+    int64_t b = ord[c];
+    s[c] = nrm[b];
+    double sign = 1.0, big = 0.0;
+    for (int64_t k = 0; k < B; k++) if (fabs(J[b * B + k]) > big) { big = fabs(J[b * B + k]); sign = J[b * B + k] < 0 ? -1.0 : 1.0; }
+    for (int64_t k = 0; k < B; k++) U[c * B + k] = sign * J[b * B + k];
+    for (int64_t f = 0; f < F; f++) V[c * F + f] = nrm[b] > 0 ? sign * A[b * F + f] / nrm[b] : 0.0;
+  }
+  free(A); free(J); free(nrm); free(ord);
+}
+
+FO_EXPORT int64_t fo_nndsvd(const double* X, int64_t F, int64_t B, int64_t min_rank, int64_t max_rank, double amount,
+                            int64_t method, int64_t seed, double* W, double* H, double* sv_out)
+{
+  int64_t r = B < F ? B : F;
+  double* U = (double*) malloc(sizeof(double) * (size_t) (r * B));
+  double* V = (double*) malloc(sizeof(double) * (size_t) (r * F));
+  double* s = (double*) malloc(sizeof(double) * (size_t) r);
+  fo_svd_jacobi(X, F, B, U, s, V);
+  if (sv_out) memcpy(sv_out, s, sizeof(double) * (size_t) r);
+  int64_t k = 0;
+  if (amount == 0) k = min_rank;                                              /* :49-50 */
+  else {
+    double cur = 0.0, total = 0.0;
+    for (int64_t i = 0; i < r; i++) total += s[i];
+    while ((cur / total) < amount && k < r) cur += s[k++];                    /* :53-55 (k < r: guard only) */
+  }
+  if (k < min_rank) k = min_rank;                                             /* :57 */
+  if (k > max_rank) k = max_rank;                                             /* :58 */
+  if (k > r) k = r;
+  if (method == 0) {                                                          /* :60-65 */
+    for (int64_t j = 0; j < k; j++) {
+      for (int64_t b = 0; b < B; b++) W[j * B + b] = fabs(U[j * B + b]);
+      for (int64_t f = 0; f < F; f++) H[f * max_rank + j] = fabs(s[j] * V[j * F + f]);
+    }
+  } else {
+    for (int64_t b = 0; b < B; b++) W[b] = fabs(U[b]);                        /* :69 */
+    for (int64_t f = 0; f < F; f++) H[f * max_rank] = sqrt(s[0]) * fabs(V[f]); /* :70 */
+    for (int64_t j = 1; j < k; j++) {                                         /* :72-104 */
+      const double *x = U + j * B, *y = V + j * F;
+      double xp = 0, yp = 0, xn = 0;
+      for (int64_t b = 0; b < B; b++) { double p = x[b] > 0 ? x[b] : 0, q = x[b] < 0 ? -x[b] : 0; xp += p * p; xn += q * q; }
+      for (int64_t f = 0; f < F; f++) { double p = y[f] > 0 ? y[f] : 0; yp += p * p; }
+      double xPNorm = sqrt(xp), yPNorm = sqrt(yp), xNNorm = sqrt(xn);
+      double yNNorm = xNNorm;                                                 /* :84  "double yNNorm = xN.norm();" */
+      double mP = xPNorm * yPNorm, mN = xNNorm * yNNorm;
+      double sigma;
+      if (mP > mN) {
+        sigma = mP;
+        for (int64_t b = 0; b < B; b++) W[j * B + b] = (x[b] > 0 ? x[b] : 0) / xPNorm;
+        double lbd = sqrt(s[j] * sigma);
+        for (int64_t f = 0; f < F; f++) H[f * max_rank + j] = lbd * ((y[f] > 0 ? y[f] : 0) / yPNorm);
+      } else {
+        sigma = mN;
+        for (int64_t b = 0; b < B; b++) W[j * B + b] = (x[b] < 0 ? -x[b] : 0) / xNNorm;
+        double lbd = sqrt(s[j] * sigma);
+        for (int64_t f = 0; f < F; f++) H[f * max_rank + j] = lbd * ((y[f] < 0 ? -y[f] : 0) / yNNorm);
+      }
+    }
+    double mean = 0.0;
+    for (int64_t e = 0; e < F * B; e++) mean += X[e];
+    mean /= (double) (F * B);                                                 /* :106 */
+    if (method == 1) {                                                        /* :107-117 */
+      fo_mt64 g; double lo = FO_EPS, hi = mean * 0.001;
+      fo_mt64_seed(&g, (uint64_t) seed);
+      for (int64_t j = 0; j < max_rank; j++)       /* column-major B x maxRank: W^T(b, j) = draw j * B + b */
+        for (int64_t b = 0; b < B; b++) { double u = fo_mt64_uniform(&g) * (hi - lo) + lo; if (W[j * B + b] < FO_EPS) W[j * B + b] = u; }
+      fo_mt64_seed(&g, (uint64_t) seed);
+      for (int64_t f = 0; f < F; f++)              /* column-major maxRank x F: H^T(j, f) = draw f * maxRank + j */
+        for (int64_t j = 0; j < max_rank; j++) { double u = fo_mt64_uniform(&g) * (hi - lo) + lo; if (H[f * max_rank + j] < FO_EPS) H[f * max_rank + j] = u; }
+    } else if (method == 2) {                                                 /* :118-125 */
+      for (int64_t e = 0; e < max_rank * B; e++) if (W[e] < FO_EPS) W[e] = mean;
+      for (int64_t e = 0; e < F * max_rank; e++) if (H[e] < FO_EPS) H[e] = mean;
+    }
+  }
+  free(U); free(V); free(s);
+  return k;
+}
+
 FO_EXPORT int fo_num_threads(void)
 {
 #ifdef _OPENMP

@@ -474,3 +474,47 @@ def hpss(spec, v_size, h_size, mode=0, h_thresh=(0.0, 1.0, 1.0, 1.0), p_thresh=(
             nrm = np.maximum(1.0 / (hm + pm + rm), EPS)
             hm, pm, rm = hm * nrm, pm * nrm, rm * nrm
     return np.stack([X0 * np.minimum(hm, 1.0), X0 * np.minimum(pm, 1.0), X0 * np.minimum(rm, 1.0)])
+
+
+# ---- NNDSVD.hpp:30-131 --------------------------------------------------------------------------------------------
+def nndsvd(X, min_rank=1, max_rank=200, amount=0.5, method=0, seed=-1):
+    """X[F][B] -> (k, W[max_rank][B], H[F][max_rank], s).  LAPACK SVD of X^T; the sign of each (u, v) pair is fixed by the
+    convention of the C restatement (largest-magnitude entry of u positive) -- see the note there on :84."""
+    X = np.asarray(X, dtype=np.float64)
+    F, B = X.shape
+    U, s, Vt = np.linalg.svd(X.T, full_matrices=False)      # U: B x r, Vt: r x F
+    sign = np.sign(U[np.abs(U).argmax(axis=0), np.arange(U.shape[1])])
+    sign[sign == 0] = 1.0
+    U = U * sign[None, :]; Vt = Vt * sign[:, None]
+    if amount == 0:
+        k = min_rank
+    else:
+        k, cur, total = 0, 0.0, s.sum()
+        while cur / total < amount and k < s.size:
+            cur += s[k]; k += 1
+    k = min(max(k, min_rank), max_rank, s.size)
+    WT = np.zeros((B, max_rank)); HT = np.zeros((max_rank, F))
+    if method == 0:
+        WT[:, :k] = np.abs(U[:, :k]); HT[:k] = np.abs(s[:k, None] * Vt[:k])
+    else:
+        WT[:, 0] = np.abs(U[:, 0]); HT[0] = np.sqrt(s[0]) * np.abs(Vt[0])
+        for j in range(1, k):
+            x, y = U[:, j], Vt[j]
+            xP, yP, xN, yN = np.maximum(x, 0), np.maximum(y, 0), np.abs(np.minimum(x, 0)), np.abs(np.minimum(y, 0))
+            xPn, yPn, xNn = np.linalg.norm(xP), np.linalg.norm(yP), np.linalg.norm(xN)
+            yNn = xNn                                        # :84 as written
+            mP, mN = xPn * yPn, xNn * yNn
+            if mP > mN:
+                u, v, sigma = xP / xPn, yP / yPn, mP
+            else:
+                u, v, sigma = xN / xNn, yN / yNn, mN
+            WT[:, j] = u; HT[j] = np.sqrt(s[j] * sigma) * v
+        mean = X.mean()
+        if method == 1:
+            lo, hi = EPS, mean * 0.001
+            Wr = (random_uniform(seed, B * max_rank) * (hi - lo) + lo).reshape(max_rank, B).T
+            Hr = (random_uniform(seed, max_rank * F) * (hi - lo) + lo).reshape(F, max_rank).T
+            WT = np.where(WT < EPS, Wr, WT); HT = np.where(HT < EPS, Hr, HT)
+        elif method == 2:
+            WT = np.where(WT < EPS, mean, WT); HT = np.where(HT < EPS, mean, HT)
+    return k, WT.T.copy(), HT.T.copy(), s

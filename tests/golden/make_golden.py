@@ -191,6 +191,25 @@ def nmfcross():
     np.savez_compressed(os.path.join(HERE, "nmfcross.npz"), source=src, target=tgt, out=out, H=H)
 
 
+def spectral_epilogues():
+    """MelBands (MelBands.hpp:43-101) and HPSS (HPSS.hpp:47-162) on the STFT of a short synthetic buffer: C oracle output,
+    cross-checked against the numpy restatement (closed form of the delay lines instead of the streaming recursion)."""
+    a = synth_audio(41, 12000)
+    S = co.stft(a.astype(np.float64), 512, 512, 128)
+    out = {"audio": a}
+    for tag, args in {"norm": (True, False, False), "pow_db": (False, True, True)}.items():
+        b1 = co.melbands(np.abs(S), 20.0, 20000.0, 40, 44100.0, 512, *args)
+        b2 = no.melbands(np.abs(S), 20.0, 20000.0, 40, 44100.0, 512, *args)
+        assert np.abs(b1 - b2).max() <= 1e-10 * np.abs(b2).max()
+        out[f"mel_{tag}"] = b1
+    for mode, ht, pt in [(0, (0, 1, 1, 1), (0, 1, 1, 1)), (1, (0.005, 0.0, 0.1, -10.0), (0, 1, 1, 1)),
+                         (2, (0.005, 10.0, 0.1, 0.0), (0.005, 10.0, 0.1, 0.0))]:
+        o1 = co.hpss(S, 31, 17, mode, ht, pt); o2 = no.hpss(S, 31, 17, mode, ht, pt)
+        assert np.abs(o1 - o2).max() <= 1e-12 * np.abs(o2).max()
+        out[f"hpss{mode}"] = o1.astype(np.complex64)
+    np.savez_compressed(os.path.join(HERE, "spectral.npz"), **out)
+
+
 def read_wav_mono_int(path):
     """Integer samples of a mono PCM file (16 / 24 bit) and the scale that turns them into the floats a host loads."""
     import struct
@@ -239,11 +258,13 @@ if __name__ == "__main__":
         config1_full()
     elif len(sys.argv) > 1 and sys.argv[1] == "nmfcross":
         nmfcross()
+    elif len(sys.argv) > 1 and sys.argv[1] == "spectral":
+        spectral_epilogues()
     elif len(sys.argv) > 1 and sys.argv[1] == "stream":
         nmffilter_stream()
     elif len(sys.argv) > 1 and sys.argv[1] == "bufstft":
         bufstft()
     else:
-        rng_kat(); fft_kat(); nmf_small(); bufnmf_wav(); nmffilter_stream(); bufstft(); config1_full(); nmfcross()
+        rng_kat(); fft_kat(); nmf_small(); bufnmf_wav(); nmffilter_stream(); bufstft(); config1_full(); nmfcross(); spectral_epilogues()
     for f in sorted(os.listdir(HERE)):
         print(f, os.path.getsize(os.path.join(HERE, f)))
