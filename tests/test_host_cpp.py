@@ -134,3 +134,28 @@ def test_rt_clients_gpu_vs_oracle_stream(oracle, host):
         ref = acts_o[f_last]
         assert np.linalg.norm(mout[b, :rank] - ref) / max(np.linalg.norm(ref), 1e-30) < 1e-4, b
     assert np.all(mout[:, rank:] == 0)
+
+
+def test_nrt_client_mirrors_compile_and_fail_loudly_without_gpu():
+    import torch
+    with tempfile.TemporaryDirectory() as t:
+        exe = compile_cpp("test_nrt_clients_gpu.cpp", os.path.join(t, "a"))
+        if torch.cuda.is_available():
+            pytest.skip("GPU present: covered by the gpu test")
+        r = subprocess.run([exe], capture_output=True, text=True, env=dict(os.environ, FLUCOMA_B200_LIB=LIB))
+        assert r.returncode != 0  # no CPU fallback: NMFSeed returns kError ("no such CUDA device") and the test's CHECK fails
+        assert "no such CUDA device" in (r.stdout + r.stderr)
+
+
+@pytest.mark.gpu
+def test_nrt_client_mirrors_gpu_vs_oracle(oracle):
+    """NMFSeedClient -> seeded NMFClient, and NMFCrossClient (with a FluidTask) through the C++ mirrors; the BufNMFCross
+    output against the oracle (NMFCrossClient.hpp:85-185)."""
+    with tempfile.TemporaryDirectory() as t:
+        exe = compile_cpp("test_nrt_clients_gpu.cpp", os.path.join(t, "a"))
+        dump = os.path.join(t, "dump.bin")
+        r = subprocess.run([exe, dump], capture_output=True, text=True, env=dict(os.environ, FLUCOMA_B200_LIB=LIB))
+        assert r.returncode == 0 and "nrt clients ok" in r.stdout, r.stdout + r.stderr
+        src, tgt, out = _read_dumps(dump, 3)
+    ref, _ = oracle.bufnmfcross(src[:, 0], tgt[:, 0], 256, 256, 64, 7, 11, 7, 20, 5, 50)
+    assert np.linalg.norm(out[:, 0] - ref) / np.linalg.norm(ref) < 1e-3
