@@ -478,6 +478,10 @@ k_nmf_tcs(Params p, const __grid_constant__ CUtensorMap tmap1, const __grid_cons
         for (int j = 0; j < 64; j++) v[j] = *reinterpret_cast<const float*>(vt + j * 128 + voff[j & 7]);
       }
       tmem_wait_ld();
+      // WAR across proxies: the V stage is about to be handed back to the TMA producer, and a generic-proxy LDS that is
+      // merely issued is not ordered before the async-proxy refill by the mbarrier alone (seen on a 16-epilogue-warp
+      // variant of this kernel, profiles/experiments: whole rows of H off by ~0.5 % about once per 10^5 warp-steps).
+      fence_proxy_async();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) { mbar_arrive(&p_free[wg]); mbar_arrive(&v_empty[st]); }
@@ -611,6 +615,7 @@ k_nmf_tcs(Params p, const __grid_constant__ CUtensorMap tmap1, const __grid_cons
 #pragma unroll
               for (int j = 0; j < 8; j++) h[8 * kb + j] = acc8[j];
             }
+            fence_proxy_async(); // generic reads of the tile before the producer's next bulk copy into it (see do_step)
             __syncwarp();
             if (lane == 0) mbar_arrive(&st_empty[jn & 1]);
           }
@@ -662,6 +667,7 @@ k_nmf_tcs(Params p, const __grid_constant__ CUtensorMap tmap1, const __grid_cons
             for (int j = 0; j < K2; j++)
               wold[j] = bf16_bits_to_f(stt[op_index_w<K>(2, k0 + j, r)]) + bf16_bits_to_f(stt[op_index_w<K>(1, k0 + j, r)]) +
                         bf16_bits_to_f(stt[op_index_w<K>(0, k0 + j, r)]);
+            fence_proxy_async(); // generic reads of the tile before the producer's next bulk copy into it (see do_step)
             __syncwarp();
             if (lane == 0) mbar_arrive(&st_empty[jn & 1]);
           }
