@@ -10,21 +10,22 @@
 //   phase 1 (H-update of a 128-frame tile t, NMF.hpp:165-170), per 64-bin chunk c:
 //       P[f][b]    = H_t W_c           tcgen05.mma SS   A = H blocks (K-major)   B = W blocks (MN-major)   M128 N64 K16
 //       R[f][b]    = V / max(P, eps)   epilogue: tcgen05.ld, swizzled LDS of the TMA tile, rcp, 2-way split, tcgen05.st
-//       hnum[f][k] += R W_c^T          tcgen05.mma TS   A = R (TMEM)             B = W blocks (K-major)    M128 N48+N16 K64
+//       hnum[f][k] += R W_c^T          tcgen05.mma TS   A = R (TMEM)             B = W blocks (K-major)    M128 N32+N16 K64
 //     then H <- H * hnum / max(hden, eps) for the tile ("tile prep").
 //   phase 2 (this tile's share of the next W-update, NMF.hpp:158-160), per 128-bin tile m and 64-frame half s:
 //       P[b][f]    = W_m^T H_ts^T      SS   A = W blocks (MN-major)  B = H blocks (K-major)    M128 N64 K16
 //       R[b][f]    = V / max(P, eps)
-//       wnum[b][k] += R H_ts           TS   A = R (TMEM)             B = H blocks (MN-major)   M128 N48+N16 K64
+//       wnum[b][k] += R H_ts           TS   A = R (TMEM)             B = H blocks (MN-major)   M128 N32+N16 K64
 //   after the last tile: W <- W * wnum / max(wden, eps), conditional column normalisation (:161-162), hden = sum_b W.
 //
-// Precision: a product of two 3-way splits keeps the six terms above 2^-24 (hh, hm, mh, hl, lh, mm), i.e. fp32-grade
-// operands with fp32 accumulation.  (A 2-way split, 16-17 mantissa bits, measured 1.3e-4 against the fp64 CPU restatement after
-// 200 iterations -- the NMF dynamics amplify the per-iteration error about 100x -- and missed the 1e-4 bar.)
-// For the second MMA the three parts of the B operand sit next to each other in shared memory, so one instruction
-// with N = 48 multiplies the leading ratio part by [X_hi | X_mid | X_lo] at once and a second one (N = 16, its own
-// accumulator columns) adds R_lo X_hi; the epilogue sums the four 16-column groups of every step's FRESH accumulator
-// with round-to-nearest adds (the tensor core's accumulate truncates, which would drift over 200 iterations).
+// Precision: W and H are carried as exact three-way splits (the STATE must not be rounded: 16-bit state measured 1.3e-4
+// against the fp64 CPU restatement after 200 iterations -- the NMF dynamics amplify a per-iteration rounding about 100x).
+// The MMAs use what their consumers can resolve: W.H keeps the terms down to 2^-16 (hh, hm, mh), because the ratio made
+// from it is itself a two-part operand, and the second MMA multiplies R_hi by [X_hi | X_mid] (one instruction, N = 32,
+// the parts sit next to each other in shared memory) and R_lo by X_hi (N = 16, its own accumulator columns).  The
+// epilogue sums the three 16-column groups of every step's FRESH accumulator with round-to-nearest adds (the tensor
+// core's accumulate truncates; accumulated over a whole job in TMEM that bias alone measured 1.3e-4).
+// Errors against the oracle after 200 iterations: see tools/tc_margin.py and profiles/r02k_experiments.txt.
 //
 // The Nyquist bin (B = 2^m + 1) does not fit the 128-wide tiles; its column is carried on the SIMT side of the epilogue
 // (a 16-term dot product per frame), so the tensor tiles cover bins 0 .. B-2 exactly.
@@ -51,14 +52,19 @@ constexpr int STAGE = 32768;
 constexpr int BT_MAX = 512;      // tensor bins (B - 1)
 constexpr int FP_MAX = 512;      // padded frames
 constexpr int NTHREADS = 384;    // warpgroup 0: producer, issuer, 2 idle warps; warpgroups 1, 2: epilogue
+#ifdef FB200_TC_ROWPAD
+constexpr uint32_t ROWB = 3 * KB * 128 + 16; // bytes per 8-bin (W) / 8-frame (H) block row: 3 parts x 2 component blocks, + 16 so that per-row accesses of consecutive block rows fall into different banks
+#else
 constexpr uint32_t ROWB = 3 * KB * 128; // bytes per 8-bin (W) / 8-frame (H) block row: 3 parts x 2 component blocks
+#endif
 
 // TMEM columns
 constexpr uint32_t TM_P = 0;      // + 64 g
 constexpr int RP = 2;             // parts of the ratio operand R written to TMEM (3 = exact fp32, 2 = hi + lo)
 constexpr uint32_t RCOLS = 32 * RP;
 constexpr uint32_t TM_R = 128;    // + RCOLS g : hi [0,32) mid [32,64) lo [64,96)
-// per-step partial of the second MMA: [0,16) leading term R_hi X_hi, [16,48) corrections R_hi [X_mid | X_lo], [48,64) R_lo X_hi.
+// per-step partial of the second MMA: [0,16) leading term R_hi X_hi, [16,32) R_hi X_mid, [32,48) R_lo X_hi ([48,64) unused:
+// R_hi X_lo is of the order of the dropped R_lo X_mid and made no measurable difference).
 // Every accumulation chain owns its columns: only MMAs of the same shape on the same accumulator address are
 // pipelined in issue order; chains of different shape must not touch each other's destination columns.
 constexpr uint32_t ACOLS = 64;
@@ -82,8 +88,8 @@ constexpr int OFF_SLOT = OFF_BAR + NBAR * 8;
 constexpr int SMEM_BYTES = OFF_SLOT + 16;
 
 // element index (in bf16 units) of W[k][b] / H[f][k], split part `part`
-__device__ __forceinline__ int wop_index(int part, int k, int b) { return ((((b >> 3) * 3 + part) * KB + (k >> 3)) << 6) + ((k & 7) << 3) + (b & 7); }
-__device__ __forceinline__ int hop_index(int part, int f, int k) { return ((((f >> 3) * 3 + part) * KB + (k >> 3)) << 6) + ((f & 7) << 3) + (k & 7); }
+__device__ __forceinline__ int wop_index(int part, int k, int b) { return (b >> 3) * (int) (ROWB / 2) + ((part * KB + (k >> 3)) << 6) + ((k & 7) << 3) + (b & 7); }
+__device__ __forceinline__ int hop_index(int part, int f, int k) { return (f >> 3) * (int) (ROWB / 2) + ((part * KB + (k >> 3)) << 6) + ((f & 7) << 3) + (k & 7); }
 
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 // warp q of epilogue warpgroup 0 with warp q of warpgroup 1 (named barriers 2..5, 64 threads)
@@ -281,9 +287,9 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
       // needs one integer add per MMA (the 14-bit start-address field never carries into the LBO field).
       const uint32_t wop_a = smem_u32(wop), hop_a = smem_u32(hop);
       constexpr uint32_t ID_P1A = make_idesc_bf16(128, 64, 0, 1);
-      constexpr uint32_t ID_P1B48 = make_idesc_bf16(128, 48, 0, 0), ID_P1B16 = make_idesc_bf16(128, 16, 0, 0);
+      constexpr uint32_t ID_P1B32 = make_idesc_bf16(128, 32, 0, 0), ID_P1B16 = make_idesc_bf16(128, 16, 0, 0);
       constexpr uint32_t ID_P2A = make_idesc_bf16(128, 64, 1, 0);
-      constexpr uint32_t ID_P2B48 = make_idesc_bf16(128, 48, 0, 1), ID_P2B16 = make_idesc_bf16(128, 16, 0, 1);
+      constexpr uint32_t ID_P2B32 = make_idesc_bf16(128, 32, 0, 1), ID_P2B16 = make_idesc_bf16(128, 16, 0, 1);
       constexpr uint32_t HI_A = (ROWB >> 4) | (1u << 14);  // first MMA operands: SBO = ROWB (block rows), version 1
       constexpr uint32_t HI_B = (128u >> 4) | (1u << 14);  // second MMA B operand: SBO = 128 (parts / component blocks along N)
       constexpr uint32_t LO_A = (128u >> 4) << 16;         // LBO = 128 (component blocks along K)
@@ -304,13 +310,12 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
         tc_fence_after();
         DBG_MARK(1, n);
         const uint32_t dP = tbase + TM_P + 64 * g;
-        // six significant terms of (A_hi + A_mid + A_lo)(B_hi + B_mid + B_lo)
+        // the terms of (A_hi + A_mid + A_lo)(B_hi + B_mid + B_lo) down to 2^-16: the ratio that is made from P is itself
+        // carried as a two-part (16-bit) operand, so the 2^-16 .. 2^-24 terms (hi lo, lo hi, mid mid) bought nothing
+        // measurable against the fp64 oracle and cost half of the first MMA's operand traffic (profiles/r02k_experiments.txt)
         mma_ss_lohi<0>(dP, alo, HI_A, blo, HI_A, idesc);                          // hi  hi
         mma_ss_lohi<1>(dP, alo, HI_A, blo + PSTEP, HI_A, idesc);                  // hi  mid
         mma_ss_lohi<1>(dP, alo + PSTEP, HI_A, blo, HI_A, idesc);                  // mid hi
-        mma_ss_lohi<1>(dP, alo, HI_A, blo + 2 * PSTEP, HI_A, idesc);              // hi  lo
-        mma_ss_lohi<1>(dP, alo + 2 * PSTEP, HI_A, blo, HI_A, idesc);              // lo  hi
-        mma_ss_lohi<1>(dP, alo + PSTEP, HI_A, blo + PSTEP, HI_A, idesc);          // mid mid
         mma_commit_warp(&p_full[g]);
         DBG_MARK(2, n);
         n++;
@@ -359,8 +364,8 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
     {
       const uint32_t myg = warp - 2;
       const uint32_t wop_a = smem_u32(wop), hop_a = smem_u32(hop);
-      constexpr uint32_t ID_P1B48 = make_idesc_bf16(128, 48, 0, 0), ID_P1B16 = make_idesc_bf16(128, 16, 0, 0);
-      constexpr uint32_t ID_P2B48 = make_idesc_bf16(128, 48, 0, 1), ID_P2B16 = make_idesc_bf16(128, 16, 0, 1);
+      constexpr uint32_t ID_P1B32 = make_idesc_bf16(128, 32, 0, 0), ID_P1B16 = make_idesc_bf16(128, 16, 0, 0);
+      constexpr uint32_t ID_P2B32 = make_idesc_bf16(128, 32, 0, 1), ID_P2B16 = make_idesc_bf16(128, 16, 0, 1);
       constexpr uint32_t HI_B = (128u >> 4) | (1u << 14);  // B operand: SBO = 128 (parts / component blocks along N)
       constexpr uint32_t LO_B = (ROWB >> 4) << 16;         // LBO = ROWB (block rows along K)
       constexpr uint32_t RSTEP = ROWB >> 4;
@@ -368,7 +373,7 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
       uint32_t n = 0;
       // The operands read here are rewritten only after the epilogue has collected every partial (b_full) of the phase
       // that used them, so this stream needs no barrier besides r_full.
-      auto issue_b = [&](uint32_t blo, uint32_t id48, uint32_t id16) {
+      auto issue_b = [&](uint32_t blo, uint32_t id32, uint32_t id16) {
         const uint32_t g = n & 1;
         if (g != myg) { n++; return; }
         mbar_wait(&r_full[g], (n >> 1) & 1);
@@ -378,17 +383,17 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
         const uint32_t dacc = tbase + TM_ACC + ACOLS * g;
         // The tensor core adds into the fp32 accumulator with truncation, so every accumulate costs up to one ulp of
         // the accumulator, always in the same direction.  Columns [0,16) therefore receive ONLY the leading term
-        // R_hi X_hi (one add per K-step); all correction terms go to the small-magnitude columns [16,64).
+        // R_hi X_hi (one add per K-step); all correction terms go to the small-magnitude columns [16,48).
         // The two accumulation chains own disjoint columns: MMAs of different shape / accumulator address are not
         // ordered against each other by the tensor pipe, only same-shape same-accumulator chains are.
 #pragma unroll
         for (int j = 0; j < 4; j++) { // K-step j = 16 bins (phase 1) / 16 frames (phase 2) = block rows 2j, 2j+1 of the step
           const uint32_t b0 = blo + 2 * j * RSTEP; // parts hi, mid, lo side by side along N
           const uint32_t rh = rbase + 8 * j;
-          if (j == 0) mma_ts_lohi<0>(dacc, rh, b0, HI_B, id48);                  // R_hi [X_hi | X_mid | X_lo] -> cols [0,48)
-          else mma_ts_lohi<1>(dacc, rh, b0, HI_B, id48);
-          if (j == 0) mma_ts_lohi<0>(dacc + 48, rh + 32, b0, HI_B, id16);        // R_lo  X_hi              -> cols [48,64)
-          else mma_ts_lohi<1>(dacc + 48, rh + 32, b0, HI_B, id16);
+          if (j == 0) mma_ts_lohi<0>(dacc, rh, b0, HI_B, id32);                  // R_hi [X_hi | X_mid] -> cols [0,32)
+          else mma_ts_lohi<1>(dacc, rh, b0, HI_B, id32);
+          if (j == 0) mma_ts_lohi<0>(dacc + 32, rh + 32, b0, HI_B, id16);        // R_lo  X_hi         -> cols [32,48)
+          else mma_ts_lohi<1>(dacc + 32, rh + 32, b0, HI_B, id16);
         }
         mma_commit_warp(&b_full[g]); // the epilogue adds this partial to its fp32 running sums
         DBG_MARK(5, n);
@@ -402,10 +407,10 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
           if (mode == PASS_STOP) { stop = true; break; }
           for_blocks(sc.p1(pass), sc.p2(pass) && mode == PASS_RUN, T, (pass & 1) != 0, [&](int kind, int t) {
             if (kind == BLK_P1)
-              for (int c = 0; c < C1; c++) issue_b(wlo_b + 8 * c * RSTEP, ID_P1B48, ID_P1B16);           // B = W rows of chunk c
+              for (int c = 0; c < C1; c++) issue_b(wlo_b + 8 * c * RSTEP, ID_P1B32, ID_P1B16);           // B = W rows of chunk c
             else if (kind == BLK_P2)
               for (int m = 0; m < MT; m++)
-                for (int s = 0; s < 2; s++) issue_b(hlo_b + (16 * t + 8 * s) * RSTEP, ID_P2B48, ID_P2B16); // B = H rows of half s
+                for (int s = 0; s < 2; s++) issue_b(hlo_b + (16 * t + 8 * s) * RSTEP, ID_P2B32, ID_P2B16); // B = H rows of half s
           });
           if (mode == PASS_FINAL) { gp++; break; }
         }
@@ -437,20 +442,19 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
       if (!out_valid) return;
       mbar_wait(&b_full[wg], out_par);
       tc_fence_after();
-      uint32_t a[32], a2[32];
+      uint32_t a[32], a2[16];
       tmem_ld32(tAcc, a);
-      tmem_ld32(tAcc + 32, a2);
+      tmem_ld16(tAcc + 32, a2);
       if (out_phase == 1) {
         tmem_wait_ld();
         float4* hp = reinterpret_cast<float4*>(hs) + (wg * 128 + r); // [j4][wg][row]
 #pragma unroll
-        for (int j4 = 0; j4 < 4; j4++) { // hs += a[k] + ((a[16+k] + a2[k]) + a2[16+k]), two components per instruction
+        for (int j4 = 0; j4 < 4; j4++) { // hs += a[k] + (a[16+k] + a2[k]), two components per instruction
           float x[4];
 #pragma unroll
           for (int i = 0; i < 4; i += 2) {
             const int k = 4 * j4 + i;
             add2(x[i], x[i + 1], __uint_as_float(a[16 + k]), __uint_as_float(a[17 + k]), __uint_as_float(a2[k]), __uint_as_float(a2[k + 1]));
-            add2(x[i], x[i + 1], x[i], x[i + 1], __uint_as_float(a2[16 + k]), __uint_as_float(a2[17 + k]));
             add2(x[i], x[i + 1], __uint_as_float(a[k]), __uint_as_float(a[k + 1]), x[i], x[i + 1]);
           }
           if (!out_first) {
@@ -468,7 +472,6 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
         for (int k = 0; k < K; k += 2) {
           float x0, x1;
           add2(x0, x1, __uint_as_float(a[16 + k]), __uint_as_float(a[17 + k]), __uint_as_float(a2[k]), __uint_as_float(a2[k + 1]));
-          add2(x0, x1, x0, x1, __uint_as_float(a2[16 + k]), __uint_as_float(a2[17 + k]));
           add2(x0, x1, __uint_as_float(a[k]), __uint_as_float(a[k + 1]), x0, x1);
           if (!out_first) add2(x0, x1, __uint_as_float(w[k]), __uint_as_float(w[k + 1]), x0, x1);
           w[k] = __float_as_uint(x0); w[k + 1] = __float_as_uint(x1);
