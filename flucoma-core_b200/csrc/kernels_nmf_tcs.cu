@@ -1,28 +1,34 @@
 // Streamed tcgen05 / TMEM / TMA engine for the NMF multiplicative updates (algorithms/public/NMF.hpp:144-183 and the
-// fixed-dictionary activation solve NMF.hpp:45-89), rank 9..32 (padded to 16 or 32), any bins = 128 m + 1, any frame count.
+// fixed-dictionary activation solve NMF.hpp:45-89), rank 9..64 (padded to 16, 32 or 64), any bins = 128 m + 1, any frame count.
 //
-// Same arithmetic as kernels_nmf_tc.cu (exact 3-way bf16 split of W and H, six cross terms for W.H, ratio V / max(WH, eps)
+// Same arithmetic as kernels_nmf_tc.cu (W.H from bf16 split operands with the terms down to 2^-16, ratio V / max(WH, eps)
 // computed by the epilogue warps straight out of TMEM and fed back as the TMEM A operand of the second MMA, every step's
 // second MMA into a FRESH accumulator that the epilogue sums with round-to-nearest adds), but no operand is resident:
-// W and H live in global memory (L2) in pre-split UMMA core-matrix layout
-//     Wop [BT/8 block rows][3 parts][K/8][8 k][8 b] bf16      Hop [Fp/8 block rows][3 parts][K/8][8 f][8 k] bf16
-// next to their exact fp32 state (d.W, d.H), and one persistent CTA per buffer streams them through shared memory with
-// bulk TMA copies.  Every half-iteration is a sequence of JOBS that all look alike:
+// the exact fp32 state (d.W, d.H) lives in global memory (L2) next to its two-part bf16 split in UMMA core-matrix layout
+//     Wop [BT/8 block rows][2 parts][K/8][8 k][8 b] bf16      Hop [Fp/8 block rows][2 parts][K/8][8 f][8 k] bf16
+// and one persistent CTA per buffer streams the operands through shared memory with bulk TMA copies.
+// Every half-iteration is a sequence of JOBS that all look alike:
 //     job(H, t): H-update of the 128-frame tile t  (NMF.hpp:165-170)   stationary = H rows of t,  stream = 64-bin W chunks
 //     job(W, m): W-update of the 128-bin  tile m  (NMF.hpp:158-161)   stationary = W rows of m,  stream = 64-frame H chunks
-//   step (64 columns):  P = stationary x chunk        tcgen05.mma SS  M128 N64, K/16 k-steps x 6 split terms
+//   step (64 columns):  P = stationary x chunk        tcgen05.mma SS  M128 N64, K/16 k-steps x 3 split terms (hh, hm, mh)
 //                       R = V / max(P, eps)           epilogue warps: tcgen05.ld, swizzled V tile, rcp, 2-way split, tcgen05.st
-//                       num += R x chunk^T            tcgen05.mma TS  M128 N = 3K (+ N = K for R_lo), 4 k-steps, fresh accumulator
-//   end of job:  H-tile / W-tile update written to global (fp32 state + split operand), partial sums for the next phase.
+//                       num += R x chunk^T            tcgen05.mma TS  M128 N = 2K (R_hi [X_hi | X_mid]) + N = K (R_lo X_hi), 4 k-steps
+//   the fresh partial of every step is added (round-to-nearest) to running sums that live in TMEM as well;
+//   end of job:  H-tile / W-tile update from the fp32 state, written back as fp32 + split operand.
 // After the last W tile of a half-iteration: column normalisation over all bins (NMF.hpp:162), rescale sweep, hden (:169).
+//
+// TMEM (512 columns): P 2 x 64 | R 2 x 64 | accumulators | running sums.
+//   rank 16 / 32: one accumulator (3K columns) and one set of sums (K) per epilogue warpgroup; a warpgroup collects its own steps.
+//   rank 64:      ONE accumulator (192 columns) and one set of sums (64): both warpgroups collect EVERY step, each its 32
+//                 components, and the single second-MMA issuer waits for both before it reuses the accumulator.
 //
 // Fixed dictionary (update_w == 0: NMFMatch / NMFFilter / BufNMF with fixed bases): a CTA takes PAIRS of frame tiles and
 // runs all iterations for them (job(H, a), job(H, b), job(H, a), ...), so the |X| tile is read from HBM once and stays in
 // L2 for the remaining iterations, and the update of tile a overlaps the steps of tile b.
 //
 // Warp roles (384 threads) as in kernels_nmf_tc.cu: warp 0 producer (V tensor tiles + operand bulk copies), warp 1 first
-// MMA issuer + TMEM owner, warps 2/3 second-MMA issuers (one per epilogue warpgroup), warps 4-11 two epilogue warpgroups on
-// alternating steps.  All sums are fixed-order: results are bitwise repeatable.
+// MMA issuer + TMEM owner, warps 2/3 second-MMA issuers (one per epilogue warpgroup; rank 64: warp 2 alone), warps 4-11 two
+// epilogue warpgroups on alternating steps.  All sums are fixed-order: results are bitwise repeatable.
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -44,29 +50,55 @@ template <int K>
 struct Cfg {
   static constexpr int KB = K / 8;                      // 8-component blocks
   static constexpr int KS = K / 16;                     // k-steps of the first MMA
-  static constexpr uint32_t ROWB = 3 * KB * 128;        // bytes per 8-row block row (3 parts)
+  static constexpr uint32_t ROWB = 2 * KB * 128;        // bytes per 8-row block row (2 parts: hi, mid)
   static constexpr uint32_t CHUNK = 8 * ROWB;           // streamed chunk: 64 rows
   static constexpr uint32_t TILE = 16 * ROWB;           // stationary tile: 128 rows
   // TMEM columns
+  static constexpr bool ONE_ACC = K == 64;              // a single accumulator / set of sums shared by both warpgroups
   static constexpr uint32_t TM_P = 0;                   // + 64 g
   static constexpr uint32_t TM_R = 128;                 // + 64 g : hi [0,32) lo [32,64)
-  static constexpr uint32_t ACOLS = 4 * K;              // [0,K) R_hi X_hi | [K,3K) R_hi [X_mid|X_lo] | [3K,4K) R_lo X_hi
-  static constexpr uint32_t TM_ACC = 256;               // + ACOLS g
-  static_assert(TM_ACC + 2 * ACOLS <= 512, "TMEM budget");
+  static constexpr uint32_t ACOLS = 3 * K;              // [0,K) R_hi X_hi | [K,2K) R_hi X_mid | [2K,3K) R_lo X_hi
+  static constexpr uint32_t TM_ACC = 256;               // + ACOLS g (rank < 64)
+  static constexpr uint32_t ASTRIDE = K == 16 ? 64 : ACOLS; // accumulator g starts at TM_ACC + ASTRIDE g
+  static constexpr uint32_t TM_SUM = TM_ACC + ACOLS;    // rank 64 only: running sums, K columns
+  static_assert(ONE_ACC ? TM_SUM + K <= 512 : TM_ACC + ASTRIDE + ACOLS <= 512, "TMEM budget");
   // shared memory map
   static constexpr int OFF_V = 0;
   static constexpr int OFF_ST = OFF_V + NS * STAGE;                 // 2 stationary tiles
   static constexpr int OFF_O = OFF_ST + 2 * (int) TILE;             // NSO streamed chunks
-  static constexpr int OFF_HS = OFF_O + NSO * (int) CHUNK;          // float [K/4][2 wg][128][4] partial numerators
-  static constexpr int OFF_PART = OFF_HS + (K / 4) * 2 * 128 * 16;  // float [8 warps][K]  wden / Nyquist partials
+  // fp32 state of the stationary tile (the tile update multiplies the exact old values): staged by the producer next to
+  // the operand tile where shared memory allows it; rank 64 has no room and reads the rows from L2 instead (its jobs are
+  // 32 steps long, the round trip is 1-2 % of a job; at rank 16 a job is 8 steps and the round trip cost 5-15 %)
+  static constexpr bool HAS_F32 = K <= 32;
+  static constexpr uint32_t F32TILE = 128 * K * 4;
+  static constexpr int OFF_F32 = OFF_O + NSO * (int) CHUNK;         // 2 x float [128 frames][K] (H job) / [K][128 bins] (W job)
+  // running sums of the partial numerators: rank <= 32 in shared memory (float [K/4][2 wg][128][4], one 16-byte slot per
+  // thread and component quad: conflict-free), rank 64 in TMEM (no shared memory left; measured on rank 16 / 32 the TMEM
+  // variant is 3-7 % slower: the epilogue's tcgen05.ld/st compete with the MMAs for the TMEM port)
+  static constexpr int OFF_HS = OFF_F32 + (HAS_F32 ? 2 * (int) F32TILE : 0);
+  static constexpr int OFF_PART = OFF_HS + (ONE_ACC ? 0 : (K / 4) * 2 * 128 * 16); // float [8 warps][K]  wden / Nyquist partials
   static constexpr int OFF_RED = OFF_PART + 8 * K * 4;              // float [8 warps][K + 4]  sum w^2 | sum w (own half), max
   static constexpr int OFF_FIN = OFF_RED + 8 * (K + 4) * 4;         // float [8][K]: wden, nyq num, inv norm, inv hden, WN, hden, sum w^2, sum w
   static constexpr int OFF_BAR = OFF_FIN + 8 * K * 4 + 16;
-  static constexpr int NBAR = 2 * NS + 2 * NSO + 4 + 8;
+  static constexpr int NBAR = 2 * NS + 2 * NSO + 4 + 8 + 1;
   static constexpr int OFF_SLOT = OFF_BAR + NBAR * 8;
   static constexpr int SMEM_BYTES = OFF_SLOT + 16;
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
+
+// N consecutive TMEM columns of this thread's lane
+template <int N>
+__device__ __forceinline__ void tmem_ldn(uint32_t taddr, uint32_t (&r)[N])
+{
+  if constexpr (N == 8) tmem_ld8(taddr, r);
+  else tmem_ld16(taddr, r);
+}
+template <int N>
+__device__ __forceinline__ void tmem_stn(uint32_t taddr, const uint32_t (&r)[N])
+{
+  if constexpr (N == 8) tmem_st8(taddr, r);
+  else tmem_st16(taddr, r);
+}
 
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 88;" ::: "memory"); }
@@ -83,9 +115,15 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
 
 // operand element index (bf16 units): row = bin (W) or frame (H), k = component
 template <int K>
-__device__ __forceinline__ int op_index_w(int part, int k, int b) { return ((((b >> 3) * 3 + part) * (K / 8) + (k >> 3)) << 6) + ((k & 7) << 3) + (b & 7); }
+__device__ __forceinline__ int op_index_w(int part, int k, int b) { return ((((b >> 3) * 2 + part) * (K / 8) + (k >> 3)) << 6) + ((k & 7) << 3) + (b & 7); }
 template <int K>
-__device__ __forceinline__ int op_index_h(int part, int f, int k) { return ((((f >> 3) * 3 + part) * (K / 8) + (k >> 3)) << 6) + ((f & 7) << 3) + (k & 7); }
+__device__ __forceinline__ int op_index_h(int part, int f, int k) { return ((((f >> 3) * 2 + part) * (K / 8) + (k >> 3)) << 6) + ((f & 7) << 3) + (k & 7); }
+// two-part split of a pair, packed pairwise: hi = bf16(x), mid = bf16(x - hi)
+__device__ __forceinline__ void split2(float x0, float x1, uint32_t& h, uint32_t& m)
+{
+  h = cvt2(x0, x1);
+  m = cvt2(x0 - bf16lo_to_f(h), x1 - bf16hi_to_f(h));
+}
 
 // one stage of the vector butterfly: lanes with bit O set keep the upper half of a[0, 2 CNT), the others the lower half
 template <int CNT, int O>
@@ -113,8 +151,8 @@ struct Params {
   float* W;            // [batch | 1][K][Bp]   fp32 state
   float* H;            // [batch][Fp][K]
   float* hden;         // [batch | 1][K]
-  __nv_bfloat16* Wop;  // [batch | 1][BT/8][3][K/8][64]
-  __nv_bfloat16* Hop;  // [batch][Fp/8][3][K/8][64]
+  __nv_bfloat16* Wop;  // [batch | 1][BT/8][2][K/8][64]
+  __nv_bfloat16* Hop;  // [batch][Fp/8][2][K/8][64]
   int batch, Fp, Bp, BT;
   int iters, upd_w, upd_h, shared_w, clamp_v;
   int units;           // work units: buffers (update_w) or (buffer, tile pair) (fixed W)
@@ -175,7 +213,7 @@ __global__ void k_tcs_pack(const float* __restrict__ W, const float* __restrict_
       const float4* src = reinterpret_cast<const float4*>(W + ((int64_t) buf * K + k) * Bp + 8 * blk);
       const float4 a = src[0], b = src[1];
       x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
-      dst = Wop + (int64_t) buf * (BT / 8) * 3 * KB * 64 + op_index_w<K>(0, k, 8 * blk);
+      dst = Wop + (int64_t) buf * (BT / 8) * 2 * KB * 64 + op_index_w<K>(0, k, 8 * blk);
     } else { // 8 consecutive components of one frame
       const int64_t j = i - w_items;
       const int kb = (int) (j % KB);
@@ -184,14 +222,13 @@ __global__ void k_tcs_pack(const float* __restrict__ W, const float* __restrict_
       const float4* src = reinterpret_cast<const float4*>(H + ((int64_t) buf * Fp + f) * K + 8 * kb);
       const float4 a = src[0], b = src[1];
       x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
-      dst = Hop + (int64_t) buf * (Fp / 8) * 3 * KB * 64 + op_index_h<K>(0, f, 8 * kb);
+      dst = Hop + (int64_t) buf * (Fp / 8) * 2 * KB * 64 + op_index_h<K>(0, f, 8 * kb);
     }
-    uint32_t ph[4], pm[4], pl[4];
+    uint32_t ph[4], pm[4];
 #pragma unroll
-    for (int q = 0; q < 4; q++) split3(x[2 * q], x[2 * q + 1], ph[q], pm[q], pl[q]);
+    for (int q = 0; q < 4; q++) split2(x[2 * q], x[2 * q + 1], ph[q], pm[q]);
     *reinterpret_cast<uint4*>(dst) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
     *reinterpret_cast<uint4*>(dst + KB * 64) = make_uint4(pm[0], pm[1], pm[2], pm[3]);
-    *reinterpret_cast<uint4*>(dst + 2 * KB * 64) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
   }
 }
 
@@ -203,7 +240,6 @@ k_nmf_tcs(Params p, const __grid_constant__ CUtensorMap tmap1, const __grid_cons
   constexpr int KB = C::KB, KS = C::KS;
   constexpr uint32_t ROWB = C::ROWB;
   extern __shared__ __align__(1024) uint8_t smem[];
-  float* hs = reinterpret_cast<float*>(smem + C::OFF_HS);
   float* part = reinterpret_cast<float*>(smem + C::OFF_PART);
   float* red = reinterpret_cast<float*>(smem + C::OFF_RED);
   float* fin = reinterpret_cast<float*>(smem + C::OFF_FIN);
@@ -227,6 +263,7 @@ k_nmf_tcs(Params p, const __grid_constant__ CUtensorMap tmap1, const __grid_cons
   uint64_t* r_full = p_full + 2;           // [2]
   uint64_t* b_full = r_full + 2;           // [2]
   uint64_t* p_free = b_full + 2;           // [2]
+  uint64_t* acc_free = p_free + 2;         // [1]    rank 64: both warpgroups have collected the step's partial
   uint32_t* slot = reinterpret_cast<uint32_t*>(smem + C::OFF_SLOT);
   volatile uint32_t* jobs_done = slot + 1; // jobs whose tile update is complete and visible in global memory
 
@@ -239,9 +276,10 @@ k_nmf_tcs(Params p, const __grid_constant__ CUtensorMap tmap1, const __grid_cons
     for (int i = 0; i < NS; i++) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 4); }
     for (int i = 0; i < NSO; i++) { mbar_init(&o_full[i], 1); mbar_init(&o_empty[i], 2); }
     for (int i = 0; i < 2; i++) {
-      mbar_init(&st_full[i], 1); mbar_init(&st_empty[i], 9); // first-MMA commit + the 8 epilogue warps (tile update reads it)
+      mbar_init(&st_full[i], 1); mbar_init(&st_empty[i], C::HAS_F32 ? 9 : 1); // first-MMA commit of the job's last step (+ the 8 epilogue warps that read the fp32 tile)
       mbar_init(&p_full[i], 1); mbar_init(&r_full[i], 4); mbar_init(&b_full[i], 1); mbar_init(&p_free[i], 4);
     }
+    mbar_init(acc_free, 8);
     mbar_fence_init();
     tma_prefetch_desc(&tmap1);
     tma_prefetch_desc(&tmap2);
@@ -251,8 +289,8 @@ k_nmf_tcs(Params p, const __grid_constant__ CUtensorMap tmap1, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tbase = *slot;
-  const int64_t wop_stride = p.shared_w ? 0 : (int64_t) (BT / 8) * 3 * KB * 64;
-  const int64_t hop_stride = (int64_t) (Fp / 8) * 3 * KB * 64;
+  const int64_t wop_stride = p.shared_w ? 0 : (int64_t) (BT / 8) * 2 * KB * 64;
+  const int64_t hop_stride = (int64_t) (Fp / 8) * 2 * KB * 64;
 
   if (warp < 4) {
     reg_dec();
@@ -287,9 +325,18 @@ k_nmf_tcs(Params p, const __grid_constant__ CUtensorMap tmap1, const __grid_cons
               }
               const uint32_t sl = jn & 1, k = jn >> 1;
               mbar_wait(&st_empty[sl], (k & 1) ^ 1);
-              mbar_arrive_expect_tx(&st_full[sl], C::TILE);
-              const __nv_bfloat16* src = (phase == 0 ? gH : gW) + (int64_t) tile * 16 * 3 * KB * 64;
+              mbar_arrive_expect_tx(&st_full[sl], C::TILE + (C::HAS_F32 ? C::F32TILE : 0u));
+              const __nv_bfloat16* src = (phase == 0 ? gH : gW) + (int64_t) tile * 16 * 2 * KB * 64;
               bulk_g2s(smem + C::OFF_ST + sl * C::TILE, src, C::TILE, &st_full[sl]);
+              if constexpr (C::HAS_F32) {
+                uint8_t* dst = smem + C::OFF_F32 + sl * C::F32TILE;
+                if (phase == 0) {
+                  bulk_g2s(dst, p.H + ((int64_t) buf * Fp + 128 * tile) * K, C::F32TILE, &st_full[sl]);
+                } else {
+                  const float* wrow = p.W + (int64_t) (p.shared_w ? 0 : buf) * K * Bp + 128 * tile;
+                  for (int k = 0; k < K; k++) bulk_g2s(dst + k * 512, wrow + (int64_t) k * Bp, 512, &st_full[sl]);
+                }
+              }
             }
             // |X| does not depend on anything: the first tiles of the job are requested before the producer blocks on the
             // chunk dependencies, so a half-iteration boundary costs one L2 round trip of a chunk, not a cold pipeline
@@ -307,7 +354,7 @@ k_nmf_tcs(Params p, const __grid_constant__ CUtensorMap tmap1, const __grid_cons
                 const uint32_t so = n % NSO, k = n / NSO;
                 mbar_wait(&o_empty[so], (k & 1) ^ 1);
                 mbar_arrive_expect_tx(&o_full[so], C::CHUNK);
-                const __nv_bfloat16* src = (phase == 0 ? gW : gH) + (int64_t) i * 8 * 3 * KB * 64;
+                const __nv_bfloat16* src = (phase == 0 ? gW : gH) + (int64_t) i * 8 * 2 * KB * 64;
                 bulk_g2s(smem + C::OFF_O + so * C::CHUNK, src, C::CHUNK, &o_full[so]);
               }
             }
@@ -344,10 +391,7 @@ k_nmf_tcs(Params p, const __grid_constant__ CUtensorMap tmap1, const __grid_cons
               if (j == 0) mma_ss_lohi<0>(dP, a, HI_A, b, HI_A, idesc);           // hi  hi
               else mma_ss_lohi<1>(dP, a, HI_A, b, HI_A, idesc);
               mma_ss_lohi<1>(dP, a, HI_A, b + PSTEP, HI_A, idesc);               // hi  mid
-              mma_ss_lohi<1>(dP, a + PSTEP, HI_A, b, HI_A, idesc);               // mid hi
-              mma_ss_lohi<1>(dP, a, HI_A, b + 2 * PSTEP, HI_A, idesc);           // hi  lo
-              mma_ss_lohi<1>(dP, a + 2 * PSTEP, HI_A, b, HI_A, idesc);           // lo  hi
-              mma_ss_lohi<1>(dP, a + PSTEP, HI_A, b + PSTEP, HI_A, idesc);       // mid mid
+              mma_ss_lohi<1>(dP, a + PSTEP, HI_A, b, HI_A, idesc);               // mid hi   (terms below 2^-16: see kernels_nmf_tc.cu)
             }
             mma_commit_warp(&p_full[g]);
             mma_commit_warp(&o_empty[so]);
@@ -356,40 +400,44 @@ k_nmf_tcs(Params p, const __grid_constant__ CUtensorMap tmap1, const __grid_cons
         });
       }
     } else {
-      // =========================================== second-MMA issuers (one per epilogue warpgroup) ===========
+      // =========================================== second-MMA issuers =========================================
+      // rank < 64: one issuing warp per epilogue warpgroup (accumulator g belongs to the steps of parity g);
+      // rank 64:   warp 2 issues every step into the one accumulator, after both warpgroups have collected the previous one.
       const uint32_t myg = warp - 2;
-      constexpr uint32_t ID_H3 = make_idesc_bf16(128, 3 * K, 0, 0), ID_H1 = make_idesc_bf16(128, K, 0, 0); // B = W chunk, K-major
-      constexpr uint32_t ID_W3 = make_idesc_bf16(128, 3 * K, 0, 1), ID_W1 = make_idesc_bf16(128, K, 0, 1); // B = H chunk, MN-major
+      constexpr uint32_t ID_H2 = make_idesc_bf16(128, 2 * K, 0, 0), ID_H1 = make_idesc_bf16(128, K, 0, 0); // B = W chunk, K-major
+      constexpr uint32_t ID_W2 = make_idesc_bf16(128, 2 * K, 0, 1), ID_W1 = make_idesc_bf16(128, K, 0, 1); // B = H chunk, MN-major
       constexpr uint32_t HI_B = (128u >> 4) | (1u << 14);  // SBO = 128 (component blocks / parts along N)
       constexpr uint32_t LO_B = (ROWB >> 4) << 16;         // LBO = ROWB (block rows along K)
       constexpr uint32_t RSTEP = ROWB >> 4;
       const uint32_t o_a = smem_u32(smem + C::OFF_O);
       uint32_t n = 0, jn = 0;
+      if (!C::ONE_ACC || myg == 0)
       for (int unit = blockIdx.x; unit < p.units; unit += gridDim.x) {
         for_jobs(p, unit, jn, [&](int phase, int, uint32_t, uint32_t, bool) {
-          const uint32_t id3 = phase == 0 ? ID_H3 : ID_W3, id1 = phase == 0 ? ID_H1 : ID_W1;
+          const uint32_t id2 = phase == 0 ? ID_H2 : ID_W2, id1 = phase == 0 ? ID_H1 : ID_W1;
           const int ns = phase == 0 ? C1 : S2;
           for (int i = 0; i < ns; i++, n++) {
             const uint32_t g = n & 1, so = n % NSO;
-            if (g != myg) continue;
+            if (!C::ONE_ACC && g != myg) continue;
             // r_full FIRST: it implies o_full(n) (the first MMA of this step waited for it), so the wait below can never
             // be a phase early; it only orders this thread behind the copy
             mbar_wait(&r_full[g], (n >> 1) & 1);
             mbar_wait(&o_full[so], (n / NSO) & 1);
+            if (C::ONE_ACC && n >= 1) mbar_wait(acc_free, (n - 1) & 1);
             tc_fence_after();
             const uint32_t blo = ((o_a + so * C::CHUNK) >> 4) | LO_B;
             const uint32_t rbase = tbase + C::TM_R + 64 * g;
-            const uint32_t dacc = tbase + C::TM_ACC + C::ACOLS * g;
+            const uint32_t dacc = tbase + C::TM_ACC + (C::ONE_ACC ? 0u : C::ASTRIDE * g);
 #pragma unroll
             for (int j = 0; j < 4; j++) { // 16 rows of the chunk per k-step
               const uint32_t b0 = blo + 2 * j * RSTEP;
               const uint32_t rh = rbase + 8 * j;
-              if (j == 0) mma_ts_lohi<0>(dacc, rh, b0, HI_B, id3);                // R_hi [X_hi | X_mid | X_lo]
-              else mma_ts_lohi<1>(dacc, rh, b0, HI_B, id3);
-              if (j == 0) mma_ts_lohi<0>(dacc + 3 * K, rh + 32, b0, HI_B, id1);   // R_lo  X_hi
-              else mma_ts_lohi<1>(dacc + 3 * K, rh + 32, b0, HI_B, id1);
+              if (j == 0) mma_ts_lohi<0>(dacc, rh, b0, HI_B, id2);                // R_hi [X_hi | X_mid]
+              else mma_ts_lohi<1>(dacc, rh, b0, HI_B, id2);
+              if (j == 0) mma_ts_lohi<0>(dacc + 2 * K, rh + 32, b0, HI_B, id1);   // R_lo  X_hi
+              else mma_ts_lohi<1>(dacc + 2 * K, rh + 32, b0, HI_B, id1);
             }
-            mma_commit_warp(&b_full[g]);
+            mma_commit_warp(&b_full[C::ONE_ACC ? 0u : g]);
             mma_commit_warp(&o_empty[so]);
           }
         });
@@ -406,47 +454,84 @@ k_nmf_tcs(Params p, const __grid_constant__ CUtensorMap tmap1, const __grid_cons
     const uint32_t lane_off = (uint32_t) (32 * q) << 16;
     const uint32_t tP = tbase + C::TM_P + 64 * wg + lane_off;
     const uint32_t tR = tbase + C::TM_R + 64 * wg + lane_off;
-    const uint32_t tAcc = tbase + C::TM_ACC + C::ACOLS * wg + lane_off;
     constexpr int K2 = K / 2;              // components this warpgroup stores / reduces in the tile updates
+    constexpr int DC = C::ONE_ACC ? K2 : K; // components a thread collects from a step's partial
+    constexpr int G = K2 >= 16 ? 16 : 8;   // TMEM access granule of the tile updates
     const int k0 = wg * K2;
+    // this thread's slice of the accumulator / of the running sums: rank 64: components [32 wg, 32 wg + 32) of the shared
+    // accumulator; rank < 64: all components of this warpgroup's own accumulator
+    const uint32_t tAcc = tbase + C::TM_ACC + (C::ONE_ACC ? (uint32_t) (K2 * wg) : C::ASTRIDE * wg) + lane_off;
+    const uint32_t tSum = tbase + C::TM_SUM + (uint32_t) (K2 * wg) + lane_off; // rank 64
+    const uint32_t tSumAll = tbase + C::TM_SUM + lane_off;
+    float* hs = reinterpret_cast<float*>(smem + C::OFF_HS);          // rank <= 32
+    float4* hp = reinterpret_cast<float4*>(hs) + (wg * 128 + r);     // [j4][wg][row]
     uint32_t n = 0, jn = 0;
     int out_valid = 0, out_first = 0;
     uint32_t out_par = 0;
-    float4* hp = reinterpret_cast<float4*>(hs) + (wg * 128 + r); // [j4][wg][row]
 
-    // collect the previous step's fresh partial (4 column groups per 16 components) into this thread's running sums
+    // Add a step's fresh partial (three column groups per component) to the running sums with round-to-nearest adds.
+    // rank 64: sums in TMEM; their stores are left in flight, the next tcgen05.wait::st of this thread covers them.
+    auto collect = [&](bool first) {
+      if constexpr (C::ONE_ACC) {
+        if (!first) tmem_wait_st(); // this thread's previous update of the same columns
+      }
+#pragma unroll
+      for (int g16 = 0; g16 < DC / 16; g16++) {
+        uint32_t a0[16], a1[16], a2[16], sacc[16];
+        tmem_ld16(tAcc + 16 * g16, a0);           // R_hi X_hi
+        tmem_ld16(tAcc + K + 16 * g16, a1);       // R_hi X_mid
+        tmem_ld16(tAcc + 2 * K + 16 * g16, a2);   // R_lo X_hi
+        if constexpr (C::ONE_ACC) {
+          if (!first) tmem_ld16(tSum + 16 * g16, sacc);
+        }
+        tmem_wait_ld();
+        if constexpr (C::ONE_ACC) {
+#pragma unroll
+          for (int k = 0; k < 16; k += 2) {
+            float x0, x1;
+            add2(x0, x1, __uint_as_float(a1[k]), __uint_as_float(a1[k + 1]), __uint_as_float(a2[k]), __uint_as_float(a2[k + 1]));
+            add2(x0, x1, __uint_as_float(a0[k]), __uint_as_float(a0[k + 1]), x0, x1);
+            if (!first) add2(x0, x1, __uint_as_float(sacc[k]), __uint_as_float(sacc[k + 1]), x0, x1);
+            sacc[k] = __float_as_uint(x0); sacc[k + 1] = __float_as_uint(x1);
+          }
+          tmem_st16(tSum + 16 * g16, sacc);
+        } else {
+#pragma unroll
+          for (int j4 = 0; j4 < 4; j4++) {
+            float x[4];
+#pragma unroll
+            for (int i = 0; i < 4; i += 2) {
+              const int k = 4 * j4 + i;
+              add2(x[i], x[i + 1], __uint_as_float(a1[k]), __uint_as_float(a1[k + 1]), __uint_as_float(a2[k]), __uint_as_float(a2[k + 1]));
+              add2(x[i], x[i + 1], __uint_as_float(a0[k]), __uint_as_float(a0[k + 1]), x[i], x[i + 1]);
+            }
+            float4* dst = hp + (4 * g16 + j4) * 256;
+            if (!first) {
+              const float4 h = *dst;
+              add2(x[0], x[1], h.x, h.y, x[0], x[1]);
+              add2(x[2], x[3], h.z, h.w, x[2], x[3]);
+            }
+            *dst = make_float4(x[0], x[1], x[2], x[3]);
+          }
+        }
+      }
+    };
+    // rank < 64: the previous step of this warpgroup
     auto drain = [&]() {
       if (!out_valid) return;
       mbar_wait(&b_full[wg], out_par);
       tc_fence_after();
-#pragma unroll
-      for (int g16 = 0; g16 < K / 16; g16++) {
-        uint32_t a0[16], a1[16], a2[16], a3[16];
-        tmem_ld16(tAcc + 16 * g16, a0);           // R_hi X_hi
-        tmem_ld16(tAcc + K + 16 * g16, a1);       // R_hi X_mid
-        tmem_ld16(tAcc + 2 * K + 16 * g16, a2);   // R_hi X_lo
-        tmem_ld16(tAcc + 3 * K + 16 * g16, a3);   // R_lo X_hi
-        tmem_wait_ld();
-#pragma unroll
-        for (int j4 = 0; j4 < 4; j4++) {
-          float x[4];
-#pragma unroll
-          for (int i = 0; i < 4; i += 2) {
-            const int k = 4 * j4 + i;
-            add2(x[i], x[i + 1], __uint_as_float(a1[k]), __uint_as_float(a1[k + 1]), __uint_as_float(a3[k]), __uint_as_float(a3[k + 1]));
-            add2(x[i], x[i + 1], x[i], x[i + 1], __uint_as_float(a2[k]), __uint_as_float(a2[k + 1]));
-            add2(x[i], x[i + 1], __uint_as_float(a0[k]), __uint_as_float(a0[k + 1]), x[i], x[i + 1]);
-          }
-          float4* dst = hp + (4 * g16 + j4) * 256;
-          if (!out_first) {
-            const float4 h = *dst;
-            add2(x[0], x[1], h.x, h.y, x[0], x[1]);
-            add2(x[2], x[3], h.z, h.w, x[2], x[3]);
-          }
-          *dst = make_float4(x[0], x[1], x[2], x[3]);
-        }
-      }
+      collect(out_first != 0);
       out_valid = 0;
+    };
+    // rank 64: step nn (any parity); hands the accumulator back to the second-MMA issuer
+    auto drain_shared = [&](uint32_t nn, bool first) {
+      mbar_wait(&b_full[0], nn & 1);
+      tc_fence_after();
+      collect(first);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_free);
     };
     uint32_t voff[8];
 #pragma unroll
@@ -480,7 +565,7 @@ k_nmf_tcs(Params p, const __grid_constant__ CUtensorMap tmap1, const __grid_cons
       tmem_wait_ld();
       // WAR across proxies: the V stage is about to be handed back to the TMA producer, and a generic-proxy LDS that is
       // merely issued is not ordered before the async-proxy refill by the mbarrier alone (seen on a 16-epilogue-warp
-      // variant of this kernel, profiles/experiments: whole rows of H off by ~0.5 % about once per 10^5 warp-steps).
+      // variant of kernels_nmf_tc.cu, profiles/experiments: whole rows of H off by ~0.5 % about once per 10^5 warp-steps).
       fence_proxy_async();
       tc_fence_before();
       __syncwarp();
@@ -496,7 +581,9 @@ k_nmf_tcs(Params p, const __grid_constant__ CUtensorMap tmap1, const __grid_cons
         sub2(l0, l1, r0, r1, bf16lo_to_f(ph[j]), bf16hi_to_f(ph[j]));
         pl[j] = cvt2(l0, l1);
       }
-      drain();
+      // R[wg] is still read by the second MMA of this warpgroup's previous step until that step's partial is complete:
+      // rank < 64 collects it here; rank 64 has collected it already (every warpgroup collects every step, in order)
+      if constexpr (!C::ONE_ACC) drain();
       tmem_st16(tR, *reinterpret_cast<uint32_t(*)[16]>(&ph[0]));
       tmem_st16(tR + 16, *reinterpret_cast<uint32_t(*)[16]>(&ph[16]));
       tmem_st16(tR + 32, *reinterpret_cast<uint32_t(*)[16]>(&pl[0]));
@@ -507,12 +594,13 @@ k_nmf_tcs(Params p, const __grid_constant__ CUtensorMap tmap1, const __grid_cons
       if (lane == 0) mbar_arrive(&r_full[wg]);
     };
 
-    // K values per thread summed over the 32 lanes with K - 1 shuffles; lane l ends with the total of value (l >> SH)
-    // (K = 32: SH = 0; K = 16: SH = 1) in a[0].
+    // K values per thread summed over the 32 lanes with shuffles (vector butterfly); afterwards lane l holds in a[0 .. PER)
+    // the totals of the values PER * (l >> SH) + j  (K = 64: two per lane, K = 32: one per lane, K = 16: one per lane pair)
     auto butterfly = [&](float (&a)[K]) { bf_stage<K / 2, 16>(a, lane); };
     constexpr int SH = K == 16 ? 1 : 0;
-    const bool bf_owner = K == 16 ? (lane & 1) == 0 : true; // lanes that hold a distinct total after the butterfly
-    const int bf_idx = lane >> SH;                          // value index: [0,K2) first kind, [K2,K) second kind
+    constexpr int PER = K == 64 ? 2 : 1;
+    const bool bf_owner = K == 16 ? (lane & 1) == 0 : true; // lanes that hold distinct totals after the butterfly
+    const int bf_idx = PER * (lane >> SH);                  // value index: [0,K2) first kind, [K2,K) second kind
 
     // wden / Nyquist-numerator partials of one frame row (new H row `h`, all K components) -> warp-private running sums
     auto frame_partials = [&](const float (&h)[K], float vn) {
@@ -528,7 +616,10 @@ k_nmf_tcs(Params p, const __grid_constant__ CUtensorMap tmap1, const __grid_cons
         a[K2 + j] = rn * x;  // Nyquist row of (V / WH) H^T  (:159)
       }
       butterfly(a);
-      if (bf_owner) part[ew * K + bf_idx] += a[0];
+      if (bf_owner) {
+#pragma unroll
+        for (int j = 0; j < PER; j++) part[ew * K + bf_idx + j] += a[j];
+      }
     };
 
     for (int unit = blockIdx.x; unit < p.units; unit += gridDim.x) {
@@ -561,7 +652,7 @@ k_nmf_tcs(Params p, const __grid_constant__ CUtensorMap tmap1, const __grid_cons
               float h[K];
               const float4* src = reinterpret_cast<const float4*>(gH + (int64_t) (f0 + r) * K);
 #pragma unroll
-              for (int j = 0; j < K / 4; j++) { const float4 x = src[j]; h[4 * j] = x.x; h[4 * j + 1] = x.y; h[4 * j + 2] = x.z; h[4 * j + 3] = x.w; }
+              for (int j = 0; j < K / 4; j++) { const float4 x = __ldcg(src + j); h[4 * j] = x.x; h[4 * j + 1] = x.y; h[4 * j + 2] = x.z; h[4 * j + 3] = x.w; }
               float vn = gV[(int64_t) (f0 + r) * Bp + BT];
               if (p.clamp_v) vn = fmaxf(vn, kEps);
               frame_partials(h, vn);
@@ -588,50 +679,85 @@ k_nmf_tcs(Params p, const __grid_constant__ CUtensorMap tmap1, const __grid_cons
           vn = gV[(int64_t) (128 * tile + r) * Bp + BT];
           if (p.clamp_v) vn = fmaxf(vn, kEps);
         }
-        for (int i = 0; i < ns; i++, n++) {
-          if ((int) (n & 1) != wg) continue;
-          do_step(n, phase == 0);
-          out_valid = 1; out_first = (i == wg); out_par = (n >> 1) & 1;
-        }
-        drain();
-        epi_bar(); // both warpgroups' partial numerators of the tile are in `hs`
-        if (phase == 0) {
-          // ---------------- H-tile update (NMF.hpp:168-170) ----------------------------------------------------------
-          const int f = 128 * tile + r;
-          float h[K];
-          { // old H row = hi + mid + lo of the job's stationary tile (small parts first: exact)
-            const __nv_bfloat16* stt = reinterpret_cast<const __nv_bfloat16*>(smem + C::OFF_ST + (jn & 1) * C::TILE);
-#pragma unroll
-            for (int kb = 0; kb < KB; kb++) {
-              float acc8[8];
-#pragma unroll
-              for (int j = 0; j < 8; j++) acc8[j] = 0.f;
-#pragma unroll
-              for (int pt = 2; pt >= 0; pt--) {
-                const uint4 u = *reinterpret_cast<const uint4*>(stt + op_index_h<K>(pt, r, 8 * kb));
-                acc8[0] += bf16lo_to_f(u.x); acc8[1] += bf16hi_to_f(u.x); acc8[2] += bf16lo_to_f(u.y); acc8[3] += bf16hi_to_f(u.y);
-                acc8[4] += bf16lo_to_f(u.z); acc8[5] += bf16hi_to_f(u.z); acc8[6] += bf16lo_to_f(u.w); acc8[7] += bf16hi_to_f(u.w);
-              }
-#pragma unroll
-              for (int j = 0; j < 8; j++) h[8 * kb + j] = acc8[j];
-            }
-            fence_proxy_async(); // generic reads of the tile before the producer's next bulk copy into it (see do_step)
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&st_empty[jn & 1]);
+        if constexpr (C::ONE_ACC) {
+          for (int i = 0; i < ns; i++, n++) {
+            if ((int) (n & 1) == wg) do_step(n, phase == 0);
+            if (i >= 1) drain_shared(n - 1, i == 1);
           }
+        } else {
+          for (int i = 0; i < ns; i++, n++) {
+            if ((int) (n & 1) != wg) continue;
+            do_step(n, phase == 0);
+            out_valid = 1; out_first = (i == wg); out_par = (n >> 1) & 1;
+          }
+        }
+        // The old fp32 values of the tile: from the staged copy, or (rank 64) from L2 with ld.cg -- the rows were written by
+        // other threads of this CTA, and an L1 line filled around such a store can be stale -- requested before the last
+        // partial is collected so that the round trip overlaps that wait.
+        float old[K]; // H job: the frame's row; W job: [0, K2) this warpgroup's components of the bin
+        if constexpr (!C::HAS_F32) {
+          if (phase == 0) {
+            const float4* src = reinterpret_cast<const float4*>(gH + (int64_t) (128 * tile + r) * K);
+#pragma unroll
+            for (int j = 0; j < K / 4; j++) { const float4 x = __ldcg(src + j); old[4 * j] = x.x; old[4 * j + 1] = x.y; old[4 * j + 2] = x.z; old[4 * j + 3] = x.w; }
+          } else {
+#pragma unroll
+            for (int j = 0; j < K2; j++) old[j] = __ldcg(gW + (int64_t) (k0 + j) * Bp + 128 * tile + r);
+          }
+        }
+        if constexpr (C::ONE_ACC) drain_shared(n - 1, ns == 1);
+        else drain();
+        if constexpr (C::HAS_F32) {
+          mbar_wait(&st_full[jn & 1], (jn >> 1) & 1); // long complete; makes the bulk copy's bytes visible to this thread
+          const float* ft = reinterpret_cast<const float*>(smem + C::OFF_F32 + (jn & 1) * C::F32TILE);
+          if (phase == 0) {
+            const float4* src = reinterpret_cast<const float4*>(ft + r * K);
+#pragma unroll
+            for (int j = 0; j < K / 4; j++) { const float4 x = src[j]; old[4 * j] = x.x; old[4 * j + 1] = x.y; old[4 * j + 2] = x.z; old[4 * j + 3] = x.w; }
+          } else {
+#pragma unroll
+            for (int j = 0; j < K2; j++) old[j] = ft[(k0 + j) * 128 + r];
+          }
+          fence_proxy_async(); // generic reads of the tile before the producer's next bulk copy into it (see do_step)
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&st_empty[jn & 1]);
+        }
+        // the running sums of the tile are complete; every thread reads values written by the other warpgroup
+        if constexpr (C::ONE_ACC) { tmem_wait_st(); tc_fence_before(); }
+        epi_bar();
+        if constexpr (C::ONE_ACC) tc_fence_after();
+        if (phase == 0) {
+          // ---------------- H-tile update (NMF.hpp:168-170) from the fp32 state -----------------------------------------
+          const int f = 128 * tile + r;
+          float (&h)[K] = old;
           float pn = 0.f;
 #pragma unroll
           for (int k = 0; k < K; k++) pn = fmaf(h[k], WN[k], pn);
           const float rn = vn / fmaxf(pn, kEps);
 #pragma unroll
-          for (int j4 = 0; j4 < K / 4; j4++) { // all K new values (the partials of the next W-update need the whole row)
-            const float4 a = *reinterpret_cast<const float4*>(hs + ((j4 * 2) * 128 + r) * 4);
-            const float4 b = *reinterpret_cast<const float4*>(hs + ((j4 * 2 + 1) * 128 + r) * 4);
-            const float num[4] = {a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w};
+          if constexpr (C::ONE_ACC) {
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
-              const int k = 4 * j4 + i;
-              h[k] = h[k] * fmaf(rn, WN[k], num[i]) * f_ihd[k];
+            for (int j16 = 0; j16 < K / 16; j16++) { // all K new values (the partials of the next W-update need the whole row)
+              uint32_t s0[16];
+              tmem_ld16(tSumAll + 16 * j16, s0);
+              tmem_wait_ld();
+#pragma unroll
+              for (int i = 0; i < 16; i++) {
+                const int k = 16 * j16 + i;
+                h[k] = h[k] * fmaf(rn, WN[k], __uint_as_float(s0[i])) * f_ihd[k];
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j4 = 0; j4 < K / 4; j4++) {
+              const float4 a = *reinterpret_cast<const float4*>(hs + ((j4 * 2) * 128 + r) * 4);
+              const float4 b = *reinterpret_cast<const float4*>(hs + ((j4 * 2 + 1) * 128 + r) * 4);
+              const float num[4] = {a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w};
+#pragma unroll
+              for (int i = 0; i < 4; i++) {
+                const int k = 4 * j4 + i;
+                h[k] = h[k] * fmaf(rn, WN[k], num[i]) * f_ihd[k];
+              }
             }
           }
           // this warpgroup stores its half of the row: fp32 state + split operand
@@ -643,15 +769,14 @@ k_nmf_tcs(Params p, const __grid_constant__ CUtensorMap tmap1, const __grid_cons
                           : make_float4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
 #pragma unroll
             for (int kb = 0; kb < K2 / 8; kb++) {
-              uint32_t ph[4], pm[4], pl[4];
+              uint32_t ph[4], pm[4];
 #pragma unroll
               for (int j = 0; j < 4; j++) {
                 const float x0 = wg ? h[K2 + 8 * kb + 2 * j] : h[8 * kb + 2 * j], x1 = wg ? h[K2 + 8 * kb + 2 * j + 1] : h[8 * kb + 2 * j + 1];
-                split3(x0, x1, ph[j], pm[j], pl[j]);
+                split2(x0, x1, ph[j], pm[j]);
               }
               *reinterpret_cast<uint4*>(gHop + op_index_h<K>(0, f, k0 + 8 * kb)) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
               *reinterpret_cast<uint4*>(gHop + op_index_h<K>(1, f, k0 + 8 * kb)) = make_uint4(pm[0], pm[1], pm[2], pm[3]);
-              *reinterpret_cast<uint4*>(gHop + op_index_h<K>(2, f, k0 + 8 * kb)) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
             }
           }
           if (p.upd_w) { frame_partials(h, vn); partials_valid = true; }
@@ -660,35 +785,39 @@ k_nmf_tcs(Params p, const __grid_constant__ CUtensorMap tmap1, const __grid_cons
           const int b = 128 * tile + r;
           float a[K]; // [0,K2) w^2, [K2,K) w of this warpgroup's components
           float mx = 0.f;
-          float wold[K2]; // old W of this bin = hi + mid + lo of the job's stationary tile
-          {
-            const unsigned short* stt = reinterpret_cast<const unsigned short*>(smem + C::OFF_ST + (jn & 1) * C::TILE);
 #pragma unroll
-            for (int j = 0; j < K2; j++)
-              wold[j] = bf16_bits_to_f(stt[op_index_w<K>(2, k0 + j, r)]) + bf16_bits_to_f(stt[op_index_w<K>(1, k0 + j, r)]) +
-                        bf16_bits_to_f(stt[op_index_w<K>(0, k0 + j, r)]);
-            fence_proxy_async(); // generic reads of the tile before the producer's next bulk copy into it (see do_step)
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&st_empty[jn & 1]);
-          }
+          for (int jg = 0; jg < K2 / G; jg++) {
+            float num[G];
+            if constexpr (C::ONE_ACC) {
+              uint32_t s0[G];
+              tmem_ldn<G>(tSumAll + k0 + G * jg, s0);
+              tmem_wait_ld();
 #pragma unroll
-          for (int j4 = 0; j4 < K2 / 4; j4++) {
-            const int jj = k0 / 4 + j4;
-            const float4 s0 = *reinterpret_cast<const float4*>(hs + ((jj * 2) * 128 + r) * 4);
-            const float4 s1 = *reinterpret_cast<const float4*>(hs + ((jj * 2 + 1) * 128 + r) * 4);
-            const float num[4] = {s0.x + s1.x, s0.y + s1.y, s0.z + s1.z, s0.w + s1.w};
+              for (int i = 0; i < G; i++) num[i] = __uint_as_float(s0[i]);
+            } else {
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
-              const int k = k0 + 4 * j4 + i;
-              const float w = wold[4 * j4 + i] * num[i] / fmaxf(f_wden[k], kEps);
+              for (int i4 = 0; i4 < G / 4; i4++) {
+                const int jj = (k0 + G * jg) / 4 + i4;
+                const float4 s0 = *reinterpret_cast<const float4*>(hs + ((jj * 2) * 128 + r) * 4);
+                const float4 s1 = *reinterpret_cast<const float4*>(hs + ((jj * 2 + 1) * 128 + r) * 4);
+                num[4 * i4] = s0.x + s1.x; num[4 * i4 + 1] = s0.y + s1.y; num[4 * i4 + 2] = s0.z + s1.z; num[4 * i4 + 3] = s0.w + s1.w;
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < G; i++) {
+              const int j = G * jg + i, k = k0 + j;
+              const float w = old[j] * num[i] / fmaxf(f_wden[k], kEps);
               gW[(int64_t) k * Bp + b] = w;
-              a[4 * j4 + i] = w * w;
-              a[K2 + 4 * j4 + i] = w;
+              a[j] = w * w;
+              a[K2 + j] = w;
               mx = fmaxf(mx, w);
             }
           }
           butterfly(a);
-          if (bf_owner) red[ew * (K + 4) + bf_idx] += a[0];
+          if (bf_owner) {
+#pragma unroll
+            for (int j = 0; j < PER; j++) red[ew * (K + 4) + bf_idx + j] += a[j];
+          }
 #pragma unroll
           for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
           if (lane == 0) red[ew * (K + 4) + K] = fmaxf(red[ew * (K + 4) + K], mx);
@@ -706,7 +835,7 @@ k_nmf_tcs(Params p, const __grid_constant__ CUtensorMap tmap1, const __grid_cons
               f_s1[et] = s1 + wn;
               WN[et] = wn;
             }
-            if (et == 64) {
+            if (et == 128) {
               float gm = 0.f;
               for (int w8 = 0; w8 < 8; w8++) gm = fmaxf(gm, red[w8 * (K + 4) + K]);
               f_gm[0] = gm;
@@ -728,7 +857,7 @@ k_nmf_tcs(Params p, const __grid_constant__ CUtensorMap tmap1, const __grid_cons
             if (et < K) WN[et] *= f_inv[et];
             epi_bar();
             // 8 consecutive bins of one component per item; four items in flight per thread (the loads come from L2)
-            const int n_items = (BT / 8) * K; // a multiple of 1024 / ... : BT/8 >= 16, K >= 16 -> multiple of 256
+            const int n_items = (BT / 8) * K; // BT/8 >= 16, K >= 16 -> a multiple of 256
             for (int base = et; base < n_items; base += 4 * 256) {
               float4 x0[4], x1[4];
 #pragma unroll
@@ -736,7 +865,7 @@ k_nmf_tcs(Params p, const __grid_constant__ CUtensorMap tmap1, const __grid_cons
                 const int it8 = base + 256 * u;
                 if (it8 < n_items) {
                   const float4* src = reinterpret_cast<const float4*>(gW + (int64_t) (it8 % K) * Bp + 8 * (it8 / K));
-                  x0[u] = src[0]; x1[u] = src[1];
+                  x0[u] = __ldcg(src); x1[u] = __ldcg(src + 1);
                 }
               }
 #pragma unroll
@@ -749,13 +878,12 @@ k_nmf_tcs(Params p, const __grid_constant__ CUtensorMap tmap1, const __grid_cons
                   a.x *= s; a.y *= s; a.z *= s; a.w *= s; b.x *= s; b.y *= s; b.z *= s; b.w *= s;
                   float4* dstw = reinterpret_cast<float4*>(gW + (int64_t) k * Bp + 8 * blk);
                   dstw[0] = a; dstw[1] = b;
-                  uint32_t ph[4], pm[4], pl[4];
-                  split3(a.x, a.y, ph[0], pm[0], pl[0]); split3(a.z, a.w, ph[1], pm[1], pl[1]);
-                  split3(b.x, b.y, ph[2], pm[2], pl[2]); split3(b.z, b.w, ph[3], pm[3], pl[3]);
+                  uint32_t ph[4], pm[4];
+                  split2(a.x, a.y, ph[0], pm[0]); split2(a.z, a.w, ph[1], pm[1]);
+                  split2(b.x, b.y, ph[2], pm[2]); split2(b.z, b.w, ph[3], pm[3]);
                   __nv_bfloat16* dst = gWop + op_index_w<K>(0, k, 8 * blk);
                   *reinterpret_cast<uint4*>(dst) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
                   *reinterpret_cast<uint4*>(dst + KB * 64) = make_uint4(pm[0], pm[1], pm[2], pm[3]);
-                  *reinterpret_cast<uint4*>(dst + 2 * KB * 64) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
                 }
               }
             }
@@ -764,7 +892,8 @@ k_nmf_tcs(Params p, const __grid_constant__ CUtensorMap tmap1, const __grid_cons
         }
         // ---------------- publish: the tile update is in global memory ------------------------------------------------
         // generic-proxy stores -> async-proxy reads (bulk copies issued by the producer of this CTA): the writer-side
-        // proxy fence plus the CTA barrier order them; no device-scope fence is needed, nobody outside the CTA reads
+        // proxy fence plus the CTA barrier order them; no device-scope fence is needed, nobody outside the CTA reads.
+        // The barrier also separates this job's reads of the running sums from the next job's first partial.
         fence_async_all();
         epi_bar();
         if (et == 0) *jobs_done = jn + 1;
@@ -781,7 +910,7 @@ k_nmf_tcs(Params p, const __grid_constant__ CUtensorMap tmap1, const __grid_cons
 bool tcs_eligible(const NmfDev& d)
 {
   const int BT = d.B - 1;
-  return (d.KP == 16 || d.KP == 32) && BT >= 128 && (BT % 128) == 0 && d.Bp == d.B + 3 && d.Fp >= 128 && (d.Fp % 128) == 0;
+  return (d.KP == 16 || d.KP == 32 || d.KP == 64) && BT >= 128 && (BT % 128) == 0 && d.Bp == d.B + 3 && d.Fp >= 128 && (d.Fp % 128) == 0;
 }
 
 template <int K>
@@ -803,7 +932,7 @@ static int32_t tcs_run_t(Plan* p, const NmfDev& d, int iters, bool upd_w, bool u
   alignas(64) CUtensorMap tmap1, tmap2;
   FB_TRY(make_v_tensor_map(p, &tmap1, d.V, d.Bp, d.Fp, d.batch, 128));
   FB_TRY(make_v_tensor_map(p, &tmap2, d.V, d.Bp, d.Fp, d.batch, 64));
-  const uint32_t bit = K == 16 ? 0x20000u : 0x40000u;
+  const uint32_t bit = K == 16 ? 0x20000u : (K == 32 ? 0x40000u : 0x80000u);
   if (!(p->attr_mask & bit)) {
     FB_CUDA(p, cudaFuncSetAttribute(k_nmf_tcs<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     p->attr_mask |= bit;
@@ -827,7 +956,8 @@ static int32_t tcs_run_t(Plan* p, const NmfDev& d, int iters, bool upd_w, bool u
 int32_t tcs_run(Plan* p, const NmfDev& d, int iters, bool upd_w, bool upd_h)
 {
   if (d.KP == 16) return tcs_run_t<16>(p, d, iters, upd_w, upd_h);
-  return tcs_run_t<32>(p, d, iters, upd_w, upd_h);
+  if (d.KP == 32) return tcs_run_t<32>(p, d, iters, upd_w, upd_h);
+  return tcs_run_t<64>(p, d, iters, upd_w, upd_h);
 }
 
 } // namespace fb200

@@ -446,7 +446,8 @@ def test_config1_full_length_wav(fb, oracle, golden_dir, name, frames):
     assert np.abs(r["resynth"][0].sum(axis=0) - a).max() < 1e-4  # the masks sum to one: the components add up to the input
 
 
-@pytest.mark.parametrize("backend,K", [("BACKEND_AUTO", 5), ("BACKEND_TCGEN05", 16), ("BACKEND_TCGEN05_STREAMED", 32)])
+@pytest.mark.parametrize("backend,K", [("BACKEND_AUTO", 5), ("BACKEND_TCGEN05", 16), ("BACKEND_TCGEN05_STREAMED", 32),
+                                       ("BACKEND_TCGEN05_STREAMED", 64)])
 def test_kl_divergence_tracks_the_oracle_per_iteration(fb, oracle, backend, K):
     """A final-state Frobenius check can hide drift along flat directions; the objective cannot.  After j iterations the
     KL divergence of the GPU factors must equal the oracle's to 1e-5 relative (fp32 factors), and never increase."""
@@ -465,12 +466,15 @@ def test_kl_divergence_tracks_the_oracle_per_iteration(fb, oracle, backend, K):
             prev = d
 
 
-def test_config4_rank64_500_iterations(fb, oracle, synth):
+@pytest.mark.parametrize("backend", ["BACKEND_SIMT", "BACKEND_TCGEN05_STREAMED"])
+def test_config4_rank64_500_iterations(fb, oracle, synth, backend):
     """BASELINE config 4 (fft 4096, hop 1024, rank 64) at its FULL iteration count, on 128 frames so that the fp64 oracle
-    finishes in seconds: W, H within 1e-4 after 500 iterations."""
+    finishes in seconds: W, H within 1e-4 after 500 iterations, on the SIMT engine and on the streamed tcgen05 engine (the
+    one a full-size config-4 batch runs on)."""
     a = np.stack([synth(3000 + b, 127 * 1024) for b in range(2)])
-    with fb.Plan(win=4096, hop=1024, fft=4096) as plan:
+    with fb.Plan(win=4096, hop=1024, fft=4096, backend=getattr(fb, backend)) as plan:
         r = plan.bufnmf(a, 64, 500, seeds=[0, 1])
+        assert plan.stats()["backend_used"] == getattr(fb, backend)
     bases, acts, _ = oracle.bufnmf_batch(a, 4096, 4096, 1024, 64, 500, np.arange(2), faithful=False)
     for b in range(2):
         assert rel(r["bases"][b], bases[b]) < TOL and rel(r["acts"][b], acts[b]) < TOL, (b, rel(r["bases"][b], bases[b]))

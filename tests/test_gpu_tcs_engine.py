@@ -1,5 +1,5 @@
 """GPU tests of the STREAMED tcgen05 NMF engine (kernels_nmf_tcs.cu), forced through FB200_BACKEND_TCGEN05_STREAMED:
-rank 16 and 32 (and ranks padded up to them), bins = 128 m + 1 up to fft 4096, frame counts beyond 512, fixed-dictionary
+rank 16, 32 and 64 (and ranks padded up to them), bins = 128 m + 1 up to fft 4096, frame counts beyond 512, fixed-dictionary
 frame streams (NMF::processFrame over many frames).  Parity against the fp64 oracle at the north_star bar (1e-4
 Frobenius-relative), agreement with the resident engine and the SIMT engine, repeatability."""
 import numpy as np
@@ -29,7 +29,9 @@ def lowrank(rng, batch, F, B, kk=6):
     (384, 513, 16, 12, True, False), (256, 513, 16, 12, False, True), (130, 513, 16, 1, True, True),
     (128, 129, 32, 5, True, True), (300, 257, 32, 20, True, True), (512, 513, 32, 30, True, True),
     (640, 1025, 32, 10, True, True), (900, 513, 16, 10, True, True), (256, 2049, 32, 6, True, True),
-    (384, 513, 32, 12, True, False), (256, 513, 32, 12, False, True), (200, 257, 20, 10, True, True), (200, 257, 9, 10, True, True)])
+    (384, 513, 32, 12, True, False), (256, 513, 32, 12, False, True), (200, 257, 20, 10, True, True), (200, 257, 9, 10, True, True),
+    (128, 129, 64, 5, True, True), (300, 513, 64, 20, True, True), (256, 2049, 64, 6, True, True), (384, 513, 64, 12, True, False),
+    (256, 513, 64, 12, False, True), (130, 257, 64, 1, True, True), (200, 257, 40, 10, True, True)])
 def test_tcs_engine_vs_oracle(fb, oracle, F, B, K, iters, uw, uh):
     rng = np.random.default_rng(F + B + K)
     X = lowrank(rng, 3, F, B)
@@ -58,7 +60,7 @@ def test_tcs_engine_matches_resident_and_simt_engines(fb):
         assert rel(Wt[b], Ws[b]) < TOL and rel(Ht[b], Hs[b]) < TOL and rel(Vt[b], Vs[b]) < TOL
 
 
-@pytest.mark.parametrize("K", [16, 32])
+@pytest.mark.parametrize("K", [16, 32, 64])
 def test_tcs_engine_many_buffers_persistent_loop(fb, oracle, K):
     """more buffers than SMs: every CTA walks several buffers, barrier phases and job counters carry over"""
     rng = np.random.default_rng(2)
@@ -74,7 +76,7 @@ def test_tcs_engine_many_buffers_persistent_loop(fb, oracle, K):
 
 
 @pytest.mark.parametrize("K,iters,uw,uh,launches", [(16, 2, True, True, 30), (32, 2, True, True, 30), (16, 3, False, True, 30),
-                                                    (32, 2, True, False, 20)])
+                                                    (32, 2, True, False, 20), (64, 2, True, True, 20), (64, 3, False, True, 20)])
 def test_tcs_engine_identical_buffers_stay_identical_under_stress(fb, K, iters, uw, uh, launches):
     """Every CTA factorises copies of ONE spectrogram with ONE seed, several buffers per CTA, many launches: all buffers of
     all launches must be bit-identical (the reference's seed tests require repeatability, TestNMF.cpp:31-45) -- any race
@@ -95,7 +97,7 @@ def test_tcs_engine_identical_buffers_stay_identical_under_stress(fb, K, iters, 
             assert bool((W == ref[0]).all()) and bool((H == ref[1]).all())
 
 
-@pytest.mark.parametrize("F,B,K", [(1000, 513, 16), (128, 257, 16), (3000, 513, 12), (700, 1025, 32)])
+@pytest.mark.parametrize("F,B,K", [(1000, 513, 16), (128, 257, 16), (3000, 513, 12), (700, 1025, 32), (600, 513, 64)])
 def test_tcs_engine_process_frames(fb, oracle, F, B, K):
     """NMF::processFrame over many frames (NMF.hpp:45-89, NMFMatchClient.hpp:106-118): fixed dictionary, 10 iterations per
     frame, tile pairs per CTA (odd tile counts leave a single-tile unit)."""
