@@ -55,6 +55,13 @@ struct Cfg {
   static constexpr uint32_t TILE = 16 * ROWB;           // stationary tile: 128 rows
   // TMEM columns
   static constexpr bool ONE_ACC = K == 64;              // a single accumulator / set of sums shared by both warpgroups
+#ifndef FB200_TCS_GROUP
+#define FB200_TCS_GROUP 4
+#endif
+  // rank 64: consecutive steps whose second MMAs accumulate in TMEM before the epilogue collects them.  Collecting is 192
+  // columns per thread and stalls the one accumulator; the tensor core's truncating accumulate is the price (a chain of
+  // 4 GROUP k-steps instead of 4): measured errors in profiles/r02k_experiments.txt.
+  static constexpr int GROUP = ONE_ACC ? FB200_TCS_GROUP : 1;
   static constexpr uint32_t TM_P = 0;                   // + 64 g
   static constexpr uint32_t TM_R = 128;                 // + 64 g : hi [0,32) lo [32,64)
   static constexpr uint32_t ACOLS = 3 * K;              // [0,K) R_hi X_hi | [K,2K) R_hi X_mid | [2K,3K) R_lo X_hi
@@ -80,7 +87,7 @@ struct Cfg {
   static constexpr int OFF_RED = OFF_PART + 8 * K * 4;              // float [8 warps][K + 4]  sum w^2 | sum w (own half), max
   static constexpr int OFF_FIN = OFF_RED + 8 * (K + 4) * 4;         // float [8][K]: wden, nyq num, inv norm, inv hden, WN, hden, sum w^2, sum w
   static constexpr int OFF_BAR = OFF_FIN + 8 * K * 4 + 16;
-  static constexpr int NBAR = 2 * NS + 2 * NSO + 4 + 8 + 1;
+  static constexpr int NBAR = 2 * NS + 2 * NSO + 4 + 8 + 1 + 2;
   static constexpr int OFF_SLOT = OFF_BAR + NBAR * 8;
   static constexpr int SMEM_BYTES = OFF_SLOT + 16;
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
@@ -156,7 +163,14 @@ struct Params {
   int batch, Fp, Bp, BT;
   int iters, upd_w, upd_h, shared_w, clamp_v;
   int units;           // work units: buffers (update_w) or (buffer, tile pair) (fixed W)
+  long long* dbg;      // developer timeline (FB200_TCS_DEBUG_TIMELINE builds only)
 };
+// developer timeline: epilogue thread 0 of CTA 0 records clock64() at the boundaries of its first 96 jobs
+#ifdef FB200_TCS_DEBUG_TIMELINE
+#define TCS_MARK(slot) do { if (p.dbg && blockIdx.x == 0 && et == 0 && jn < 96) p.dbg[jn * 8 + (slot)] = clock64(); } while (0)
+#else
+#define TCS_MARK(slot) do { } while (0)
+#endif
 
 // The job sequence of one work unit, identical for every warp role: f(phase, tile, need_st, need_c, per_tile) with phase
 // 0 = H job, 1 = W job.  The need_* values tell the producer how many jobs of this CTA (counted over all units, `jn`)
@@ -263,7 +277,8 @@ k_nmf_tcs(Params p, const __grid_constant__ CUtensorMap tmap1, const __grid_cons
   uint64_t* r_full = p_full + 2;           // [2]
   uint64_t* b_full = r_full + 2;           // [2]
   uint64_t* p_free = b_full + 2;           // [2]
-  uint64_t* acc_free = p_free + 2;         // [1]    rank 64: both warpgroups have collected the step's partial
+  uint64_t* acc_free = p_free + 2;         // [1]    rank 64: both warpgroups have collected the group's partial
+  uint64_t* r_free = acc_free + 1;         // [2]    rank 64: the second MMA that read R[g] has completed
   uint32_t* slot = reinterpret_cast<uint32_t*>(smem + C::OFF_SLOT);
   volatile uint32_t* jobs_done = slot + 1; // jobs whose tile update is complete and visible in global memory
 
@@ -280,6 +295,7 @@ k_nmf_tcs(Params p, const __grid_constant__ CUtensorMap tmap1, const __grid_cons
       mbar_init(&p_full[i], 1); mbar_init(&r_full[i], 4); mbar_init(&b_full[i], 1); mbar_init(&p_free[i], 4);
     }
     mbar_init(acc_free, 8);
+    mbar_init(&r_free[0], 1); mbar_init(&r_free[1], 1);
     mbar_fence_init();
     tma_prefetch_desc(&tmap1);
     tma_prefetch_desc(&tmap2);
@@ -410,7 +426,7 @@ k_nmf_tcs(Params p, const __grid_constant__ CUtensorMap tmap1, const __grid_cons
       constexpr uint32_t LO_B = (ROWB >> 4) << 16;         // LBO = ROWB (block rows along K)
       constexpr uint32_t RSTEP = ROWB >> 4;
       const uint32_t o_a = smem_u32(smem + C::OFF_O);
-      uint32_t n = 0, jn = 0;
+      uint32_t n = 0, jn = 0, grp = 0;
       if (!C::ONE_ACC || myg == 0)
       for (int unit = blockIdx.x; unit < p.units; unit += gridDim.x) {
         for_jobs(p, unit, jn, [&](int phase, int, uint32_t, uint32_t, bool) {
@@ -423,7 +439,8 @@ k_nmf_tcs(Params p, const __grid_constant__ CUtensorMap tmap1, const __grid_cons
             // be a phase early; it only orders this thread behind the copy
             mbar_wait(&r_full[g], (n >> 1) & 1);
             mbar_wait(&o_full[so], (n / NSO) & 1);
-            if (C::ONE_ACC && n >= 1) mbar_wait(acc_free, (n - 1) & 1);
+            const bool gstart = (i % C::GROUP) == 0, gend = (i % C::GROUP) == C::GROUP - 1 || i == ns - 1;
+            if (C::ONE_ACC && gstart && grp >= 1) mbar_wait(acc_free, (grp - 1) & 1);
             tc_fence_after();
             const uint32_t blo = ((o_a + so * C::CHUNK) >> 4) | LO_B;
             const uint32_t rbase = tbase + C::TM_R + 64 * g;
@@ -432,12 +449,17 @@ k_nmf_tcs(Params p, const __grid_constant__ CUtensorMap tmap1, const __grid_cons
             for (int j = 0; j < 4; j++) { // 16 rows of the chunk per k-step
               const uint32_t b0 = blo + 2 * j * RSTEP;
               const uint32_t rh = rbase + 8 * j;
-              if (j == 0) mma_ts_lohi<0>(dacc, rh, b0, HI_B, id2);                // R_hi [X_hi | X_mid]
+              if (j == 0 && gstart) mma_ts_lohi<0>(dacc, rh, b0, HI_B, id2);      // R_hi [X_hi | X_mid]
               else mma_ts_lohi<1>(dacc, rh, b0, HI_B, id2);
-              if (j == 0) mma_ts_lohi<0>(dacc + 2 * K, rh + 32, b0, HI_B, id1);   // R_lo  X_hi
+              if (j == 0 && gstart) mma_ts_lohi<0>(dacc + 2 * K, rh + 32, b0, HI_B, id1); // R_lo  X_hi
               else mma_ts_lohi<1>(dacc + 2 * K, rh + 32, b0, HI_B, id1);
             }
-            mma_commit_warp(&b_full[C::ONE_ACC ? 0u : g]);
+            if constexpr (C::ONE_ACC) {
+              mma_commit_warp(&r_free[g]);
+              if (gend) { mma_commit_warp(&b_full[0]); grp++; }
+            } else {
+              mma_commit_warp(&b_full[g]);
+            }
             mma_commit_warp(&o_empty[so]);
           }
         });
@@ -465,7 +487,7 @@ k_nmf_tcs(Params p, const __grid_constant__ CUtensorMap tmap1, const __grid_cons
     const uint32_t tSumAll = tbase + C::TM_SUM + lane_off;
     float* hs = reinterpret_cast<float*>(smem + C::OFF_HS);          // rank <= 32
     float4* hp = reinterpret_cast<float4*>(hs) + (wg * 128 + r);     // [j4][wg][row]
-    uint32_t n = 0, jn = 0;
+    uint32_t n = 0, jn = 0, grp = 0;
     int out_valid = 0, out_first = 0;
     uint32_t out_par = 0;
 
@@ -524,9 +546,11 @@ k_nmf_tcs(Params p, const __grid_constant__ CUtensorMap tmap1, const __grid_cons
       collect(out_first != 0);
       out_valid = 0;
     };
-    // rank 64: step nn (any parity); hands the accumulator back to the second-MMA issuer
-    auto drain_shared = [&](uint32_t nn, bool first) {
-      mbar_wait(&b_full[0], nn & 1);
+    // rank 64: the group of steps that has just ended (both warpgroups, each its 32 components); hands the accumulator
+    // back to the second-MMA issuer
+    auto drain_shared = [&](bool first) {
+      mbar_wait(&b_full[0], grp & 1);
+      grp++;
       tc_fence_after();
       collect(first);
       tc_fence_before();
@@ -581,9 +605,10 @@ k_nmf_tcs(Params p, const __grid_constant__ CUtensorMap tmap1, const __grid_cons
         sub2(l0, l1, r0, r1, bf16lo_to_f(ph[j]), bf16hi_to_f(ph[j]));
         pl[j] = cvt2(l0, l1);
       }
-      // R[wg] is still read by the second MMA of this warpgroup's previous step until that step's partial is complete:
-      // rank < 64 collects it here; rank 64 has collected it already (every warpgroup collects every step, in order)
+      // R[wg] is still read by the second MMA of this warpgroup's previous step: rank < 64 collects that step's partial
+      // here (b_full), rank 64 waits for the MMA's own completion signal
       if constexpr (!C::ONE_ACC) drain();
+      else if (nn >= 2) mbar_wait(&r_free[wg], ((nn >> 1) - 1) & 1);
       tmem_st16(tR, *reinterpret_cast<uint32_t(*)[16]>(&ph[0]));
       tmem_st16(tR + 16, *reinterpret_cast<uint32_t(*)[16]>(&ph[16]));
       tmem_st16(tR + 32, *reinterpret_cast<uint32_t(*)[16]>(&pl[0]));
@@ -673,16 +698,19 @@ k_nmf_tcs(Params p, const __grid_constant__ CUtensorMap tmap1, const __grid_cons
           partials_valid = false;
         }
         // ---------------- steps ------------------------------------------------------------------------------------
+        TCS_MARK(0);
+#ifdef FB200_TCS_DEBUG_TIMELINE
+        if (p.dbg && blockIdx.x == 0 && et == 0 && jn < 96) p.dbg[jn * 8 + 7] = phase * 1000 + tile;
+#endif
         const int ns = phase == 0 ? C1 : S2;
         float vn = 0.f;
-        if (phase == 0) { // Nyquist magnitude of this thread's frame: fetched now, used in the tile update
-          vn = gV[(int64_t) (128 * tile + r) * Bp + BT];
-          if (p.clamp_v) vn = fmaxf(vn, kEps);
-        }
+        if (phase == 0) vn = gV[(int64_t) (128 * tile + r) * Bp + BT]; // Nyquist magnitude of this thread's frame: requested now, first
+                                                                        // touched in the tile update (a use here exposes a DRAM round trip per job)
         if constexpr (C::ONE_ACC) {
           for (int i = 0; i < ns; i++, n++) {
             if ((int) (n & 1) == wg) do_step(n, phase == 0);
-            if (i >= 1) drain_shared(n - 1, i == 1);
+            // the group that ended with the previous step (one step of lag: its last second MMA runs meanwhile)
+            if (i >= 1 && ((i - 1) % C::GROUP) == C::GROUP - 1) drain_shared(i - 1 < C::GROUP);
           }
         } else {
           for (int i = 0; i < ns; i++, n++) {
@@ -705,8 +733,10 @@ k_nmf_tcs(Params p, const __grid_constant__ CUtensorMap tmap1, const __grid_cons
             for (int j = 0; j < K2; j++) old[j] = __ldcg(gW + (int64_t) (k0 + j) * Bp + 128 * tile + r);
           }
         }
-        if constexpr (C::ONE_ACC) drain_shared(n - 1, ns == 1);
+        TCS_MARK(1);
+        if constexpr (C::ONE_ACC) drain_shared(ns <= C::GROUP);
         else drain();
+        TCS_MARK(2);
         if constexpr (C::HAS_F32) {
           mbar_wait(&st_full[jn & 1], (jn >> 1) & 1); // long complete; makes the bulk copy's bytes visible to this thread
           const float* ft = reinterpret_cast<const float*>(smem + C::OFF_F32 + (jn & 1) * C::F32TILE);
@@ -718,18 +748,17 @@ k_nmf_tcs(Params p, const __grid_constant__ CUtensorMap tmap1, const __grid_cons
 #pragma unroll
             for (int j = 0; j < K2; j++) old[j] = ft[(k0 + j) * 128 + r];
           }
-          fence_proxy_async(); // generic reads of the tile before the producer's next bulk copy into it (see do_step)
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&st_empty[jn & 1]);
         }
         // the running sums of the tile are complete; every thread reads values written by the other warpgroup
         if constexpr (C::ONE_ACC) { tmem_wait_st(); tc_fence_before(); }
         epi_bar();
         if constexpr (C::ONE_ACC) tc_fence_after();
+        TCS_MARK(3);
         if (phase == 0) {
           // ---------------- H-tile update (NMF.hpp:168-170) from the fp32 state -----------------------------------------
           const int f = 128 * tile + r;
           float (&h)[K] = old;
+          if (p.clamp_v) vn = fmaxf(vn, kEps); // NMF.hpp:60
           float pn = 0.f;
 #pragma unroll
           for (int k = 0; k < K; k++) pn = fmaf(h[k], WN[k], pn);
@@ -856,34 +885,43 @@ k_nmf_tcs(Params p, const __grid_constant__ CUtensorMap tmap1, const __grid_cons
             epi_bar();
             if (et < K) WN[et] *= f_inv[et];
             epi_bar();
-            // 8 consecutive bins of one component per item; four items in flight per thread (the loads come from L2)
-            const int n_items = (BT / 8) * K; // BT/8 >= 16, K >= 16 -> a multiple of 256
-            for (int base = et; base < n_items; base += 4 * 256) {
-              float4 x0[4], x1[4];
+            // Rescale sweep over W (fp32 state + split operand).  One warp pass = one component block (8 k) x 32 bins:
+            // lane = (k & 7, 8-bin group), so that the fp32 rows are touched in 128-byte runs AND the 16-byte operand units
+            // of a core matrix (8 k x 8 bins, 128 bytes) are written by 8 adjacent lanes.  (An item-per-thread mapping with
+            // 32 different lines per instruction made this sweep 29 % of a rank-64 iteration: developer timeline, r02y.)
+            {
+              const int kk = lane >> 2, bq = lane & 3;
+              const int n_pass = KB * (BT / 32);
+              constexpr int U = 4; // passes in flight per warp (16 made no difference: the sweep moves 1.5 MB per rank-64 buffer
+                                   // against the |X| streams of all other CTAs, it is bandwidth, not latency)
+              for (int w0 = ew; w0 < n_pass; w0 += 8 * U) {
+                float4 x0[U], x1[U];
 #pragma unroll
-              for (int u = 0; u < 4; u++) {
-                const int it8 = base + 256 * u;
-                if (it8 < n_items) {
-                  const float4* src = reinterpret_cast<const float4*>(gW + (int64_t) (it8 % K) * Bp + 8 * (it8 / K));
-                  x0[u] = __ldcg(src); x1[u] = __ldcg(src + 1);
+                for (int u = 0; u < U; u++) {
+                  const int wi = w0 + 8 * u;
+                  if (wi < n_pass) {
+                    const int k = 8 * (wi % KB) + kk, bin0 = 32 * (wi / KB) + 8 * bq;
+                    const float4* src = reinterpret_cast<const float4*>(gW + (int64_t) k * Bp + bin0);
+                    x0[u] = __ldcg(src); x1[u] = __ldcg(src + 1);
+                  }
                 }
-              }
 #pragma unroll
-              for (int u = 0; u < 4; u++) {
-                const int it8 = base + 256 * u;
-                if (it8 < n_items) {
-                  const int k = it8 % K, blk = it8 / K;
-                  const float s = f_inv[k];
-                  float4 a = x0[u], b = x1[u];
-                  a.x *= s; a.y *= s; a.z *= s; a.w *= s; b.x *= s; b.y *= s; b.z *= s; b.w *= s;
-                  float4* dstw = reinterpret_cast<float4*>(gW + (int64_t) k * Bp + 8 * blk);
-                  dstw[0] = a; dstw[1] = b;
-                  uint32_t ph[4], pm[4];
-                  split2(a.x, a.y, ph[0], pm[0]); split2(a.z, a.w, ph[1], pm[1]);
-                  split2(b.x, b.y, ph[2], pm[2]); split2(b.z, b.w, ph[3], pm[3]);
-                  __nv_bfloat16* dst = gWop + op_index_w<K>(0, k, 8 * blk);
-                  *reinterpret_cast<uint4*>(dst) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-                  *reinterpret_cast<uint4*>(dst + KB * 64) = make_uint4(pm[0], pm[1], pm[2], pm[3]);
+                for (int u = 0; u < U; u++) {
+                  const int wi = w0 + 8 * u;
+                  if (wi < n_pass) {
+                    const int k = 8 * (wi % KB) + kk, bin0 = 32 * (wi / KB) + 8 * bq;
+                    const float sc = f_inv[k];
+                    float4 a = x0[u], b = x1[u];
+                    a.x *= sc; a.y *= sc; a.z *= sc; a.w *= sc; b.x *= sc; b.y *= sc; b.z *= sc; b.w *= sc;
+                    float4* dstw = reinterpret_cast<float4*>(gW + (int64_t) k * Bp + bin0);
+                    dstw[0] = a; dstw[1] = b;
+                    uint32_t ph[4], pm[4];
+                    split2(a.x, a.y, ph[0], pm[0]); split2(a.z, a.w, ph[1], pm[1]);
+                    split2(b.x, b.y, ph[2], pm[2]); split2(b.z, b.w, ph[3], pm[3]);
+                    __nv_bfloat16* dst = gWop + op_index_w<K>(0, k, bin0);
+                    *reinterpret_cast<uint4*>(dst) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+                    *reinterpret_cast<uint4*>(dst + KB * 64) = make_uint4(pm[0], pm[1], pm[2], pm[3]);
+                  }
                 }
               }
             }
@@ -894,9 +932,13 @@ k_nmf_tcs(Params p, const __grid_constant__ CUtensorMap tmap1, const __grid_cons
         // generic-proxy stores -> async-proxy reads (bulk copies issued by the producer of this CTA): the writer-side
         // proxy fence plus the CTA barrier order them; no device-scope fence is needed, nobody outside the CTA reads.
         // The barrier also separates this job's reads of the running sums from the next job's first partial.
+        TCS_MARK(4);
         fence_async_all();
         epi_bar();
+        TCS_MARK(5);
         if (et == 0) *jobs_done = jn + 1;
+        // the staged fp32 tile has been read (generic proxy) before the fence above: hand its buffer back to the producer
+        if (C::HAS_F32 && lane == 0) mbar_arrive(&st_empty[jn & 1]);
       });
     }
   }
@@ -923,6 +965,14 @@ static int32_t tcs_run_t(Plan* p, const NmfDev& d, int iters, bool upd_w, bool u
   FB_CUDA(p, p->wop_buf.ensure(wop_bytes));
   FB_CUDA(p, p->hop_buf.ensure(hop_bytes));
   Params q{};
+  q.dbg = nullptr;
+#ifdef FB200_TCS_DEBUG_TIMELINE
+  if (getenv("FB200_TCS_TIMELINE")) {
+    FB_CUDA(p, p->out_b.ensure(sizeof(long long) * 96 * 8));
+    FB_CUDA(p, cudaMemsetAsync(p->out_b.p, 0, sizeof(long long) * 96 * 8, p->stream));
+    q.dbg = p->out_b.as<long long>();
+  }
+#endif
   q.V = d.V; q.W = d.W; q.H = d.H; q.hden = d.hden;
   q.Wop = p->wop_buf.as<__nv_bfloat16>(); q.Hop = p->hop_buf.as<__nv_bfloat16>();
   q.batch = d.batch; q.Fp = d.Fp; q.Bp = d.Bp; q.BT = BT;
@@ -950,6 +1000,19 @@ static int32_t tcs_run_t(Plan* p, const NmfDev& d, int iters, bool upd_w, bool u
   cudaEventRecord(p->kev[p->kev_used++], p->stream);
   p->launches++; p->launches_nmf++;
   FB_CUDA(p, cudaGetLastError());
+#ifdef FB200_TCS_DEBUG_TIMELINE
+  if (q.dbg) {
+    long long h[96 * 8];
+    FB_CUDA(p, cudaMemcpyAsync(h, q.dbg, sizeof h, cudaMemcpyDeviceToHost, p->stream));
+    FB_CUDA(p, cudaStreamSynchronize(p->stream));
+    fprintf(stderr, "job kind tile | start  steps_done  collected  sums_visible  updated  published | steps  update+publish  (cycles)\n");
+    for (int j = 0; j < 96 && h[j * 8]; j++) {
+      const long long* e = h + j * 8;
+      fprintf(stderr, "%3d %s %3lld | %9lld %9lld %9lld %9lld %9lld %9lld | %8lld %8lld\n", j, e[7] >= 1000 ? "W" : "H", e[7] % 1000, e[0] - h[0], e[1] - h[0],
+              e[2] - h[0], e[3] - h[0], e[4] - h[0], e[5] - h[0], e[1] - e[0], e[5] - e[1]);
+    }
+  }
+#endif
   return FB200_OK;
 }
 
