@@ -56,7 +56,7 @@ struct Cfg {
   // TMEM columns
   static constexpr bool ONE_ACC = K == 64;              // a single accumulator / set of sums shared by both warpgroups
 #ifndef FB200_TCS_GROUP
-#define FB200_TCS_GROUP 4
+#define FB200_TCS_GROUP 2
 #endif
   // rank 64: consecutive steps whose second MMAs accumulate in TMEM before the epilogue collects them.  Collecting is 192
   // columns per thread and stalls the one accumulator; the tensor core's truncating accumulate is the price (a chain of
