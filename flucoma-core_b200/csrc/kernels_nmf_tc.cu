@@ -25,7 +25,7 @@
 // the parts sit next to each other in shared memory) and R_lo by X_hi (N = 16, its own accumulator columns).  The
 // epilogue sums the three 16-column groups of every step's FRESH accumulator with round-to-nearest adds (the tensor
 // core's accumulate truncates; accumulated over a whole job in TMEM that bias alone measured 1.3e-4).
-// Errors against the oracle after 200 iterations: see tools/tc_margin.py and profiles/r02k_experiments.txt.
+// Errors against the fp64 CPU restatement after 200 iterations: see tools/tc_margin.py and profiles/r02k_experiments.txt.
 //
 // The Nyquist bin (B = 2^m + 1) does not fit the 128-wide tiles; its column is carried on the SIMT side of the epilogue
 // (a 16-term dot product per frame), so the tensor tiles cover bins 0 .. B-2 exactly.
@@ -312,7 +312,7 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
         const uint32_t dP = tbase + TM_P + 64 * g;
         // the terms of (A_hi + A_mid + A_lo)(B_hi + B_mid + B_lo) down to 2^-16: the ratio that is made from P is itself
         // carried as a two-part (16-bit) operand, so the 2^-16 .. 2^-24 terms (hi lo, lo hi, mid mid) bought nothing
-        // measurable against the fp64 oracle and cost half of the first MMA's operand traffic (profiles/r02k_experiments.txt)
+        // measurable against the fp64 CPU restatement and cost half of the first MMA's operand traffic (profiles/r02k_experiments.txt)
         mma_ss_lohi<0>(dP, alo, HI_A, blo, HI_A, idesc);                          // hi  hi
         mma_ss_lohi<1>(dP, alo, HI_A, blo + PSTEP, HI_A, idesc);                  // hi  mid
         mma_ss_lohi<1>(dP, alo + PSTEP, HI_A, blo, HI_A, idesc);                  // mid hi
