@@ -1,0 +1,8 @@
+#!/bin/bash
+cd $GRAFT_REPO_ROOT
+mkdir -p gpurun_out
+timeout 2400 python -m pytest tests -m gpu -q -x > gpurun_out/r03a_pytest.log 2>&1; echo "rc=$?" >> gpurun_out/r03a_pytest.log
+grep -E "^(FAILED|ERROR)|passed|failed" gpurun_out/r03a_pytest.log | tail -5
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r03a_smoke.log 2>&1; echo "smoke rc=$?"
+for c in 5 1; do timeout 600 python bench.py --config $c --steps 5 --warmup 3 --no-cpu > gpurun_out/r03a_bench_c$c.json 2> gpurun_out/r03a_bench_c$c.err; python -c "
+import json; d=json.load(open('gpurun_out/r03a_bench_c$c.json')); print('c$c', round(d['ms_per_step'],2), 'e2e', round(d['e2e']['ms_per_step'],2), d['stages_ms_per_step'], d['roofline']['kernel'][:12], round(d['roofline']['avg_launch_ms'],3), round(d['roofline']['frac'],4))"; done
