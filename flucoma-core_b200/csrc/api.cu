@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <chrono>
+#include <functional>
 #include <random>
 #include <thread>
 
@@ -108,7 +109,7 @@ struct StageTimer {
 // h_audio != nullptr: the audio still sits in (pinned) host memory; every wave is uploaded into d_audio on the plan's
 // copy stream while the previous waves run their kernels, so that only the first upload is exposed.
 int32_t run_stft(Plan* p, const float* d_audio, int64_t batch, int64_t n, int64_t F, float* V, int64_t Fp, int64_t Bp,
-                 float2* spec_all, int64_t half, const float* h_audio = nullptr, int hop_override = 0)
+                 float2* spec_all, int64_t half, const float* h_audio = nullptr, int hop_override = 0, bool guard_staging = true)
 {
   const int B = p->bins;
   int64_t wave = wave_size(p, F, batch, 1);
@@ -117,8 +118,12 @@ int32_t run_stft(Plan* p, const float* d_audio, int64_t batch, int64_t n, int64_
     size_t nw = (size_t) ((batch + wave - 1) / wave);
     while (p->cev.size() < nw + 1) { cudaEvent_t e; FB_CUDA(p, cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); p->cev.push_back(e); }
     // the copy stream must not overwrite the staging buffer before everything queued so far has finished with it
-    FB_CUDA(p, cudaEventRecord(p->cev[nw], p->stream));
-    FB_CUDA(p, cudaStreamWaitEvent(p->copy_stream, p->cev[nw], 0));
+    // (not for the second part of a split call: its region of the buffer is untouched, and the wait would put the
+    // upload behind the first part's update kernel)
+    if (guard_staging) {
+      FB_CUDA(p, cudaEventRecord(p->cev[nw], p->stream));
+      FB_CUDA(p, cudaStreamWaitEvent(p->copy_stream, p->cev[nw], 0));
+    }
     size_t i = 0;
     for (int64_t b0 = 0; b0 < batch; b0 += wave, i++) {
       int64_t nb = std::min(wave, batch - b0);
@@ -277,9 +282,20 @@ void simt_run_iters(Plan* p, NmfDev& d, int n, bool upd_w, bool upd_h)
 // small copies on the plan's copy stream while the kernel runs, reports iterations 1..n (each exactly once, in order) as
 // the batch advances, and raises a cancel word in host-mapped memory when a callback returns 0 (CTA 0 relays it into the
 // device word all CTAs sample).  See `Ctl`.
-int32_t run_tc_async(Plan* p, NmfDev& d, int iters, bool upd_w, bool upd_h, fb200_progress_fn progress, void* user)
+// `parts`: consecutive slices of the batch, each its own persistent launch (a call whose audio sits in host memory runs a
+// first slice of one buffer per SM while the rest is still being uploaded: see fb200_bufnmf); `before_launch(i)` queues
+// whatever slice i needs on the stream ahead of its launch.  Without a callback the launches are simply queued.
+int32_t run_tc_parts(Plan* p, NmfDev* parts, int nparts, const std::function<int32_t(int)>& before_launch, int iters, bool upd_w, bool upd_h,
+                     fb200_progress_fn progress, void* user)
 {
-  const int grid = tc_grid(p, d);
+  constexpr int SLOT = 256; // control words per part: [0] cancel, [1 + cta] pass counters
+  if (!progress) {
+    for (int i = 0; i < nparts; i++) {
+      if (before_launch) FB_TRY(before_launch(i));
+      FB_TRY(tc_run(p, parts[i], iters, upd_w, upd_h, nullptr, nullptr));
+    }
+    return FB200_OK;
+  }
   FB_CUDA(p, p->ctrl_dev.ensure(sizeof(unsigned int) * 1025));
   FB_CUDA(p, p->ctrl.ensure(sizeof(unsigned int) * 1026));
   unsigned int* host = reinterpret_cast<unsigned int*>(p->ctrl.p); // [0, 1024): counters read back; [1024]: the word "1"
@@ -289,10 +305,16 @@ int32_t run_tc_async(Plan* p, NmfDev& d, int iters, bool upd_w, bool upd_h, fb20
   host[1024] = 0u; // the cancel request: written by this thread, read by CTA 0 through the mapping below
   unsigned int* host_dev = nullptr;
   FB_CUDA(p, cudaHostGetDevicePointer(reinterpret_cast<void**>(&host_dev), host, 0));
-  FB_TRY(tc_run(p, d, iters, upd_w, upd_h, dev, host_dev + 1024));
-  FB_CUDA(p, cudaEventRecord(p->ev_async, p->stream));
   const int64_t npass = (upd_w && upd_h) ? iters + 1 : iters;
-  const int64_t total = (int64_t) d.batch * npass;
+  int64_t total = 0;
+  int grid = 0;
+  for (int i = 0; i < nparts; i++) {
+    if (before_launch) FB_TRY(before_launch(i));
+    FB_TRY(tc_run(p, parts[i], iters, upd_w, upd_h, dev + i * SLOT, host_dev + 1024));
+    total += (int64_t) parts[i].batch * npass;
+    grid = std::max(grid, tc_grid(p, parts[i]));
+  }
+  FB_CUDA(p, cudaEventRecord(p->ev_async, p->stream));
   int64_t reported = 0;
   bool cancelled = false;
   auto report_up_to = [&](int64_t it) -> int32_t {
@@ -312,16 +334,17 @@ int32_t run_tc_async(Plan* p, NmfDev& d, int iters, bool upd_w, bool upd_h, fb20
     if (q == cudaSuccess) break;
     if (q != cudaErrorNotReady) { p->err = std::string("CUDA error: ") + cudaGetErrorString(q); return FB200_ERR_CUDA; }
     if (!cancelled) {
-      FB_CUDA(p, cudaMemcpyAsync(host, dev + 1, sizeof(unsigned int) * (size_t) grid, cudaMemcpyDeviceToHost, p->copy_stream));
-      FB_CUDA(p, cudaStreamSynchronize(p->copy_stream));
+      FB_CUDA(p, cudaMemcpyAsync(host, dev, sizeof(unsigned int) * (size_t) (nparts * SLOT), cudaMemcpyDeviceToHost, p->poll_stream));
+      FB_CUDA(p, cudaStreamSynchronize(p->poll_stream));
       int64_t done = 0;
-      for (int i = 0; i < grid; i++) done += host[i];
+      for (int i = 0; i < nparts; i++)
+        for (int c = 0; c < grid; c++) done += host[i * SLOT + 1 + c];
       // iteration `it` is reported once the batch as a whole has done the work of `it` iterations; the last one at the end
       FB_TRY(report_up_to(std::min<int64_t>(iters - 1, done * iters / std::max<int64_t>(1, total))));
     }
     std::this_thread::sleep_for(std::chrono::microseconds(250));
   }
-  FB_CUDA(p, cudaStreamSynchronize(p->copy_stream));
+  FB_CUDA(p, cudaStreamSynchronize(p->poll_stream));
   FB_TRY(report_up_to(iters));
   return cancelled ? FB200_CANCELLED : FB200_OK;
 }
@@ -364,7 +387,7 @@ int32_t run_nmf_loop(Plan* p, NmfDev& d, int iters, bool upd_w, bool upd_h, fb20
     return FB200_OK;
   };
   if (!progress) return run_group(iters);
-  if (stride == FB200_PROGRESS_ASYNC && use_tc) return run_tc_async(p, d, iters, upd_w, upd_h, progress, user);
+  if (stride == FB200_PROGRESS_ASYNC && use_tc) return run_tc_parts(p, &d, 1, nullptr, iters, upd_w, upd_h, progress, user);
   const int s = stride == FB200_PROGRESS_ASYNC ? 8 : std::max(1, stride);
   for (int it0 = 0; it0 < iters; it0 += s) {
     const int n = std::min(s, iters - it0);
@@ -484,6 +507,7 @@ int32_t fb200_plan_create(const fb200_config* cfg, fb200_plan** out)
   if (cudaGetDeviceProperties(&prop, cfg->device) == cudaSuccess) p->sm_count = prop.multiProcessorCount;
   bool ok = cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking) == cudaSuccess;
   ok = ok && cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+  ok = ok && cudaStreamCreateWithFlags(&p->poll_stream, cudaStreamNonBlocking) == cudaSuccess;
   for (auto& e : p->ev) ok = ok && cudaEventCreate(&e) == cudaSuccess;
   ok = ok && p->window.ensure(sizeof(float) * (size_t) p->win) == cudaSuccess;
   if (!ok) {
@@ -516,6 +540,7 @@ void fb200_plan_destroy(fb200_plan* p)
   for (auto& e : p->kev) cudaEventDestroy(e);
   for (auto& e : p->cev) cudaEventDestroy(e);
   if (p->copy_stream) { cudaStreamSynchronize(p->copy_stream); cudaStreamDestroy(p->copy_stream); }
+  if (p->poll_stream) { cudaStreamSynchronize(p->poll_stream); cudaStreamDestroy(p->poll_stream); }
   if (p->stream) cudaStreamDestroy(p->stream);
   delete p;
 }
@@ -802,15 +827,46 @@ int32_t fb200_bufnmf(fb200_plan* p, const fb200_bufnmf_args* a)
     FB_CUDA(p, p->spec.ensure(sizeof(float2) * (size_t) (batch * F * B)));
     spec_all = p->spec.as<float2>();
   }
-  FB_TRY(run_stft(p, (const float*) d_audio, batch, n, F, d.V, d.Fp, d.Bp, spec_all, p->win / 2,
-                  host ? (const float*) a->audio : nullptr));
-  t.mark(2);
+  // A call whose audio sits in host memory and that runs on the resident tensor-core engine is split: the first
+  // sm_count buffers (one per CTA: exactly one round of the persistent kernel) are uploaded, transformed and started,
+  // and the upload of the rest runs under that launch instead of in front of everything (config 2: 536 MB = 9.7 ms of
+  // PCIe time, of which 1.4 ms stay exposed).  The number of rounds is unchanged: 1 + ceil((batch - sm) / sm).
+  const int be = p->cfg.backend;
+  const bool async_or_none = !a->progress || a->progress_stride == FB200_PROGRESS_ASYNC;
+  const bool split = host && needs_analysis && a->iterations > 0 && async_or_none && batch >= 3 * (int64_t) p->sm_count &&
+                     (be == FB200_BACKEND_AUTO || be == FB200_BACKEND_TCGEN05) && tc_eligible(d);
   const float* U_h = nullptr;
-  if (!dW0 || !dH0) FB_TRY(draw_uniforms(p, batch, u_stride, any_random, &U, &U_h));
-  launch_nmf_init(p, d, U, U_h, u_stride, dW0, dH0, 0);
-  t.mark(3);
-  int32_t st = run_nmf_loop(p, d, a->iterations * (needs_analysis ? 1 : 0), !fix_w, !fix_h, a->progress,
-                            a->progress_user, a->progress_stride);      // :268-271
+  int32_t st = FB200_OK;
+  if (!split) {
+    FB_TRY(run_stft(p, (const float*) d_audio, batch, n, F, d.V, d.Fp, d.Bp, spec_all, p->win / 2,
+                    host ? (const float*) a->audio : nullptr));
+    t.mark(2);
+    if (!dW0 || !dH0) FB_TRY(draw_uniforms(p, batch, u_stride, any_random, &U, &U_h));
+    launch_nmf_init(p, d, U, U_h, u_stride, dW0, dH0, 0);
+    t.mark(3);
+    st = run_nmf_loop(p, d, a->iterations * (needs_analysis ? 1 : 0), !fix_w, !fix_h, a->progress,
+                      a->progress_user, a->progress_stride);            // :268-271
+  } else {
+    t.mark(2);
+    if (!dW0 || !dH0) FB_TRY(draw_uniforms(p, batch, u_stride, any_random, &U, &U_h));
+    launch_nmf_init(p, d, U, U_h, u_stride, dW0, dH0, 0); // does not depend on |X|
+    t.mark(3);
+    const int64_t head = p->sm_count;
+    NmfDev parts[2] = {d, d};
+    parts[0].batch = (int) head;
+    parts[1].batch = (int) (batch - head);
+    parts[1].V = d.V + head * d.Fp * d.Bp;
+    parts[1].W = d.W + head * d.KP * d.Bp;
+    parts[1].H = d.H + head * d.Fp * d.KP;
+    parts[1].hden = d.hden + head * d.KP;
+    auto front = [&](int i) -> int32_t {
+      const int64_t b0 = i ? head : 0, nb = i ? batch - head : head;
+      return run_stft(p, (const float*) d_audio + b0 * n, nb, n, F, d.V + b0 * d.Fp * d.Bp, d.Fp, d.Bp,
+                      spec_all ? spec_all + b0 * F * B : nullptr, p->win / 2, (const float*) a->audio + b0 * n, 0, i == 0);
+    };
+    p->backend_used = FB200_BACKEND_TCGEN05;
+    st = run_tc_parts(p, parts, 2, front, a->iterations, !fix_w, !fix_h, a->progress, a->progress_user);
+  }
   if (st < 0) return st;
   t.mark(4);
   if (st == FB200_CANCELLED) {                                           // :273-274

@@ -96,6 +96,7 @@ struct Plan {
   int win = 0, hop = 0, fft = 0, bins = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr; // host -> device uploads that overlap with kernels on `stream`
+  cudaStream_t poll_stream = nullptr; // the asynchronous progress mode reads the device counters here (never behind an upload)
   std::vector<cudaEvent_t> cev;       // one event per upload wave (+ one fence)
   cudaEvent_t ev[10]{};
   cudaEvent_t ev_async = nullptr;     // completion of the persistent launch the asynchronous progress mode polls

@@ -163,3 +163,27 @@ def test_tc_engine_async_cancel_finishes_the_iteration_in_flight(fb):
             if min(at) < iters:
                 break
     assert min(at) < iters, "the cancel arrived after everything had finished in three attempts"
+
+
+def test_bufnmf_host_call_split_into_a_first_round_and_the_rest(fb):
+    """fb200_bufnmf with HOST audio on the resident engine starts one buffer per SM while the rest of the batch is still
+    being uploaded (two persistent launches).  Results must be bit-identical to the unsplit device-memory call, with and
+    without an asynchronous progress callback, and the callback must still see iterations 1..n exactly once, in order."""
+    torch = pytest.importorskip("torch")
+    from tests.golden.make_golden import synth_audio
+    sm = torch.cuda.get_device_properties(0).multi_processor_count
+    batch, n = 3 * sm + 7, 8192
+    a = np.stack([synth_audio(50 + (b % 9), n) * (1.0 + 0.01 * b) for b in range(batch)]).astype(np.float32)
+    seeds = np.arange(batch)
+    with fb.Plan(win=256, hop=64, fft=256) as plan:
+        rd = plan.bufnmf(torch.from_numpy(a).cuda(), 16, 12, seeds=seeds, resynth=True)      # device memory: one launch
+        assert plan.stats()["backend_used"] == fb.BACKEND_TCGEN05 and plan.stats()["update_kernel_launches"] == 1
+        rh = plan.bufnmf(a, 16, 12, seeds=seeds, resynth=True)                               # host memory: split
+        assert plan.stats()["backend_used"] == fb.BACKEND_TCGEN05 and plan.stats()["update_kernel_launches"] == 2
+        seen = []
+        rp = plan.bufnmf(a, 16, 12, seeds=seeds, progress=lambda it: seen.append(it) or True, progress_stride=fb.PROGRESS_ASYNC)
+        assert plan.stats()["update_kernel_launches"] == 2
+    assert seen == list(range(1, 13))
+    for k in ("bases", "acts", "resynth"):
+        assert np.array_equal(np.asarray(rd[k].cpu() if hasattr(rd[k], "cpu") else rd[k]), rh[k]), k
+    assert np.array_equal(rh["bases"], rp["bases"]) and np.array_equal(rh["acts"], rp["acts"])
