@@ -833,8 +833,10 @@ int32_t fb200_bufnmf(fb200_plan* p, const fb200_bufnmf_args* a)
   // PCIe time, of which 1.4 ms stay exposed).  The number of rounds is unchanged: 1 + ceil((batch - sm) / sm).
   const int be = p->cfg.backend;
   const bool async_or_none = !a->progress || a->progress_stride == FB200_PROGRESS_ASYNC;
+  const bool can_tc1 = (be == FB200_BACKEND_AUTO || be == FB200_BACKEND_TCGEN05) && tc_eligible(d);
+  const bool can_tc2 = !can_tc1 && be != FB200_BACKEND_SIMT && tcs_eligible(d) && !fix_w && !a->progress; // the streamed engine has no in-kernel progress
   const bool split = host && needs_analysis && a->iterations > 0 && async_or_none && batch >= 3 * (int64_t) p->sm_count &&
-                     (be == FB200_BACKEND_AUTO || be == FB200_BACKEND_TCGEN05) && tc_eligible(d);
+                     (can_tc1 || can_tc2);
   const float* U_h = nullptr;
   int32_t st = FB200_OK;
   if (!split) {
@@ -864,8 +866,18 @@ int32_t fb200_bufnmf(fb200_plan* p, const fb200_bufnmf_args* a)
       return run_stft(p, (const float*) d_audio + b0 * n, nb, n, F, d.V + b0 * d.Fp * d.Bp, d.Fp, d.Bp,
                       spec_all ? spec_all + b0 * F * B : nullptr, p->win / 2, (const float*) a->audio + b0 * n, 0, i == 0);
     };
-    p->backend_used = FB200_BACKEND_TCGEN05;
-    st = run_tc_parts(p, parts, 2, front, a->iterations, !fix_w, !fix_h, a->progress, a->progress_user);
+    if (can_tc1) {
+      p->backend_used = FB200_BACKEND_TCGEN05;
+      st = run_tc_parts(p, parts, 2, front, a->iterations, !fix_w, !fix_h, a->progress, a->progress_user);
+    } else {
+      p->backend_used = FB200_BACKEND_TCGEN05_STREAMED;
+      parts[0].op_total = parts[1].op_total = (int) batch;
+      parts[0].op_first = 0; parts[1].op_first = (int) head;
+      for (int i = 0; i < 2 && st == FB200_OK; i++) {
+        st = front(i);
+        if (st == FB200_OK) st = tcs_run(p, parts[i], a->iterations, !fix_w, !fix_h);
+      }
+    }
   }
   if (st < 0) return st;
   t.mark(4);

@@ -89,6 +89,8 @@ struct NmfDev {
   int tiles_per_cta;  // consecutive 128-frame tiles handled by one CTA
   int clamp_v;        // processFrame clamps the input magnitudes at eps (NMF.hpp:60)
   int shared_w;       // 1: a single W (batch stride 0) shared by all buffers (processFrame path)
+  int op_first, op_total; // streamed engine: this NmfDev is buffers [op_first, op_first + batch) of a call of op_total buffers
+                          // (split calls: the operand arrays are sized for the whole call, each part uses its own slice); 0, 0 = whole call
 };
 
 struct Plan {

@@ -961,9 +961,10 @@ static int32_t tcs_run_t(Plan* p, const NmfDev& d, int iters, bool upd_w, bool u
   using C = Cfg<K>;
   const int BT = d.B - 1;
   const int nw = d.shared_w ? 1 : d.batch;
-  const size_t wop_bytes = (size_t) nw * (BT / 8) * C::ROWB, hop_bytes = (size_t) d.batch * (d.Fp / 8) * C::ROWB;
-  FB_CUDA(p, p->wop_buf.ensure(wop_bytes));
-  FB_CUDA(p, p->hop_buf.ensure(hop_bytes));
+  const int total = d.op_total > 0 ? d.op_total : d.batch, first = d.op_total > 0 ? d.op_first : 0;
+  const size_t wop_one = (size_t) (BT / 8) * C::ROWB, hop_one = (size_t) (d.Fp / 8) * C::ROWB;
+  FB_CUDA(p, p->wop_buf.ensure((d.shared_w ? 1 : (size_t) total) * wop_one));
+  FB_CUDA(p, p->hop_buf.ensure((size_t) total * hop_one));
   Params q{};
   q.dbg = nullptr;
 #ifdef FB200_TCS_DEBUG_TIMELINE
@@ -974,7 +975,8 @@ static int32_t tcs_run_t(Plan* p, const NmfDev& d, int iters, bool upd_w, bool u
   }
 #endif
   q.V = d.V; q.W = d.W; q.H = d.H; q.hden = d.hden;
-  q.Wop = p->wop_buf.as<__nv_bfloat16>(); q.Hop = p->hop_buf.as<__nv_bfloat16>();
+  q.Wop = reinterpret_cast<__nv_bfloat16*>(p->wop_buf.as<uint8_t>() + (d.shared_w ? 0 : (size_t) first * wop_one));
+  q.Hop = reinterpret_cast<__nv_bfloat16*>(p->hop_buf.as<uint8_t>() + (size_t) first * hop_one);
   q.batch = d.batch; q.Fp = d.Fp; q.Bp = d.Bp; q.BT = BT;
   q.iters = iters; q.upd_w = upd_w ? 1 : 0; q.upd_h = upd_h ? 1 : 0; q.shared_w = d.shared_w; q.clamp_v = d.clamp_v;
   const int T = d.Fp / 128;

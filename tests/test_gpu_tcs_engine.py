@@ -139,3 +139,21 @@ def test_tcs_engine_exact_progress_and_cancel(fb, oracle):
     for b in range(2):
         Wo, Ho, _, _ = oracle.nmf_process(X[b], 32, 5, True, True, 1 + b)
         assert rel(W[b], Wo) < TOL and rel(H[b], Ho) < TOL
+
+
+def test_bufnmf_host_call_split_on_the_streamed_engine(fb):
+    """fb200_bufnmf with HOST audio at rank 32: the first sm_count buffers are started while the rest uploads (two launches,
+    each with its own slice of the operand arrays); bit-identical to the unsplit device-memory call."""
+    torch = pytest.importorskip("torch")
+    from tests.golden.make_golden import synth_audio
+    sm = torch.cuda.get_device_properties(0).multi_processor_count
+    batch, n = 3 * sm + 5, 8192
+    a = np.stack([synth_audio(70 + (b % 7), n) * (1.0 + 0.01 * b) for b in range(batch)]).astype(np.float32)
+    seeds = np.arange(batch)
+    with fb.Plan(win=256, hop=64, fft=256) as plan:
+        rd = plan.bufnmf(torch.from_numpy(a).cuda(), 32, 10, seeds=seeds)
+        assert plan.stats()["backend_used"] == fb.BACKEND_TCGEN05_STREAMED and plan.stats()["update_kernel_launches"] == 1
+        rh = plan.bufnmf(a, 32, 10, seeds=seeds)
+        assert plan.stats()["backend_used"] == fb.BACKEND_TCGEN05_STREAMED and plan.stats()["update_kernel_launches"] == 2
+    for k in ("bases", "acts"):
+        assert np.array_equal(np.asarray(rd[k].cpu() if hasattr(rd[k], "cpu") else rd[k]), rh[k]), k
