@@ -717,7 +717,8 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
             float s = 0.f;
             for (int tt = 0; tt < T; tt++)
               for (int w4 = 0; w4 < 4; w4++) s += part[(tt * 8 + own + w4) * 32 + et];
-            fin[et] = s; // [0,16) wden, [16,32) Nyquist wnum
+            fin[et] = et < 16 ? 1.0f / fmaxf(s, kEps) : s; // [0,16) 1 / max(wden, eps) (one reciprocal per component instead of a
+                                                           // division per element of the update), [16,32) Nyquist wnum
           }
           epi_bar();
           float wnew[2][16];
@@ -738,7 +739,7 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
               for (int k = 0; k < K; k++) {
                 float wold = bf16_bits_to_f(wp[wop_index(2, k, b)]) + bf16_bits_to_f(wp[wop_index(1, k, b)]) + bf16_bits_to_f(wp[wop_index(0, k, b)]);
                 float num = __uint_as_float(wn[k]) + __uint_as_float(wn[16 + k]);
-                float w = wold * num / fmaxf(fin[k], kEps);
+                float w = wold * num * fin[k];
                 wnew[i][k] = w;
                 ss[k] = fmaf(w, w, ss[k]);
                 sm[k] += w;
@@ -750,7 +751,7 @@ k_nmf_tc(NmfDev d, const __grid_constant__ CUtensorMap tmap1, const __grid_const
           if (et == 0) {
 #pragma unroll
             for (int k = 0; k < K; k++) {
-              float w = WN[k] * fin[16 + k] / fmaxf(fin[k], kEps);
+              float w = WN[k] * fin[16 + k] * fin[k];
               wnq[k] = w;
               ss[k] = fmaf(w, w, ss[k]);
               sm[k] += w;

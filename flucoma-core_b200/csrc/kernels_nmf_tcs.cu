@@ -257,7 +257,7 @@ k_nmf_tcs(Params p, const __grid_constant__ CUtensorMap tmap1, const __grid_cons
   float* part = reinterpret_cast<float*>(smem + C::OFF_PART);
   float* red = reinterpret_cast<float*>(smem + C::OFF_RED);
   float* fin = reinterpret_cast<float*>(smem + C::OFF_FIN);
-  float* f_wden = fin;             // [K] sum_f H
+  float* f_wden = fin;             // [K] 1 / max(sum_f H, eps)
   float* f_nyq = fin + K;          // [K] Nyquist numerator
   float* f_inv = fin + 2 * K;      // [K] 1 / column norm
   float* f_ihd = fin + 3 * K;      // [K] 1 / max(hden, eps)
@@ -689,7 +689,8 @@ k_nmf_tcs(Params p, const __grid_constant__ CUtensorMap tmap1, const __grid_cons
             const int owner = (k / K2) * 4, idx = kind * K2 + (k % K2);
             float s = 0.f;
             for (int w4 = 0; w4 < 4; w4++) s += part[(owner + w4) * K + idx];
-            (kind ? f_nyq : f_wden)[k] = s;
+            if (kind) f_nyq[k] = s;
+            else f_wden[k] = 1.0f / fmaxf(s, kEps); // the reciprocal: the tile updates multiply
           }
           epi_bar();
           for (int e = et; e < 8 * K; e += 256) part[e] = 0.f;
@@ -835,7 +836,7 @@ k_nmf_tcs(Params p, const __grid_constant__ CUtensorMap tmap1, const __grid_cons
 #pragma unroll
             for (int i = 0; i < G; i++) {
               const int j = G * jg + i, k = k0 + j;
-              const float w = old[j] * num[i] / fmaxf(f_wden[k], kEps);
+              const float w = old[j] * num[i] * f_wden[k];
               gW[(int64_t) k * Bp + b] = w;
               a[j] = w * w;
               a[K2 + j] = w;
@@ -859,7 +860,7 @@ k_nmf_tcs(Params p, const __grid_constant__ CUtensorMap tmap1, const __grid_cons
               const int owner = (et / K2) * 4, idx = et % K2;
               float s2 = 0.f, s1 = 0.f;
               for (int w4 = 0; w4 < 4; w4++) { s2 += red[(owner + w4) * (K + 4) + idx]; s1 += red[(owner + w4) * (K + 4) + K2 + idx]; }
-              const float wn = WN[et] * f_nyq[et] / fmaxf(f_wden[et], kEps); // Nyquist bin, carried on the SIMT side
+              const float wn = WN[et] * f_nyq[et] * f_wden[et]; // Nyquist bin, carried on the SIMT side
               f_s2[et] = fmaf(wn, wn, s2);
               f_s1[et] = s1 + wn;
               WN[et] = wn;
