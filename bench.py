@@ -500,9 +500,15 @@ def run_ours(args):
                                 "frac": (achieved / peak_tf) if achieved else None, "traffic": traffic,
                                 "kernel": kname, "peak_source": which,
                                 "note": "achieved counts the algorithmic 8*B*K flops per frame per iteration; the tensor pipe "
-                                        "executes 7x that (6-term operand split + 4-term ratio split), see DESIGN.md",
+                                        "executes 6x that (3 split terms in each of the two MMAs), see DESIGN.md 4.2",
                                 "launches_per_step": nl, "avg_launch_ms": ms_kernel / nl,
                                 "kernel_share_of_step": ms_kernel / (agg["ms_total"] / args.steps)}
+            if agg["backend"] == 3 and ms_kernel > 0:
+                # the streamed engine reads |X| twice per iteration (H and W half-iterations are not fused) and the batch
+                # does not fit L2: for configs 3 / 4 HBM is the nearer roof
+                xb = 2.0 * 4.0 * (B - 1) * frames_rank * w["iters"]
+                line["roofline"]["hbm_view"] = {"algorithmic_x_bytes": xb, "achieved": xb / (ms_kernel * 1e-3) / 1e9, "peak": peak_gbs,
+                                                "unit": "GB/s", "frac": xb / (ms_kernel * 1e-3) / 1e9 / peak_gbs}
         if world == 1 and not args.no_cpu:
             cb = cpu_baselines(w, None if args.config in (1, 2, 5) else max(1, w["iters"] // 10))
             line["cpu_baseline"] = cb
