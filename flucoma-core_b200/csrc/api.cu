@@ -365,14 +365,14 @@ int32_t run_nmf_loop(Plan* p, NmfDev& d, int iters, bool upd_w, bool upd_h, fb20
     return FB200_OK;
   }
   // engine choice: the resident tensor-core engine for its shapes (rank 16, <= 513 bins, <= 512 frames, W updated or not),
-  // the streamed one for everything else it covers (rank 9..32, any bins = 128 m + 1, any frame count, fixed-W frame
+  // the streamed one for everything else it covers (rank 9..64, any bins = 128 m + 1, any frame count, fixed-W frame
   // streams) when there are enough independent work units to fill the SMs, the SIMT engine for the rest
   const int be = p->cfg.backend;
   const bool tc1 = (be == FB200_BACKEND_AUTO || be == FB200_BACKEND_TCGEN05) && tc_eligible(d);
   const int64_t units = upd_w ? d.batch : (int64_t) d.batch * ((d.Fp / 128 + 1) / 2);
   const bool tc2 = !tc1 && be != FB200_BACKEND_SIMT && tcs_eligible(d) && (be != FB200_BACKEND_AUTO || units >= 32);
   if (!tc1 && !tc2 && (be == FB200_BACKEND_TCGEN05 || be == FB200_BACKEND_TCGEN05_STREAMED)) {
-    p->err = "tensor-core backend requested but the shape does not qualify (rank 9..32, bins = 128 m + 1, frames padded to 128)";
+    p->err = "tensor-core backend requested but the shape does not qualify (rank 9..64, bins = 128 m + 1, frames padded to 128)";
     return FB200_ERR_UNSUPPORTED;
   }
   const bool use_tc = tc1;
@@ -410,7 +410,7 @@ int32_t run_h_only(Plan* p, NmfDev& d, int iters)
     return tcs_run(p, d, iters, false, true);
   }
   if (be == FB200_BACKEND_TCGEN05 || be == FB200_BACKEND_TCGEN05_STREAMED) {
-    p->err = "tensor-core backend requested but the shape does not qualify (rank 9..32, bins = 128 m + 1)";
+    p->err = "tensor-core backend requested but the shape does not qualify (rank 9..64, bins = 128 m + 1)";
     return FB200_ERR_UNSUPPORTED;
   }
   simt_launch_tile(p, d, 1, 0, iters);

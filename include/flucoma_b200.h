@@ -60,7 +60,7 @@ typedef enum fb200_backend {
   FB200_BACKEND_AUTO = 0,
   FB200_BACKEND_SIMT = 1,             /* fp32 CUDA-core engine: any shape */
   FB200_BACKEND_TCGEN05 = 2,          /* tensor-core engines; as a request: whichever of the two takes the shape */
-  FB200_BACKEND_TCGEN05_STREAMED = 3  /* tensor-core engine with W/H streamed from L2 (rank 9..32, any bins = 128 m + 1, any
+  FB200_BACKEND_TCGEN05_STREAMED = 3  /* tensor-core engine with W/H streamed from L2 (rank 9..64, any bins = 128 m + 1, any
                                          frame count, fixed-dictionary frame streams); as a request: force it */
 } fb200_backend;
 
