@@ -166,6 +166,10 @@ int32_t run_istft(Plan* p, float2* spec, int64_t nsig, int64_t F, int64_t n, flo
                   int64_t out_stride = -1, int stream_norm = 0)
 {
   if (out_stride < 0) out_stride = n;
+  if (istft_fused_eligible(p, nsig, F, n, half)) { // one kernel from spectra to samples; cuFFT for the sizes it does not take
+    const int32_t st = launch_istft_fused(p, spec, nsig, F, n, out, half, out_stride, stream_norm);
+    if (st != FB200_ERR_UNSUPPORTED) return st;
+  }
   int64_t wave = wave_size(p, F, nsig, 1);
   FB_CUDA(p, p->frames.ensure(sizeof(float) * (size_t) (wave * F * p->fft)));
   for (int64_t s0 = 0; s0 < nsig; s0 += wave) {

@@ -1,4 +1,5 @@
-// Fused forward STFT: audio -> (window, real FFT, |X|) in ONE kernel, no frame materialisation, no complex round trip.
+// Fused forward and inverse STFT.
+// Forward: audio -> (window, real FFT, |X|) in ONE kernel, no frame materialisation, no complex round trip.
 //   STFT::process + STFT::magnitude, algorithms/public/STFT.hpp:90-108, 61-66; FFT conventions algorithms/util/FFT.hpp:92-108.
 // A CTA takes a run of consecutive frames of one buffer.  The samples they cover -- (frames - 1) * hop + win of them,
 // each shared by win / hop frames -- are brought into shared memory ONCE by TMA (cp.async.bulk.tensor over a 2-D map
@@ -228,6 +229,232 @@ __global__ void __launch_bounds__(256, 3) k_stft_fused(const __grid_constant__ C
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Fused inverse STFT: complex spectra -> (inverse real FFT, window, overlap-add, / sum w^2) in ONE kernel.
+//   ISTFT::process, algorithms/public/STFT.hpp:178-199 (and the streaming normalisation of BufferedProcess.hpp:231-237).
+// A CTA owns a range of S = fpb * hop padded output positions of one signal and transforms every frame that reaches into
+// it (its fpb frames plus the ceil(win / hop) - 1 frames before them: recomputed, not exchanged -- no atomics, fixed
+// summation order, bitwise repeatable).  Per frame: the spectrum row (B = fft / 2 + 1 complex values, the only HBM read)
+// goes to shared memory, the inverse of the real-input split builds the fft / 2 complex points whose inverse transform
+// is the frame (x[2m] + i x[2m+1]), the inverse runs as conj(FFT(conj Z)) on the forward Stockham stages above, the
+// windowed samples of the round's frames are parked in shared memory and gathered, frame by frame in ascending order,
+// into the CTA's output tile.  The cuFFT pipeline this replaces wrote and re-read an fft-sample frame per spectrum row
+// (8 KB at fft 1024) and needed a cuFFT plan per (frames x signals) shape -- tens of milliseconds on first use.
+template <int NC>
+__global__ void __launch_bounds__(256, 2) k_istft_fused(const float2* __restrict__ spec, const float* __restrict__ window,
+                                                     const float2* __restrict__ tw, int win, int hop, int half, int64_t n, int F, int fpb,
+                                                     int nct, float* __restrict__ out, int64_t out_stride, int stream_norm)
+{
+  constexpr int TPF = NC / 8, G = 256 / TPF, NP = NC + NC / 32 + 1;
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int S = fpb * hop;
+  float* acc = reinterpret_cast<float*>(smem);                          // [S] output tile (padded positions p0 .. p0 + S)
+  float* ys = acc + S;                                                  // [G][win] windowed frames of the current round
+  float2* bufA = reinterpret_cast<float2*>(ys + G * win);               // [G][NP]
+  float2* bufB = bufA + G * NP;                                         // [G][NP]
+  const int tid = threadIdx.x, g = tid / TPF, t = tid % TPF;
+  const int c = blockIdx.x % nct;
+  const int64_t sig = blockIdx.x / nct;
+  const int p0 = c * S; // all positions fit 31 bits (istft_fused_eligible)
+  const int i_hi = min(F - 1, (p0 + S - 1) / hop);
+  const int i_lo = p0 - win + 1 <= 0 ? 0 : (p0 - win + hop) / hop; // ceil((p0 - win + 1) / hop)
+  for (int i = tid; i < S; i += 256) acc[i] = 0.f;
+  float2* A = bufA + g * NP;
+  float2* Bf = bufB + g * NP;
+  const float2* sp = tw + NC;
+  const float scale = 1.0f / (float) (2 * NC);
+  constexpr int NST = (NC >= 512) ? 2 : 1;
+  float2 twr[NST][7];
+  {
+    int Ns = 8;
+#pragma unroll
+    for (int s = 0; s < NST; s++, Ns *= 8) {
+      const int k = t & (Ns - 1), tstep = NC / (Ns * 8);
+#pragma unroll
+      for (int r = 1; r < 8; r++) twr[s][r - 1] = tw[r * k * tstep];
+    }
+  }
+  __syncthreads();
+  for (int i0 = i_lo; i0 <= i_hi; i0 += G) {
+    const int fi = i0 + g;
+    const bool live = fi <= i_hi;
+    if (live) { // the spectrum row of this frame -> shared memory (all nine loads of a thread in flight together)
+      const float2* row = spec + (sig * F + fi) * (int64_t) (NC + 1);
+      float2 x[8];
+#pragma unroll
+      for (int r = 0; r < 8; r++) x[r] = row[t + r * TPF];
+      float2 xl = make_float2(0.f, 0.f);
+      if (t == 0) xl = row[NC];
+      if (t == 0) { x[0].y = 0.f; xl.y = 0.f; } // a real signal's DC and Nyquist bins are real: the C2R convention ignores what is there
+#pragma unroll
+      for (int r = 0; r < 8; r++) Bf[pad(t + r * TPF)] = x[r];
+      if (t == 0) Bf[pad(NC)] = xl;
+    }
+    __syncthreads();
+    float2 v[8];
+    if (live) {
+      // inverse of the real-input split (cf. the forward kernel): with a = X[m] + conj X[NC-m], b = X[m] - conj X[NC-m],
+      // Z[m] = a + i e^{+2 pi i m / fft} b is the spectrum of z[j] = x[2j] + i x[2j+1] scaled by fft (the unnormalised C2R
+      // convention); the inverse transform is taken as conj(FFT(conj Z))
+#pragma unroll
+      for (int r = 0; r < 8; r++) {
+        const int m = t + r * TPF;
+        const float2 xk = Bf[pad(m)];
+        float2 xn = Bf[pad(NC - m)];
+        xn.y = -xn.y;
+        const float2 a = cadd(xk, xn), b = csub(xk, xn);
+        float2 e = sp[m];
+        e.y = -e.y;                               // e^{+2 pi i m / fft}
+        const float2 eb = cmul(e, b);
+        const float2 z = make_float2(a.x - eb.y, a.y + eb.x); // a + i (e b)
+        v[r] = make_float2(z.x, -z.y);
+      }
+      dft8(v);
+#pragma unroll
+      for (int r = 0; r < 8; r++) A[pad(8 * t + r)] = v[r];
+    }
+    __syncthreads(); // also: every thread has read the spectrum row out of Bf before the next stage writes there
+    float2* in = A;
+    float2* outb = Bf;
+    int Ns = 8;
+#pragma unroll
+    for (int s = 0; s < NST; s++, Ns *= 8) {
+      if (live) {
+        const int k = t & (Ns - 1);
+#pragma unroll
+        for (int r = 0; r < 8; r++) v[r] = in[pad(t + r * TPF)];
+#pragma unroll
+        for (int r = 1; r < 8; r++) v[r] = cmul(v[r], twr[s][r - 1]);
+        dft8(v);
+        const int j0 = (t - k) * 8 + k;
+#pragma unroll
+        for (int r = 0; r < 8; r++) outb[pad(j0 + r * Ns)] = v[r];
+      }
+      __syncthreads();
+      float2* sw = in; in = outb; outb = sw;
+    }
+    constexpr int LOG = NC == 128 ? 7 : (NC == 256 ? 8 : (NC == 512 ? 9 : (NC == 1024 ? 10 : 11)));
+    constexpr int TAIL = 1 << (LOG % 3);
+    if (TAIL > 1) {
+      if (live) {
+        constexpr int NB = NC / TAIL;
+        for (int j = t; j < NB; j += TPF) {
+          const int k = j & (Ns - 1);
+          float2 u[4];
+#pragma unroll
+          for (int r = 0; r < TAIL; r++) u[r] = in[pad(j + r * NB)];
+#pragma unroll
+          for (int r = 1; r < TAIL; r++) u[r] = cmul(u[r], tw[r * k]);
+          if (TAIL == 2) dft2(u[0], u[1]);
+          else dft4(u[0], u[1], u[2], u[3]);
+          const int j0 = (j - k) * TAIL + k;
+#pragma unroll
+          for (int r = 0; r < TAIL; r++) outb[pad(j0 + r * Ns)] = u[r];
+        }
+      }
+      __syncthreads();
+      float2* sw = in; in = outb; outb = sw;
+    }
+    // ---- window: x[2m] = Re w[m], x[2m+1] = -Im w[m]; the frame's first `win` samples * window / fft (STFT.hpp:189-193)
+    if (live) {
+      float* y = ys + g * win;
+      for (int m = t; 2 * m < win; m += TPF) {
+        const float2 w = in[pad(m)];
+        const int j = 2 * m;
+        y[j] = w.x * scale * window[j];
+        if (j + 1 < win) y[j + 1] = -w.y * scale * window[j + 1];
+      }
+    }
+    __syncthreads();
+    { // ---- gather the round's frames into the tile, ascending frame order per position
+      const int gl = min(G, i_hi - i0 + 1);
+      const int r0 = i0 * hop; // first position of the round's first frame
+      const int lo = max(p0, r0), hi = min(p0 + S, r0 + (gl - 1) * hop + win);
+      for (int pp = lo + tid; pp < hi; pp += 256) {
+        const int rel = pp - r0; // >= 0
+        const int g_hi = min(gl - 1, rel / hop);
+        const int g_lo = rel - win + 1 <= 0 ? 0 : (rel - win + hop) / hop;
+        float a = acc[pp - p0];
+        for (int gg = g_lo; gg <= g_hi; gg++) a += ys[gg * win + rel - gg * hop];
+        acc[pp - p0] = a;
+      }
+    }
+    __syncthreads();
+  }
+  // ---- normalise and write the owned samples: t = pos - half in [0, n)
+  for (int i = tid; i < S; i += 256) {
+    const int pos = p0 + i, ts = pos - half;
+    if (ts < 0 || ts >= n) continue;
+    const int f_hi = min(F - 1, pos / hop);
+    const int f_lo = pos - win + 1 <= 0 ? 0 : (pos - win + hop) / hop;
+    float nrm = 0.f;
+    for (int f = f_lo; f <= f_hi; f++) {
+      const float w = window[pos - f * hop];
+      nrm = fmaf(w, w, nrm);
+    }
+    const float a = acc[i];
+    out[sig * out_stride + ts] = stream_norm ? (a != 0.f ? a / (nrm > 0.f ? nrm : 1.f) : a) : a / fmaxf(nrm, kEps);
+  }
+}
+
+// true when the fused inverse takes this call (else cuFFT C2R + k_ola)
+bool istft_fused_eligible(const Plan* p, int64_t nsig, int64_t F, int64_t n, int64_t half)
+{
+  const int fft = p->fft;
+  if (fft != 256 && fft != 512 && fft != 1024 && fft != 2048 && fft != 4096) return false;
+  if (p->hop > p->win || nsig <= 0 || F <= 0 || n <= 0 || half < 0) return false;
+  if (n + half >= ((int64_t) 1 << 31) || F >= ((int64_t) 1 << 30)) return false;
+  return getenv("FB200_ISTFT_CUFFT") == nullptr;
+}
+
+template <int NC>
+static int32_t launch_inv_t(Plan* p, const float2* spec, int64_t nsig, int64_t F, int64_t n, float* out, int64_t half, int64_t out_stride,
+                            int stream_norm)
+{
+  constexpr int TPF = NC / 8, G = 256 / TPF, NP = NC + NC / 32 + 1;
+  // positions per CTA: up to 8192 (32 KB of accumulators; 12288 / 6144 / 4096 measured within 3 % of it), at least one hop;
+  // the frames before the range are recomputed
+  static const int s_max = getenv("FB200_ISTFT_S") ? atoi(getenv("FB200_ISTFT_S")) : 8192;
+  int fpb = std::max(1, s_max / p->hop);
+  const int64_t span = n + half; // padded positions that produce output
+  fpb = (int) std::min<int64_t>(fpb, (span + p->hop - 1) / p->hop);
+  const int S = fpb * p->hop;
+  const int nct = (int) ((span + S - 1) / S);
+  const size_t smem = sizeof(float) * (size_t) (S + G * p->win) + 2 * sizeof(float2) * (size_t) (G * NP);
+  if (smem > 200 * 1024) return FB200_ERR_UNSUPPORTED;
+  if ((int64_t) nct * nsig >= ((int64_t) 1 << 31)) return FB200_ERR_UNSUPPORTED;
+  FB_CUDA(p, cudaFuncSetAttribute(k_istft_fused<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); // per device
+  k_istft_fused<NC><<<(unsigned) (nct * nsig), 256, smem, p->stream>>>(spec, p->window.as<float>(), p->twiddle.as<float2>(), p->win, p->hop, (int) half, n,
+                                                                       (int) F, fpb, nct, out, out_stride, stream_norm);
+  p->launches++;
+  FB_CUDA(p, cudaGetLastError());
+  return FB200_OK;
+}
+
+static int32_t ensure_twiddles(Plan* p)
+{
+  const int NC = p->fft / 2;
+  if (!p->twiddle.p) {
+    FB_CUDA(p, p->twiddle.ensure(sizeof(float2) * (size_t) (2 * NC + 1)));
+    k_stft_twiddles<<<(NC + 256) / 256, 256, 0, p->stream>>>(p->twiddle.as<float2>(), NC);
+    p->launches++;
+  }
+  return FB200_OK;
+}
+
+int32_t launch_istft_fused(Plan* p, const float2* spec, int64_t nsig, int64_t F, int64_t n, float* out, int64_t half, int64_t out_stride,
+                           int stream_norm)
+{
+  FB_TRY(ensure_twiddles(p));
+  switch (p->fft / 2) {
+  case 128: return launch_inv_t<128>(p, spec, nsig, F, n, out, half, out_stride, stream_norm);
+  case 256: return launch_inv_t<256>(p, spec, nsig, F, n, out, half, out_stride, stream_norm);
+  case 512: return launch_inv_t<512>(p, spec, nsig, F, n, out, half, out_stride, stream_norm);
+  case 1024: return launch_inv_t<1024>(p, spec, nsig, F, n, out, half, out_stride, stream_norm);
+  default: return launch_inv_t<2048>(p, spec, nsig, F, n, out, half, out_stride, stream_norm);
+  }
+}
+
 static int32_t make_audio_tensor_map(Plan* p, CUtensorMap* tmap, const float* audio, int64_t n, int64_t batch)
 {
   typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -292,11 +519,7 @@ int32_t launch_stft_fused(Plan* p, const float* audio, int64_t batch, int64_t n,
                           float2* spec, int64_t half, int hop)
 {
   const int NC = p->fft / 2;
-  if (!p->twiddle.p) {
-    FB_CUDA(p, p->twiddle.ensure(sizeof(float2) * (size_t) (2 * NC + 1)));
-    k_stft_twiddles<<<(NC + 256) / 256, 256, 0, p->stream>>>(p->twiddle.as<float2>(), NC);
-    p->launches++;
-  }
+  FB_TRY(ensure_twiddles(p));
   alignas(64) CUtensorMap amap;
   FB_TRY(make_audio_tensor_map(p, &amap, audio, n, batch));
   switch (NC) {

@@ -503,3 +503,34 @@ def test_fused_stft_kernel_vs_oracle_and_cufft_path(fb, oracle, n, win, fft, hop
         assert rel(spec[b], S) < 2e-6 and rel(mag[b], np.abs(S)) < 2e-6, (rel(spec[b], S), rel(mag[b], np.abs(S)))
         assert rel(spec[b], spec_c[b]) < 2e-6
     assert np.all(spec[..., 0].imag == 0) and np.all(spec[..., -1].imag == 0)  # FFT.hpp:99-101
+
+
+@pytest.mark.parametrize("n,win,fft,hop", [(8192, 256, 256, 64), (6001, 400, 512, 100), (130816, 1024, 1024, 256),
+                                           (40000, 2048, 2048, 512), (70000, 4096, 4096, 1024), (12000, 1000, 4096, 250),
+                                           (4096, 512, 512, 512), (300, 256, 256, 128)])
+def test_fused_istft_kernel_vs_oracle_and_cufft_path(fb, oracle, n, win, fft, hop):
+    """The fused inverse (spectrum rows -> shared-memory inverse FFT -> window -> overlap-add -> normalise, one kernel:
+    kernels_stft_fused.cu) against the fp64 oracle's ISTFT (STFT.hpp:178-199) and against the cuFFT C2R + k_ola pipeline it
+    replaces (FB200_ISTFT_CUFFT=1 forces the fallback); arbitrary (non-analysis) spectra, so the overlap-add really sums."""
+    rng = np.random.default_rng(n + fft)
+    F = n // hop + 1
+    B = fft // 2 + 1
+    S = (rng.standard_normal((3, F, B)) + 1j * rng.standard_normal((3, F, B))).astype(np.complex64)
+    S[..., 0] = S[..., 0].real
+    S[..., -1] = S[..., -1].real
+    with fb.Plan(win=win, hop=hop, fft=fft) as plan:
+        y = plan.istft(S, n)  # the first call also builds the plan's twiddle table
+        y2 = plan.istft(S, n)
+        launches_fused = plan.stats()["launches_total"]
+        os.environ["FB200_ISTFT_CUFFT"] = "1"
+        try:
+            y_c = plan.istft(S, n)
+            launches_cufft = plan.stats()["launches_total"]
+        finally:
+            del os.environ["FB200_ISTFT_CUFFT"]
+    assert launches_fused < launches_cufft  # one kernel instead of cuFFT C2R + overlap-add
+    assert np.array_equal(y, y2)  # fixed summation order
+    for b in range(3):
+        ref = oracle.istft(S[b].astype(np.complex128), win, fft, hop, n)
+        assert rel(y[b], ref) < 3e-6, rel(y[b], ref)
+        assert rel(y[b], y_c[b]) < 3e-6
