@@ -911,14 +911,22 @@ int32_t fb200_bufnmf(fb200_plan* p, const fb200_bufnmf_args* a)
   if (resynth) {
     int64_t wave = std::max<int64_t>(1, wave_size(p, F, batch * K, 1) / K);
     wave = std::min(wave, batch);
-    FB_CUDA(p, p->cspec.ensure(sizeof(float2) * (size_t) (wave * K * F * B)));
+    // fused path: the masks are applied while the inverse kernel loads its spectrum rows, the masked spectra are never
+    // written; else mask kernel -> cuFFT C2R -> overlap-add
+    const bool fused_inv = istft_fused_eligible(p, wave * K, F, n, p->win / 2);
+    if (fused_inv) FB_CUDA(p, p->frames.ensure(sizeof(float) * (size_t) (wave * F * B)));
+    else FB_CUDA(p, p->cspec.ensure(sizeof(float2) * (size_t) (wave * K * F * B)));
     float* dst_all = a->resynth_out;
     if (host) { FB_CUDA(p, p->stage.ensure(sizeof(float) * (size_t) (wave * K * n))); }
     for (int64_t b0 = 0; b0 < batch; b0 += wave) {
       int64_t nb = std::min(wave, batch - b0);
-      launch_mask(p, d, spec_all, b0, nb, p->cspec.as<float2>());
       float* dst = host ? p->stage.as<float>() : dst_all + b0 * K * n;
-      FB_TRY(run_istft(p, p->cspec.as<float2>(), nb * K, F, n, dst, p->win / 2));
+      int32_t stf = fused_inv ? launch_masked_istft_fused(p, d, spec_all, b0, nb, n, dst, p->win / 2, p->frames.as<float>()) : FB200_ERR_UNSUPPORTED;
+      if (stf == FB200_ERR_UNSUPPORTED) {
+        FB_CUDA(p, p->cspec.ensure(sizeof(float2) * (size_t) (wave * K * F * B)));
+        launch_mask(p, d, spec_all, b0, nb, p->cspec.as<float2>());
+        FB_TRY(run_istft(p, p->cspec.as<float2>(), nb * K, F, n, dst, p->win / 2));
+      } else if (stf < 0) return stf;
       if (host) {
         FB_CUDA(p, cudaMemcpyAsync(a->resynth_out + b0 * K * n, dst, sizeof(float) * (size_t) (nb * K * n), cudaMemcpyDeviceToHost, p->stream));
         FB_CUDA(p, cudaStreamSynchronize(p->stream)); // staging buffer is reused by the next wave

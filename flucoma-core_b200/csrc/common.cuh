@@ -201,6 +201,8 @@ void launch_ola(Plan* p, const float* y, int64_t nsig, int64_t F, int64_t n, flo
 // kernels_stft_fused.cu -----------------------------------------------------------------------------------------
 bool stft_fused_eligible(const Plan* p, const float* audio, int64_t n, int64_t batch, int hop);
 bool istft_fused_eligible(const Plan* p, int64_t nsig, int64_t F, int64_t n, int64_t half);
+int32_t launch_masked_istft_fused(Plan* p, const NmfDev& d, const float2* spec, int64_t b0, int64_t nb, int64_t n, float* out, int64_t half,
+                                  float* scratch);
 int32_t launch_istft_fused(Plan* p, const float2* spec, int64_t nsig, int64_t F, int64_t n, float* out, int64_t half, int64_t out_stride,
                            int stream_norm);
 // audio [batch][n] -> V[batch][Fp][Bp] magnitudes (may be null) and/or spec [batch][F][B] (may be null); one kernel

@@ -240,10 +240,48 @@ __global__ void __launch_bounds__(256, 3) k_stft_fused(const __grid_constant__ C
 // windowed samples of the round's frames are parked in shared memory and gathered, frame by frame in ascending order,
 // into the CTA's output tile.  The cuFFT pipeline this replaces wrote and re-read an fft-sample frame per spectrum row
 // (8 KB at fft 1024) and needed a cuFFT plan per (frames x signals) shape -- tens of milliseconds on first use.
-template <int NC>
+// MASK: the rows are not read from `spec` as they are but as component k of buffer b of a BufNMF resynthesis,
+//   X_k[f][b] = X[f][b] * min(1, H[f][k] W[k][b] / max(sum_j H[f][j] W[j][b], eps))      (NMF::estimate + RatioMask, exponent 1)
+// with signal index = buffer * K + k; 1 / max(sum, eps) comes precomputed per (frame, bin) from k_inv_estimate, so the masked
+// spectra (K complex spectrograms per buffer) are never written.
+struct InvMask {
+  const float* W;    // [buffers | 1][KP][Bp]
+  const float* H;    // [buffers][Fp][KP]
+  const float* invV; // [nb][F][B], buffers b0 .. b0 + nb
+  int64_t b0;
+  int K, KP, Bp, Fp, shared_w;
+};
+
+// invV[bl][f][bin] = 1 / max(sum_k H[f][k] W[k][bin], eps), the same fmaf chain as k_mask
+template <int KMAX>
+__global__ void __launch_bounds__(256) k_inv_estimate(InvMask mk, int F, int B, float* __restrict__ invV)
+{
+  extern __shared__ float hs8[]; // [8][KP]
+  const int KP = mk.KP, K = mk.K;
+  const int64_t bl = blockIdx.y, buf = mk.b0 + bl;
+  const int f0 = blockIdx.x * 8;
+  const float* __restrict__ W = mk.W + (mk.shared_w ? (int64_t) 0 : buf * KP * mk.Bp);
+  const float* __restrict__ H = mk.H + (buf * mk.Fp + f0) * KP;
+  const int nf = min(8, F - f0);
+  for (int e = threadIdx.x; e < 8 * KP; e += 256) hs8[e] = e < nf * KP ? H[e] : 0.f;
+  __syncthreads();
+  for (int bin = threadIdx.x; bin < B; bin += 256) {
+    float w[KMAX];
+#pragma unroll
+    for (int k = 0; k < KMAX; k++) w[k] = k < K ? W[(int64_t) k * mk.Bp + bin] : 0.f;
+    for (int i = 0; i < nf; i++) {
+      float v = 0.f;
+#pragma unroll
+      for (int k = 0; k < KMAX; k++) v = fmaf(hs8[i * KP + (k < KP ? k : 0)], w[k], v);
+      invV[(bl * F + f0 + i) * B + bin] = 1.0f / fmaxf(v, kEps);
+    }
+  }
+}
+
+template <int NC, bool MASK>
 __global__ void __launch_bounds__(256, 2) k_istft_fused(const float2* __restrict__ spec, const float* __restrict__ window,
                                                      const float2* __restrict__ tw, int win, int hop, int half, int64_t n, int F, int fpb,
-                                                     int nct, float* __restrict__ out, int64_t out_stride, int stream_norm)
+                                                     int nct, float* __restrict__ out, int64_t out_stride, int stream_norm, InvMask mk)
 {
   constexpr int TPF = NC / 8, G = 256 / TPF, NP = NC + NC / 32 + 1;
   extern __shared__ __align__(128) uint8_t smem[];
@@ -278,13 +316,34 @@ __global__ void __launch_bounds__(256, 2) k_istft_fused(const float2* __restrict
   for (int i0 = i_lo; i0 <= i_hi; i0 += G) {
     const int fi = i0 + g;
     const bool live = fi <= i_hi;
-    if (live) { // the spectrum row of this frame -> shared memory (all nine loads of a thread in flight together)
-      const float2* row = spec + (sig * F + fi) * (int64_t) (NC + 1);
+    if (live) { // the spectrum row of this frame -> shared memory (all loads of a thread in flight together)
       float2 x[8];
-#pragma unroll
-      for (int r = 0; r < 8; r++) x[r] = row[t + r * TPF];
       float2 xl = make_float2(0.f, 0.f);
-      if (t == 0) xl = row[NC];
+      if constexpr (MASK) {
+        const int64_t bl = sig / mk.K, buf = mk.b0 + bl;
+        const int k = (int) (sig - bl * mk.K);
+        const float2* row = spec + (buf * F + fi) * (int64_t) (NC + 1);
+        const float* wrow = mk.W + (mk.shared_w ? (int64_t) 0 : buf * mk.KP * mk.Bp) + (int64_t) k * mk.Bp;
+        const float* irow = mk.invV + (bl * F + fi) * (int64_t) (NC + 1);
+        const float h = mk.H[(buf * mk.Fp + fi) * mk.KP + k];
+        float wv[8], iv[8];
+#pragma unroll
+        for (int r = 0; r < 8; r++) { x[r] = row[t + r * TPF]; wv[r] = wrow[t + r * TPF]; iv[r] = irow[t + r * TPF]; }
+        float wl = 0.f, il = 0.f;
+        if (t == 0) { xl = row[NC]; wl = wrow[NC]; il = irow[NC]; }
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+          const float m = fminf(1.0f, h * wv[r] * iv[r]);
+          x[r] = make_float2(x[r].x * m, x[r].y * m);
+        }
+        const float ml = fminf(1.0f, h * wl * il);
+        xl = make_float2(xl.x * ml, xl.y * ml);
+      } else {
+        const float2* row = spec + (sig * F + fi) * (int64_t) (NC + 1);
+#pragma unroll
+        for (int r = 0; r < 8; r++) x[r] = row[t + r * TPF];
+        if (t == 0) xl = row[NC];
+      }
       if (t == 0) { x[0].y = 0.f; xl.y = 0.f; } // a real signal's DC and Nyquist bins are real: the C2R convention ignores what is there
 #pragma unroll
       for (int r = 0; r < 8; r++) Bf[pad(t + r * TPF)] = x[r];
@@ -409,7 +468,7 @@ bool istft_fused_eligible(const Plan* p, int64_t nsig, int64_t F, int64_t n, int
 
 template <int NC>
 static int32_t launch_inv_t(Plan* p, const float2* spec, int64_t nsig, int64_t F, int64_t n, float* out, int64_t half, int64_t out_stride,
-                            int stream_norm)
+                            int stream_norm, const InvMask* mk)
 {
   constexpr int TPF = NC / 8, G = 256 / TPF, NP = NC + NC / 32 + 1;
   // positions per CTA: up to 8192 (32 KB of accumulators; 12288 / 6144 / 4096 measured within 3 % of it), at least one hop;
@@ -423,9 +482,15 @@ static int32_t launch_inv_t(Plan* p, const float2* spec, int64_t nsig, int64_t F
   const size_t smem = sizeof(float) * (size_t) (S + G * p->win) + 2 * sizeof(float2) * (size_t) (G * NP);
   if (smem > 200 * 1024) return FB200_ERR_UNSUPPORTED;
   if ((int64_t) nct * nsig >= ((int64_t) 1 << 31)) return FB200_ERR_UNSUPPORTED;
-  FB_CUDA(p, cudaFuncSetAttribute(k_istft_fused<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); // per device
-  k_istft_fused<NC><<<(unsigned) (nct * nsig), 256, smem, p->stream>>>(spec, p->window.as<float>(), p->twiddle.as<float2>(), p->win, p->hop, (int) half, n,
-                                                                       (int) F, fpb, nct, out, out_stride, stream_norm);
+  if (mk) {
+    FB_CUDA(p, cudaFuncSetAttribute(k_istft_fused<NC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); // per device
+    k_istft_fused<NC, true><<<(unsigned) (nct * nsig), 256, smem, p->stream>>>(spec, p->window.as<float>(), p->twiddle.as<float2>(), p->win, p->hop,
+                                                                               (int) half, n, (int) F, fpb, nct, out, out_stride, stream_norm, *mk);
+  } else {
+    FB_CUDA(p, cudaFuncSetAttribute(k_istft_fused<NC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); // per device
+    k_istft_fused<NC, false><<<(unsigned) (nct * nsig), 256, smem, p->stream>>>(spec, p->window.as<float>(), p->twiddle.as<float2>(), p->win, p->hop,
+                                                                                (int) half, n, (int) F, fpb, nct, out, out_stride, stream_norm, InvMask{});
+  }
   p->launches++;
   FB_CUDA(p, cudaGetLastError());
   return FB200_OK;
@@ -442,17 +507,42 @@ static int32_t ensure_twiddles(Plan* p)
   return FB200_OK;
 }
 
-int32_t launch_istft_fused(Plan* p, const float2* spec, int64_t nsig, int64_t F, int64_t n, float* out, int64_t half, int64_t out_stride,
-                           int stream_norm)
+static int32_t launch_inv(Plan* p, const float2* spec, int64_t nsig, int64_t F, int64_t n, float* out, int64_t half, int64_t out_stride,
+                          int stream_norm, const InvMask* mk)
 {
   FB_TRY(ensure_twiddles(p));
   switch (p->fft / 2) {
-  case 128: return launch_inv_t<128>(p, spec, nsig, F, n, out, half, out_stride, stream_norm);
-  case 256: return launch_inv_t<256>(p, spec, nsig, F, n, out, half, out_stride, stream_norm);
-  case 512: return launch_inv_t<512>(p, spec, nsig, F, n, out, half, out_stride, stream_norm);
-  case 1024: return launch_inv_t<1024>(p, spec, nsig, F, n, out, half, out_stride, stream_norm);
-  default: return launch_inv_t<2048>(p, spec, nsig, F, n, out, half, out_stride, stream_norm);
+  case 128: return launch_inv_t<128>(p, spec, nsig, F, n, out, half, out_stride, stream_norm, mk);
+  case 256: return launch_inv_t<256>(p, spec, nsig, F, n, out, half, out_stride, stream_norm, mk);
+  case 512: return launch_inv_t<512>(p, spec, nsig, F, n, out, half, out_stride, stream_norm, mk);
+  case 1024: return launch_inv_t<1024>(p, spec, nsig, F, n, out, half, out_stride, stream_norm, mk);
+  default: return launch_inv_t<2048>(p, spec, nsig, F, n, out, half, out_stride, stream_norm, mk);
   }
+}
+
+int32_t launch_istft_fused(Plan* p, const float2* spec, int64_t nsig, int64_t F, int64_t n, float* out, int64_t half, int64_t out_stride,
+                           int stream_norm)
+{
+  return launch_inv(p, spec, nsig, F, n, out, half, out_stride, stream_norm, nullptr);
+}
+
+// BufNMF resynthesis of buffers [b0, b0 + nb): rank masked spectra per buffer -> out[(bl * K + k) * n ..], without writing them.
+// spec = the unmasked spectra of ALL buffers [batch][F][B]; scratch = nb * F * B floats.
+int32_t launch_masked_istft_fused(Plan* p, const NmfDev& d, const float2* spec, int64_t b0, int64_t nb, int64_t n, float* out, int64_t half,
+                                  float* scratch)
+{
+  InvMask mk{};
+  mk.W = d.W; mk.H = d.H; mk.invV = scratch; mk.b0 = b0;
+  mk.K = d.K; mk.KP = d.KP; mk.Bp = d.Bp; mk.Fp = d.Fp; mk.shared_w = d.shared_w;
+  dim3 grid((unsigned) ((d.F + 7) / 8), (unsigned) nb);
+  const size_t sm = sizeof(float) * 8 * d.KP;
+  if (d.KP <= 4) k_inv_estimate<4><<<grid, 256, sm, p->stream>>>(mk, d.F, d.B, scratch);
+  else if (d.KP <= 8) k_inv_estimate<8><<<grid, 256, sm, p->stream>>>(mk, d.F, d.B, scratch);
+  else if (d.KP <= 16) k_inv_estimate<16><<<grid, 256, sm, p->stream>>>(mk, d.F, d.B, scratch);
+  else if (d.KP <= 32) k_inv_estimate<32><<<grid, 256, sm, p->stream>>>(mk, d.F, d.B, scratch);
+  else k_inv_estimate<64><<<grid, 256, sm, p->stream>>>(mk, d.F, d.B, scratch);
+  p->launches++;
+  return launch_inv(p, spec, nb * d.K, d.F, n, out, half, n, 0, &mk);
 }
 
 static int32_t make_audio_tensor_map(Plan* p, CUtensorMap* tmap, const float* audio, int64_t n, int64_t batch)

@@ -534,3 +534,20 @@ def test_fused_istft_kernel_vs_oracle_and_cufft_path(fb, oracle, n, win, fft, ho
         ref = oracle.istft(S[b].astype(np.complex128), win, fft, hop, n)
         assert rel(y[b], ref) < 3e-6, rel(y[b], ref)
         assert rel(y[b], y_c[b]) < 3e-6
+
+
+def test_bufnmf_resynthesis_fused_mask_and_inverse_vs_cufft_pipeline(fb, synth):
+    """BufNMF resynthesis applies the ratio masks while the fused inverse kernel loads its spectrum rows (the masked spectra
+    are never written); FB200_ISTFT_CUFFT=1 runs mask kernel -> cuFFT C2R -> overlap-add instead.  Same masks bit for bit,
+    inverse transforms within fp32 rounding; the components add up to the input either way (the masks sum to one)."""
+    a = np.stack([synth(400 + b, 20000) for b in range(5)])
+    with fb.Plan(win=512, hop=128, fft=512) as plan:
+        r = plan.bufnmf(a, 6, 15, seeds=np.arange(5), resynth=True)
+        os.environ["FB200_ISTFT_CUFFT"] = "1"
+        try:
+            rc = plan.bufnmf(a, 6, 15, seeds=np.arange(5), resynth=True)
+        finally:
+            del os.environ["FB200_ISTFT_CUFFT"]
+    assert np.array_equal(r["bases"], rc["bases"]) and np.array_equal(r["acts"], rc["acts"])
+    assert rel(r["resynth"], rc["resynth"]) < 3e-6
+    assert np.abs(r["resynth"].sum(axis=1) - a).max() < 1e-4
