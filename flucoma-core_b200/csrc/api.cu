@@ -834,12 +834,13 @@ int32_t fb200_bufnmf(fb200_plan* p, const fb200_bufnmf_args* a)
   // A call whose audio sits in host memory and that runs on the resident tensor-core engine is split: the first
   // sm_count buffers (one per CTA: exactly one round of the persistent kernel) are uploaded, transformed and started,
   // and the upload of the rest runs under that launch instead of in front of everything (config 2: 536 MB = 9.7 ms of
-  // PCIe time, of which 1.4 ms stay exposed).  The number of rounds is unchanged: 1 + ceil((batch - sm) / sm).
+  // PCIe time, of which 1.4 ms stay exposed).  The number of rounds is unchanged for every batch > sm: 1 + ceil((batch - sm) / sm)
+  // = ceil(batch / sm).
   const int be = p->cfg.backend;
   const bool async_or_none = !a->progress || a->progress_stride == FB200_PROGRESS_ASYNC;
   const bool can_tc1 = (be == FB200_BACKEND_AUTO || be == FB200_BACKEND_TCGEN05) && tc_eligible(d);
   const bool can_tc2 = !can_tc1 && be != FB200_BACKEND_SIMT && tcs_eligible(d) && !fix_w && !a->progress; // the streamed engine has no in-kernel progress
-  const bool split = host && needs_analysis && a->iterations > 0 && async_or_none && batch >= 3 * (int64_t) p->sm_count &&
+  const bool split = host && needs_analysis && a->iterations > 0 && async_or_none && batch > (int64_t) p->sm_count &&
                      (can_tc1 || can_tc2);
   const float* U_h = nullptr;
   int32_t st = FB200_OK;
