@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(256) k_inv_estimate(InvMask mk, int F, int B, 
 }
 
 template <int NC, bool MASK>
-__global__ void __launch_bounds__(256, 2) k_istft_fused(const float2* __restrict__ spec, const float* __restrict__ window,
+__global__ void __launch_bounds__(256, 3) k_istft_fused(const float2* __restrict__ spec, const float* __restrict__ window,
                                                      const float2* __restrict__ tw, int win, int hop, int half, int64_t n, int F, int fpb,
                                                      int nct, float* __restrict__ out, int64_t out_stride, int stream_norm, InvMask mk)
 {
@@ -471,9 +471,10 @@ static int32_t launch_inv_t(Plan* p, const float2* spec, int64_t nsig, int64_t F
                             int stream_norm, const InvMask* mk)
 {
   constexpr int TPF = NC / 8, G = 256 / TPF, NP = NC + NC / 32 + 1;
-  // positions per CTA: up to 8192 (32 KB of accumulators; 12288 / 6144 / 4096 measured within 3 % of it), at least one hop;
+  // positions per CTA: up to 6144 (24 KB of accumulators: with the 80 registers of the kernel three CTAs share an SM; 8192 with
+  // two CTAs measured 12 % slower), at least one hop;
   // the frames before the range are recomputed
-  static const int s_max = getenv("FB200_ISTFT_S") ? atoi(getenv("FB200_ISTFT_S")) : 8192;
+  static const int s_max = getenv("FB200_ISTFT_S") ? atoi(getenv("FB200_ISTFT_S")) : 6144;
   int fpb = std::max(1, s_max / p->hop);
   const int64_t span = n + half; // padded positions that produce output
   fpb = (int) std::min<int64_t>(fpb, (span + p->hop - 1) / p->hop);
