@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(256, 3) k_stft_fused(const __grid_constant__ C
         float2 X = cadd(a, tb);
         if (k == 0 || k == NC) X.y = 0.f; // exact by construction up to rounding; FFT.hpp:99-101 leaves them at zero
         if (srow) srow[k] = X;
-        if (vrow) vrow[k] = hypotf(X.x, X.y);
+        if (vrow) vrow[k] = sqrtf(fmaf(X.x, X.x, X.y * X.y)); // hypotf's range scaling is not needed for audio magnitudes and cost 9 % of the kernel
       }
     }
     __syncthreads(); // the buffers are reused by the next round
