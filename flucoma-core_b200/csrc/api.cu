@@ -191,7 +191,7 @@ int32_t alloc_nmf(Plan* p, NmfDev& d)
   FB_CUDA(p, p->H.ensure(sizeof(float) * (size_t) d.batch * d.Fp * d.KP));
   FB_CUDA(p, p->hden.ensure(sizeof(float) * (size_t) d.batch * d.KP));
   d.V = p->V.as<float>(); d.W = p->W.as<float>(); d.H = p->H.as<float>(); d.hden = p->hden.as<float>();
-  d.wnum_part = nullptr; d.wden_part = nullptr;
+  d.wnum_part = nullptr; d.wden_part = nullptr; d.ticket = nullptr;
   return FB200_OK;
 }
 
@@ -200,6 +200,11 @@ int32_t alloc_partials(Plan* p, NmfDev& d)
   FB_CUDA(p, p->wnum_part.ensure(sizeof(float) * (size_t) d.batch * d.ctas_per_buf * d.KP * d.Bp));
   FB_CUDA(p, p->wden_part.ensure(sizeof(float) * (size_t) d.batch * d.ctas_per_buf * d.KP));
   d.wnum_part = p->wnum_part.as<float>(); d.wden_part = p->wden_part.as<float>();
+  if (p->ticket.cap < sizeof(int) * (size_t) d.batch) { // grows: (re)zero once; the kernels leave it zero
+    FB_CUDA(p, p->ticket.ensure(sizeof(int) * (size_t) d.batch));
+    FB_CUDA(p, cudaMemsetAsync(p->ticket.p, 0, sizeof(int) * (size_t) d.batch, p->stream));
+  }
+  d.ticket = p->ticket.as<int>();
   return FB200_OK;
 }
 
@@ -266,15 +271,16 @@ int32_t draw_frame_h0(Plan* p, int64_t seed, int64_t frames, int64_t K, const fl
 void simt_run_iters(Plan* p, NmfDev& d, int n, bool upd_w, bool upd_h)
 {
   if (upd_w && upd_h) {
+    // (the W finalisation runs inside the tile launch, in the last CTA of every buffer, when the plan has a ticket array)
     simt_launch_tile(p, d, 0, 1, 1); // W-numerator of the first iteration
-    simt_launch_w_finalize(p, d);
+    if (!d.ticket) simt_launch_w_finalize(p, d);
     for (int it = 1; it < n; it++) {
       simt_launch_tile(p, d, 1, 1, 1); // H-update of iteration `it` fused with the W-numerator of `it+1`
-      simt_launch_w_finalize(p, d);
+      if (!d.ticket) simt_launch_w_finalize(p, d);
     }
     simt_launch_tile(p, d, 1, 0, 1); // H-update of the last iteration
   } else if (upd_w) {
-    for (int it = 0; it < n; it++) { simt_launch_tile(p, d, 0, 1, 1); simt_launch_w_finalize(p, d); }
+    for (int it = 0; it < n; it++) { simt_launch_tile(p, d, 0, 1, 1); if (!d.ticket) simt_launch_w_finalize(p, d); }
   } else {
     for (int it = 0; it < n; it++) simt_launch_tile(p, d, 1, 0, 1);
   }
@@ -536,7 +542,7 @@ void fb200_plan_destroy(fb200_plan* p)
   if (p->stream) cudaStreamSynchronize(p->stream);
   for (auto& kv : p->fft_plans) cufftDestroy(kv.second);
   DevBuf* bufs[] = {&p->window, &p->audio, &p->stage, &p->frames, &p->spec, &p->cspec, &p->V, &p->W, &p->H, &p->hden,
-                    &p->wnum_part, &p->wden_part, &p->rnd, &p->seeds, &p->scale, &p->out_a, &p->out_b, &p->ctrl_dev, &p->wop_buf, &p->hop_buf, &p->twiddle, &p->x0, &p->x1, &p->x2, &p->x3, &p->x4, &p->x5};
+                    &p->wnum_part, &p->wden_part, &p->ticket, &p->rnd, &p->seeds, &p->scale, &p->out_a, &p->out_b, &p->ctrl_dev, &p->wop_buf, &p->hop_buf, &p->twiddle, &p->x0, &p->x1, &p->x2, &p->x3, &p->x4, &p->x5};
   for (auto* b : bufs) b->release();
   p->pin_a.release(); p->pin_b.release(); p->ctrl.release();
   if (p->ev_async) cudaEventDestroy(p->ev_async);

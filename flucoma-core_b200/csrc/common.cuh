@@ -83,6 +83,7 @@ struct NmfDev {
   float* hden;      // [batch][KP]       sum_b W[k][b]      (NMF.hpp:169)
   float* wnum_part; // [batch][ctas][KP][Bp] per-CTA partials of (V/WH) H^T  (NMF.hpp:159)
   float* wden_part; // [batch][ctas][KP]     per-CTA partials of sum_f H[f][k] (NMF.hpp:160)
+  int* ticket;      // [batch] zero between launches: the last tile CTA of a buffer runs the W finalisation (null: separate kernel)
   int batch, F, B, K;
   int Fp, Bp, KP;
   int ctas_per_buf;   // grid.x of the tile kernel
@@ -117,7 +118,7 @@ struct Plan {
   DevBuf frames;   // float [wave*F][fft]  cuFFT real side
   DevBuf spec;     // float2 [batch][F][B] (kept when resynthesis is requested) or [wave][F][B]
   DevBuf cspec;    // float2 [wave][K][F][B] masked component spectra
-  DevBuf V, W, H, hden, wnum_part, wden_part, rnd, seeds, scale, out_a, out_b;
+  DevBuf V, W, H, hden, wnum_part, wden_part, ticket, rnd, seeds, scale, out_a, out_b;
   HostBuf pin_a, pin_b;
   HostBuf ctrl;    // pinned read-back of the progress counters of the asynchronous progress mode
   DevBuf ctrl_dev; // device control words: [0] cancel request, [1 + cta] finished (buffer, pass) units

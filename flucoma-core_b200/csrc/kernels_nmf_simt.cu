@@ -97,6 +97,60 @@ __device__ __forceinline__ void ratio_tile(const float* __restrict__ Vt, int Bp,
   }
 }
 
+// W <- W * wnum / max(wden, eps); if max(W) > eps normalise each W row (Eigen column) to unit L2; hden = sum_b W.
+// NMF.hpp:161-162, :169.  One CTA per buffer, one warp per component row.  The partials come from other CTAs (ld.cg: an L1
+// line of an earlier iteration may still be around when this runs inside the tile kernel).
+template <int KP>
+__device__ __forceinline__ void w_finalize_body(const NmfDev& d, int buf)
+{
+  __shared__ float wden[KP];
+  __shared__ float inv_norm[KP];
+  __shared__ float wmax[8];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nc = d.ctas_per_buf, Bp = d.Bp;
+  float* __restrict__ W = d.W + (int64_t) buf * KP * Bp;
+  const float* __restrict__ part = d.wnum_part + (int64_t) buf * nc * KP * Bp;
+  if (tid < KP) {
+    float s = 0.f;
+    for (int c = 0; c < nc; c++) s += __ldcg(d.wden_part + ((int64_t) buf * nc + c) * KP + tid);
+    wden[tid] = fmaxf(s, kEps);
+  }
+  __syncthreads();
+  float mx = 0.f;
+  for (int k = warp; k < KP; k += 8) {
+    float ss = 0.f;
+    float den = wden[k];
+    for (int b = lane; b < Bp; b += 32) {
+      float wn = 0.f;
+      for (int c = 0; c < nc; c++) wn += __ldcg(part + ((int64_t) c * KP + k) * Bp + b);
+      float w = W[(int64_t) k * Bp + b] * wn / den;
+      W[(int64_t) k * Bp + b] = w;
+      ss = fmaf(w, w, ss);
+      mx = fmaxf(mx, w);
+    }
+    for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    if (lane == 0) inv_norm[k] = ss > 0.f ? 1.0f / sqrtf(ss) : 0.f;
+  }
+  for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (lane == 0) wmax[warp] = mx;
+  __syncthreads();
+  float gmax = wmax[0];
+#pragma unroll
+  for (int i = 1; i < 8; i++) gmax = fmaxf(gmax, wmax[i]);
+  const bool norm = gmax > kEps;
+  for (int k = warp; k < KP; k += 8) {
+    float sc = norm ? inv_norm[k] : 1.0f;
+    float sum = 0.f;
+    for (int b = lane; b < Bp; b += 32) {
+      float w = W[(int64_t) k * Bp + b];
+      if (norm) { w *= sc; W[(int64_t) k * Bp + b] = w; }
+      sum += w;
+    }
+    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0) d.hden[(int64_t) buf * KP + k] = sum;
+  }
+}
+
 template <int KP>
 __global__ void __launch_bounds__(NT) k_nmf_tile(NmfDev d, int do_h, int do_w, int h_iters)
 {
@@ -280,60 +334,31 @@ __global__ void __launch_bounds__(NT) k_nmf_tile(NmfDev d, int do_h, int do_w, i
       if (c + 1 < nchunks) store_w_chunk<KP>(Wc + ((c + 1) & 1) * KP * WCS, tid, wr);
       __syncthreads();
     }
+    // The CTA that finishes last for this buffer reduces the partials and updates W (fixed summation order, whoever runs it):
+    // one launch per iteration instead of two -- a single-buffer call is launch-bound (config 1: 101 + 100 launches).
+    if (d.ticket) {
+      __shared__ int s_last;
+      __threadfence(); // this CTA's partials are visible device-wide before its ticket is
+      __syncthreads();
+      if (tid == 0) {
+        const int tk = atomicAdd(d.ticket + buf, 1);
+        s_last = tk == (int) gridDim.x - 1;
+        if (s_last) d.ticket[buf] = 0; // ready for the next launch
+      }
+      __syncthreads();
+      if (s_last) {
+        __threadfence();
+        w_finalize_body<KP>(d, buf);
+      }
+    }
   }
 }
 
-// W <- W * wnum / max(wden, eps); if max(W) > eps normalise each W row (Eigen column) to unit L2; hden = sum_b W.
-// NMF.hpp:161-162, :169.  One CTA per buffer, one warp per component row.
+// stand-alone form of the W finalisation (kept for callers that have no ticket array)
 template <int KP>
 __global__ void __launch_bounds__(NT) k_w_finalize(NmfDev d)
 {
-  __shared__ float wden[KP];
-  __shared__ float inv_norm[KP];
-  __shared__ float wmax[8];
-  const int buf = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int nc = d.ctas_per_buf, Bp = d.Bp;
-  float* __restrict__ W = d.W + (int64_t) buf * KP * Bp;
-  const float* __restrict__ part = d.wnum_part + (int64_t) buf * nc * KP * Bp;
-  if (tid < KP) {
-    float s = 0.f;
-    for (int c = 0; c < nc; c++) s += d.wden_part[((int64_t) buf * nc + c) * KP + tid];
-    wden[tid] = fmaxf(s, kEps);
-  }
-  __syncthreads();
-  float mx = 0.f;
-  for (int k = warp; k < KP; k += 8) {
-    float ss = 0.f;
-    float den = wden[k];
-    for (int b = lane; b < Bp; b += 32) {
-      float wn = 0.f;
-      for (int c = 0; c < nc; c++) wn += part[((int64_t) c * KP + k) * Bp + b];
-      float w = W[(int64_t) k * Bp + b] * wn / den;
-      W[(int64_t) k * Bp + b] = w;
-      ss = fmaf(w, w, ss);
-      mx = fmaxf(mx, w);
-    }
-    for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-    if (lane == 0) inv_norm[k] = ss > 0.f ? 1.0f / sqrtf(ss) : 0.f;
-  }
-  for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-  if (lane == 0) wmax[warp] = mx;
-  __syncthreads();
-  float gmax = wmax[0];
-#pragma unroll
-  for (int i = 1; i < 8; i++) gmax = fmaxf(gmax, wmax[i]);
-  const bool norm = gmax > kEps;
-  for (int k = warp; k < KP; k += 8) {
-    float sc = norm ? inv_norm[k] : 1.0f;
-    float sum = 0.f;
-    for (int b = lane; b < Bp; b += 32) {
-      float w = W[(int64_t) k * Bp + b];
-      if (norm) { w *= sc; W[(int64_t) k * Bp + b] = w; }
-      sum += w;
-    }
-    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    if (lane == 0) d.hden[(int64_t) buf * KP + k] = sum;
-  }
+  w_finalize_body<KP>(d, blockIdx.x);
 }
 
 // Vhat = W H  (NMF.hpp:182 / :88), written dense [batch][F][B] in the caller's dtype
