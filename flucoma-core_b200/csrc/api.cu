@@ -200,10 +200,10 @@ int32_t alloc_partials(Plan* p, NmfDev& d)
   FB_CUDA(p, p->wnum_part.ensure(sizeof(float) * (size_t) d.batch * d.ctas_per_buf * d.KP * d.Bp));
   FB_CUDA(p, p->wden_part.ensure(sizeof(float) * (size_t) d.batch * d.ctas_per_buf * d.KP));
   d.wnum_part = p->wnum_part.as<float>(); d.wden_part = p->wden_part.as<float>();
-  if (p->ticket.cap < sizeof(int) * (size_t) d.batch) { // grows: (re)zero once; the kernels leave it zero
-    FB_CUDA(p, p->ticket.ensure(sizeof(int) * (size_t) d.batch));
-    FB_CUDA(p, cudaMemsetAsync(p->ticket.p, 0, sizeof(int) * (size_t) d.batch, p->stream));
-  }
+  // the kernels leave the tickets at zero; they are cleared once per call anyway (a launch that failed half-way must not
+  // poison the next call)
+  FB_CUDA(p, p->ticket.ensure(sizeof(int) * (size_t) d.batch));
+  FB_CUDA(p, cudaMemsetAsync(p->ticket.p, 0, sizeof(int) * (size_t) d.batch, p->stream));
   d.ticket = p->ticket.as<int>();
   return FB200_OK;
 }
