@@ -207,22 +207,28 @@ __global__ void __launch_bounds__(256, 3) k_stft_fused(const __grid_constant__ C
       __syncthreads();
       float2* sw = in; in = out; out = sw;
     }
-    // ---- real-input split: X[k] = (Z[k] + conj Z[N-k]) / 2 - i e^{-2 pi i k / fft} (Z[k] - conj Z[N-k]) / 2, k = 0 .. NC
+    // ---- real-input split: X[k] = a - i q with a = (Z[k] + conj Z[N-k]) / 2, q = e^{-2 pi i k / fft} (Z[k] - conj Z[N-k]) / 2,
+    //      and from the same pair X[N-k] = conj(a) - i conj(q): k = 0 .. NC / 2 yields all NC + 1 bins
     if (live) {
       const int f = f_tile + fl;
       float* vrow = V ? V + ((int64_t) buf * Fp + f) * Bp : nullptr;
       float2* srow = spec ? spec + ((int64_t) buf * F + f) * (NC + 1) : nullptr;
-      for (int k = t; k <= NC; k += TPF) {
-        const float2 z = in[pad(k & (NC - 1))];
+      for (int k = t; k <= NC / 2; k += TPF) {
+        const float2 z = in[pad(k)];
         float2 zc = in[pad((NC - k) & (NC - 1))];
         zc.y = -zc.y;
         const float2 a = make_float2(0.5f * (z.x + zc.x), 0.5f * (z.y + zc.y));
         const float2 b = make_float2(0.5f * (z.x - zc.x), 0.5f * (z.y - zc.y));
-        const float2 tb = mul_mi(cmul(sp[k], b));
-        float2 X = cadd(a, tb);
-        if (k == 0 || k == NC) X.y = 0.f; // exact by construction up to rounding; FFT.hpp:99-101 leaves them at zero
-        if (srow) srow[k] = X;
-        if (vrow) vrow[k] = sqrtf(fmaf(X.x, X.x, X.y * X.y)); // hypotf's range scaling is not needed for audio magnitudes and cost 9 % of the kernel
+        const float2 q = cmul(sp[k], b);
+        float2 X0 = make_float2(a.x + q.y, a.y - q.x);   // bin k
+        float2 X1 = make_float2(a.x - q.y, -a.y - q.x);  // bin NC - k
+        if (k == 0) { X0.y = 0.f; X1.y = 0.f; } // exact by construction up to rounding; FFT.hpp:99-101 leaves them at zero
+        if (srow) srow[k] = X0;
+        if (vrow) vrow[k] = sqrtf(fmaf(X0.x, X0.x, X0.y * X0.y)); // hypotf's range scaling is not needed for audio magnitudes and cost 9 % of the kernel
+        if (2 * k != NC) {
+          if (srow) srow[NC - k] = X1;
+          if (vrow) vrow[NC - k] = sqrtf(fmaf(X1.x, X1.x, X1.y * X1.y));
+        }
       }
     }
     __syncthreads(); // the buffers are reused by the next round
